@@ -1,0 +1,139 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (run in the build
+container only: /root/reference does not exist on the GPU box).
+
+    PYTHONDONTWRITEBYTECODE=1 OPENBLAS_NUM_THREADS=1 python oracle/make_golden.py
+
+Everything stored is an output of the reference's own functions
+(``ls_spa.ls_spa``, ``square_shapley``, ``reduce_data``) or of the numpy/scipy
+generators its drivers use, on seeded inputs that the tests can regenerate with
+``oracle.samplers_oracle.gen_data``.  Raw data matrices are not stored (size);
+a sha256 of their bytes is, so a test can tell if the regenerated inputs differ.
+"""
+
+from __future__ import annotations
+
+import hashlib
+import itertools
+import os
+import sys
+
+import numpy as np
+
+REF = "/root/reference"
+sys.path.insert(0, REF)
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ls_spa as ref_pkg  # noqa: E402  (the reference package)
+
+ref_mod = sys.modules["ls_spa.ls_spa"]
+from oracle import samplers_oracle as so  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def digest(*arrays):
+    h = hashlib.sha256()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def results_dict(res, prefix=""):
+    d = {
+        prefix + "attribution": res.attribution,
+        prefix + "theta": res.theta,
+        prefix + "overall_error": np.float64(res.overall_error),
+        prefix + "attribution_errors": res.attribution_errors,
+        prefix + "r_squared": np.float64(res.r_squared),
+        prefix + "error_history": res.error_history,
+    }
+    if res.attribution_history is not None:
+        d[prefix + "attribution_history"] = res.attribution_history
+    return d
+
+
+def toy():
+    z = np.load(os.path.join(REF, "data", "toy_data.npz"))
+    Xtr, Xte, ytr, yte = (z[k] for k in ("X_train", "X_test", "y_train", "y_test"))
+    out = {"X_train": Xtr, "X_test": Xte, "y_train": ytr, "y_test": yte}
+    out.update(results_dict(ref_pkg.ls_spa(Xtr, Xte, ytr, yte), "default_"))
+    out.update(results_dict(ref_pkg.ls_spa(Xtr, Xte, ytr, yte, reg=0.1), "reg01_"))
+    out.update(results_dict(ref_pkg.ls_spa(Xtr, Xte, ytr, yte, return_attribution_history=True), "hist_"))
+    R_tr, R_te, c_tr, c_te = ref_mod.reduce_data(Xtr, Xte, ytr, yte, 0.0)
+    ynsq = np.linalg.norm(yte) ** 2
+    perms = np.array(list(itertools.permutations(range(3))))
+    lifts = np.array([ref_mod.square_shapley(R_tr, R_te, c_tr, c_te, ynsq, pm) for pm in perms])
+    out.update(R_tr=R_tr, R_te=R_te, c_tr=c_tr, c_te=c_te, y_norm_sq=ynsq, perms=perms, lifts=lifts)
+    np.savez_compressed(os.path.join(OUT, "toy.npz"), **out)
+    print("toy attribution", out["default_attribution"])
+
+
+def synthetic(tag, p, n, m, reg, k, seed_data=42, seed_perm=42, exact_small=False):
+    rng = np.random.default_rng(seed_data)
+    conditioning = 20.0 if p >= 20 else float(p)        # keep >=1 latent factor at small p
+    Xtr, Xte, ytr, yte, theta_true, _ = so.gen_data(rng, p, n, m, conditioning=conditioning)
+    R_tr, R_te, c_tr, c_te = ref_mod.reduce_data(Xtr, Xte, ytr, yte, reg)
+    ynsq = np.linalg.norm(yte) ** 2
+    out = dict(p=p, n=n, m=m, reg=reg, conditioning=conditioning, seed_data=seed_data,
+               data_sha256=digest(Xtr, Xte, ytr, yte),
+               R_tr=R_tr, R_te=R_te, c_tr=c_tr, c_te=c_te, y_norm_sq=ynsq)
+    methods = {}
+    methods["random"] = so.perms_random(p, k, seed_perm)
+    methods["argsort"] = so.perms_argsort(p, k, seed_perm)[0]
+    methods["permutohedron"] = so.perms_permutohedron(p, k, seed_perm)[0]
+    if exact_small:
+        methods["exact"] = so.perms_exact(p, k, first=0)
+    for name, perms in methods.items():
+        out[f"perms_{name}"] = perms.astype(np.int16)
+        lifts = np.array([ref_mod.square_shapley(R_tr, R_te, c_tr, c_te, ynsq, pm) for pm in perms])
+        out[f"lifts_{name}"] = lifts
+        for anti in (False, True):
+            res = ref_pkg.ls_spa(Xtr, Xte, ytr, yte, reg=reg, perms=list(perms), tolerance=0.0,
+                                 batch_size=max(k // 4, 2), antithetical=anti,
+                                 return_attribution_history=True)
+            out.update(results_dict(res, f"{name}_anti{int(anti)}_"))
+    np.savez_compressed(os.path.join(OUT, f"{tag}.npz"), **out)
+    print(tag, "r2", out["random_anti0_r_squared"], "sum attr", out["random_anti0_attribution"].sum())
+
+
+def exact_p7():
+    """The reference's own exact path (p < 9): all 5040 permutations."""
+    p, n, m = 7, 400, 300
+    rng = np.random.default_rng(7)
+    Xtr, Xte, ytr, yte, _, _ = so.gen_data(rng, p, n, m, conditioning=float(p))
+    res = ref_pkg.ls_spa(Xtr, Xte, ytr, yte, reg=0.05, return_attribution_history=False)
+    R_tr, R_te, c_tr, c_te = ref_mod.reduce_data(Xtr, Xte, ytr, yte, 0.05)
+    out = dict(p=p, n=n, m=m, reg=0.05, conditioning=float(p), seed_data=7,
+               data_sha256=digest(Xtr, Xte, ytr, yte), R_tr=R_tr, R_te=R_te, c_tr=c_tr,
+               c_te=c_te, y_norm_sq=np.linalg.norm(yte) ** 2)
+    out.update(results_dict(res, "default_"))
+    np.savez_compressed(os.path.join(OUT, "exact_p7.npz"), **out)
+    print("exact_p7 attribution", res.attribution)
+
+
+def streams():
+    """Permutation streams alone, for the bit-exactness tests of the device generators."""
+    out = {}
+    for p, k in ((9, 64), (37, 64), (100, 512), (1000, 8)):
+        out[f"random_p{p}_seed42"] = so.perms_random(p, k, 42).astype(np.int16)
+    out["random_p100_seed7"] = so.perms_random(100, 128, 7).astype(np.int16)
+    for p, k, seed in ((10, 256, 42), (100, 1024, 42), (100, 256, 7), (1000, 16, 42)):
+        out[f"argsort_p{p}_seed{seed}"] = so.perms_argsort(p, k, seed)[0].astype(np.int16)
+    for p, k, seed in ((10, 256, 42), (11, 64, 42), (100, 1024, 42), (100, 256, 7), (1000, 16, 42)):
+        out[f"permutohedron_p{p}_seed{seed}"] = so.perms_permutohedron(p, k, seed)[0].astype(np.int16)
+    out["exact_p5"] = so.perms_exact(5).astype(np.int16)
+    out["exact_p10_first"] = so.perms_exact(10, 512).astype(np.int16)
+    out["exact_p10_at_3000000"] = so.perms_exact(10, 512, first=3_000_000).astype(np.int16)
+    np.savez_compressed(os.path.join(OUT, "streams.npz"), **out)
+    print("streams", {k: v.shape for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    toy()
+    exact_p7()
+    synthetic("syn_p10", p=10, n=500, m=400, reg=0.0, k=48, exact_small=True)
+    synthetic("syn_p33", p=33, n=600, m=500, reg=1e-2, k=32)
+    synthetic("syn_p100", p=100, n=1500, m=1200, reg=0.0, k=32)
+    synthetic("syn_p100_reg", p=100, n=1000, m=60, reg=1e-2, k=16, seed_data=5, seed_perm=11)
+    synthetic("syn_p160", p=160, n=900, m=700, reg=1e-3, k=8, seed_data=3, seed_perm=3)
+    streams()
