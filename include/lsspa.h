@@ -1,0 +1,173 @@
+/*
+ * lsspa.h -- C ABI of the B200-native LS-SPA hot path (libls_spa_b200.so).
+ *
+ * The reference (cvxgrp/ls-spa) is pure Python and has no FFI of its own; the
+ * entry points below are the device-side replacements for the NumPy/SciPy/LAPACK
+ * calls on its hot path.  Each one cites the reference lines (paths relative to the
+ * reference checkout) it replaces.  INTEGRATION.md shows the ctypes stub a
+ * maintainer of the reference would add to call them.
+ *
+ * Conventions
+ *   - every function returns an int status: 0 = ok, <0 = LSSPA_E_* below, and
+ *     -(1000 + cudaError_t) when a CUDA call failed (see lsspa_status_string);
+ *   - all data pointers are DEVICE pointers unless the name ends in _host;
+ *   - matrices are row-major float64 unless stated otherwise;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *     nothing synchronises the host -- the caller owns synchronisation;
+ *   - no hidden global state: scratch memory is passed in by the caller and its
+ *     size is obtained from the matching *_workspace_bytes function.
+ */
+#ifndef LSSPA_H_
+#define LSSPA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define LSSPA_API __attribute__((visibility("default")))
+#else
+#define LSSPA_API
+#endif
+
+#define LSSPA_ABI_VERSION 1
+
+#define LSSPA_OK 0
+#define LSSPA_E_BADARG (-1)     /* null pointer / non-positive size / p out of range */
+#define LSSPA_E_WORKSPACE (-2)  /* workspace too small                               */
+#define LSSPA_E_NODEVICE (-3)   /* no CUDA device / wrong architecture               */
+#define LSSPA_E_UNSUPPORTED (-4)
+
+#define LSSPA_ERR_DRAWS 1024 /* ls_spa/ls_spa.py:334  size=2**10 */
+
+LSSPA_API int lsspa_abi_version(void);
+LSSPA_API const char *lsspa_status_string(int status);
+/* number of SMs / bytes of opt-in shared memory of the current device (0 on failure) */
+LSSPA_API int lsspa_device_sm_count(void);
+LSSPA_API int lsspa_device_smem_optin(void);
+
+/* ------------------------------------------------------------------------
+ * 1. Tall-skinny reduction            replaces reduce_data, ls_spa/ls_spa.py:290-318
+ *    (np.linalg.qr of the (N+p) x p train block and the M x p test block, :314-315,
+ *    and the Q^T y products, :316-317).
+ *
+ * lsspa_tsqr_rows:  rows [0,nrows) of [X / divisor | y / divisor] (X row-major with
+ *    leading dimension ldx, p columns) are reduced to `nparts` upper-triangular
+ *    (p+1) x (p+1) factors, one per CTA, written to parts[nparts][slot] where
+ *    slot = lsspa_tsqr_slot_doubles(p); the last 8 doubles of a slot hold the
+ *    CTA's partial sum of (y/divisor)^2 in [0].  nparts = lsspa_tsqr_num_parts().
+ * lsspa_tsqr_merge: stacks `count` factors (same slot layout) in groups of `group`
+ *    and re-triangularises each group: out[ceil(count/group)][slot].  Repeated until
+ *    one factor is left; its leading p x p block is R, its last column holds c
+ *    (and the (p,p) entry the residual norm), out[..][(p+1)^2] the sum of squares.
+ *    The sqrt(reg)*I ridge rows (:310) are one more "factor" in the stack.
+ * ------------------------------------------------------------------------ */
+LSSPA_API int64_t lsspa_tsqr_slot_doubles(int p);
+LSSPA_API int lsspa_tsqr_num_parts(int p, int64_t nrows);
+LSSPA_API int lsspa_tsqr_rows(const double *X, int64_t ldx, const double *y, int64_t nrows, int p,
+                    double divisor, double *parts, int nparts, void *stream);
+LSSPA_API int lsspa_tsqr_merge(const double *parts, int count, int group, int p, double *out,
+                     void *stream);
+
+/* ------------------------------------------------------------------------
+ * 2. Permutation sources (int32 indices, perms_out[count][p])
+ *    exact          itertools.permutations(range(p)), ls_spa/ls_spa.py:171
+ *                   (lexicographic rank first_rank .. first_rank+count-1)
+ *    pcg64          default_rng(seed).permutation(p) repeated, ls_spa/ls_spa.py:168,175
+ *                   (numpy PCG64 XSL-RR + buffered next_uint32 + masked-rejection
+ *                   Fisher-Yates).  `gen_state` is 6 x uint64 on the device:
+ *                   {state_hi, state_lo, inc_hi, inc_lo, has_uint32, uinteger}; it is
+ *                   advanced in place so that calls chain.  status_flag (device int)
+ *                   is set non-zero if the raw-draw budget was exhausted.
+ *    sobol_argsort  np.argsort(Sobol(p, seed).random(n), axis=1),
+ *                   experiments/ground_truth_medium.py:70-71; sv[p][30], shift[p] are
+ *                   scipy's scrambled direction numbers / digital shift (uint32)
+ *    permutohedron  experiments/ground_truth_medium.py:56-67 fed by
+ *                   MultivariateNormalQMC(zeros(p-1), inv_transform=False); sv/shift
+ *                   belong to its Sobol engine of dimension 2*ceil((p-1)/2)
+ * ------------------------------------------------------------------------ */
+LSSPA_API int lsspa_perms_exact(int p, uint64_t first_rank, int64_t count, int32_t *perms_out, void *stream);
+LSSPA_API size_t lsspa_perms_pcg64_workspace_bytes(int p, int64_t count);
+LSSPA_API int lsspa_perms_pcg64(int p, uint64_t *gen_state, int64_t count, int32_t *perms_out,
+                      void *workspace, size_t workspace_bytes, int *status_flag, void *stream);
+LSSPA_API int lsspa_perms_sobol_argsort(int p, const uint32_t *sv, const uint32_t *shift, int bits,
+                              uint64_t first_index, int64_t count, int32_t *perms_out, void *stream);
+LSSPA_API int lsspa_perms_permutohedron(int p, const uint32_t *sv, const uint32_t *shift, int bits,
+                              uint64_t first_index, int64_t count, int32_t *perms_out, void *stream);
+
+/* ------------------------------------------------------------------------
+ * 3. Per-permutation core             replaces square_shapley, ls_spa/ls_spa.py:256-287
+ *    and the antithetic pair average, :205-208.
+ *
+ * R_tr_cm / R_te_cm are the p x p reduced factors stored COLUMN-major (column j
+ * contiguous, leading dimension p), c_tr / c_te the reduced targets (p).  For each of
+ * the `count` permutations the lift vector (p) is written to lifts_out[count][p]; with
+ * antithetical != 0 the row is the mean of the lifts of perm and perm[::-1].
+ * ------------------------------------------------------------------------ */
+LSSPA_API size_t lsspa_lifts_workspace_bytes(int p, int64_t count);
+LSSPA_API int lsspa_lifts(int p, const double *R_tr_cm, const double *c_tr, const double *R_te_cm,
+                const double *c_te, double y_norm_sq, const int32_t *perms, int64_t count,
+                int antithetical, double *lifts_out, void *workspace, size_t workspace_bytes,
+                void *stream);
+
+/* ------------------------------------------------------------------------
+ * 4. Estimator                        replaces ls_spa/ls_spa.py:186-236
+ *    (merge_sample_mean/cov :103-119, error_estimates :321-341, stop test :229).
+ *
+ * State lives in one device buffer of lsspa_estimator_state_bytes(p, max_batches)
+ * bytes, zero-initialised by lsspa_estimator_init.  One lsspa_estimator_update call
+ * consumes `nbatch` consecutive batches of `batch` lift rows each (the last may be
+ * short: total_rows), in order; for every batch it Chan-merges the batch moments into
+ * (count, mean, biased cov), draws LSSPA_ERR_DRAWS Gaussian vectors with covariance
+ * unbiased_cov / count (factor-free: z_s = sum_k g_ks (l_k - mean) / sqrt(n(n-1))),
+ * takes the 0.95 quantiles, appends the overall error to the history and raises the
+ * stop flag when it is < tolerance.  Batches after the stop are ignored, exactly as the
+ * reference's `break`.
+ * With nranks > 1 `partials` holds, per batch, nranks partial moment blocks gathered
+ * from the ranks (layout lsspa_estimator_partial_doubles) and lifts may be NULL.
+ * ------------------------------------------------------------------------ */
+LSSPA_API size_t lsspa_estimator_state_bytes(int p, int max_batches);
+LSSPA_API int64_t lsspa_estimator_partial_doubles(int p);
+LSSPA_API int lsspa_estimator_init(void *state, int p, int max_batches, double tolerance, int estimate_errors,
+                         void *stream);
+/* Partial moments of this rank's rows of each batch.  batch_desc (device, int64[nbatch][3]) =
+ * {first row in `lifts`, row count (may be 0), global index of the first sample}; the global
+ * index keys the counter-based Gaussian stream, so results do not depend on the sharding.
+ * partials[nbatch][partial_doubles] = {n, mean[p], sum (l-mean)(l-mean)^T [p][p],
+ * G[1024] = sum_k g_ks, S[p][1024] = sum_k g_ks (l_k - mean)}. */
+LSSPA_API int lsspa_estimator_partials(int p, const double *lifts, const int64_t *batch_desc, int nbatch,
+                             uint64_t seed, int estimate_errors, double *partials, void *stream);
+/* partials laid out [nranks][nbatch][partial_doubles] (what an all-gather produces) */
+LSSPA_API int lsspa_estimator_update(void *state, int p, int max_batches, const double *partials, int nbatch,
+                           int nranks, int estimate_errors, void *stream);
+/* copies {count, stopped, n_history, overall_error} to 4 doubles, mean[p],
+ * attribution_errors[p], error_history[n_history<=max_batches] (device -> device) */
+LSSPA_API int lsspa_estimator_read(const void *state, int p, int max_batches, double *summary4, double *mean,
+                         double *feat_err, double *err_hist, double *cov_or_null, void *stream);
+/* running means after each sample (attribution_history, :217-219): hist[k] =
+ * (carry_sum + sum_{r<=k} lifts[r]) / (carry_count + k + 1); carry is updated */
+LSSPA_API int lsspa_prefix_means(int p, const double *lifts, int64_t rows, double *carry_sum,
+                       double carry_count, double *hist_out, void *stream);
+/* standalone merge, the device twin of merge_sample_mean / merge_sample_cov */
+LSSPA_API int lsspa_merge_moments(int p, double *mean, double *cov, double old_n, const double *new_mean,
+                        const double *new_cov_or_null, double new_n, void *stream);
+
+/* ------------------------------------------------------------------------
+ * 5. Epilogue                          replaces ls_spa/ls_spa.py:240-243
+ *    theta = np.linalg.lstsq(R_tr, c_tr, rcond=None)[0]: minimum-norm solution through a
+ *    one-sided Jacobi SVD (singular values <= eps * p * sigma_max dropped, as numpy does);
+ *    r_squared = (|c_te|^2 - |c_te - R_te theta|^2) / y_norm_sq
+ *    out[p+1] = {theta[0..p), r_squared}
+ * ------------------------------------------------------------------------ */
+LSSPA_API size_t lsspa_theta_r2_workspace_bytes(int p);
+LSSPA_API int lsspa_theta_r2(int p, const double *R_tr_cm, const double *c_tr, const double *R_te_cm,
+                             const double *c_te, double y_norm_sq, double *out, void *workspace,
+                             size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSSPA_H_ */

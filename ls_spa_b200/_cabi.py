@@ -1,0 +1,79 @@
+"""ctypes binding of libls_spa_b200.so (the C ABI declared in include/lsspa.h).
+
+There is deliberately no fallback: if the library is missing or cannot be loaded
+the import of any compute entry point raises, and on a machine without a CUDA
+device every compute call raises ``LsSpaCudaError``.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libls_spa_b200.so")
+
+c_i32, c_i64, c_u64, c_f64 = C.c_int, C.c_int64, C.c_uint64, C.c_double
+vp, sz = C.c_void_p, C.c_size_t
+
+# name -> (restype, argtypes); must list every symbol include/lsspa.h declares
+SIGNATURES = {
+    "lsspa_abi_version": (c_i32, []),
+    "lsspa_status_string": (C.c_char_p, [c_i32]),
+    "lsspa_device_sm_count": (c_i32, []),
+    "lsspa_device_smem_optin": (c_i32, []),
+    "lsspa_tsqr_slot_doubles": (c_i64, [c_i32]),
+    "lsspa_tsqr_num_parts": (c_i32, [c_i32, c_i64]),
+    "lsspa_tsqr_rows": (c_i32, [vp, c_i64, vp, c_i64, c_i32, c_f64, vp, c_i32, vp]),
+    "lsspa_tsqr_merge": (c_i32, [vp, c_i32, c_i32, c_i32, vp, vp]),
+    "lsspa_perms_exact": (c_i32, [c_i32, c_u64, c_i64, vp, vp]),
+    "lsspa_perms_pcg64_workspace_bytes": (sz, [c_i32, c_i64]),
+    "lsspa_perms_pcg64": (c_i32, [c_i32, vp, c_i64, vp, vp, sz, vp, vp]),
+    "lsspa_perms_sobol_argsort": (c_i32, [c_i32, vp, vp, c_i32, c_u64, c_i64, vp, vp]),
+    "lsspa_perms_permutohedron": (c_i32, [c_i32, vp, vp, c_i32, c_u64, c_i64, vp, vp]),
+    "lsspa_lifts_workspace_bytes": (sz, [c_i32, c_i64]),
+    "lsspa_lifts": (c_i32, [c_i32, vp, vp, vp, vp, c_f64, vp, c_i64, c_i32, vp, vp, sz, vp]),
+    "lsspa_estimator_state_bytes": (sz, [c_i32, c_i32]),
+    "lsspa_estimator_partial_doubles": (c_i64, [c_i32]),
+    "lsspa_estimator_init": (c_i32, [vp, c_i32, c_i32, c_f64, c_i32, vp]),
+    "lsspa_estimator_partials": (c_i32, [c_i32, vp, vp, c_i32, c_u64, c_i32, vp, vp]),
+    "lsspa_estimator_update": (c_i32, [vp, c_i32, c_i32, vp, c_i32, c_i32, c_i32, vp]),
+    "lsspa_estimator_read": (c_i32, [vp, c_i32, c_i32, vp, vp, vp, vp, vp, vp]),
+    "lsspa_prefix_means": (c_i32, [c_i32, vp, c_i64, vp, c_f64, vp, vp]),
+    "lsspa_merge_moments": (c_i32, [c_i32, vp, vp, c_f64, vp, vp, c_f64, vp]),
+    "lsspa_theta_r2_workspace_bytes": (sz, [c_i32]),
+    "lsspa_theta_r2": (c_i32, [c_i32, vp, vp, vp, vp, c_f64, vp, vp, sz, vp]),
+}
+
+
+class LsSpaCudaError(RuntimeError):
+    """A C-ABI call returned a non-zero status, or the CUDA library is unusable."""
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and attach the signatures."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LsSpaCudaError(
+            f"{LIB_PATH} is missing: build it with `python -m ls_spa_b200.build` "
+            "(there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.lsspa_abi_version() != 1:
+        raise LsSpaCudaError("libls_spa_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        msg = load().lsspa_status_string(status).decode()
+        raise LsSpaCudaError(f"{what or 'lsspa call'} failed: {msg} (status {status})")

@@ -1,0 +1,306 @@
+"""Device pipeline of one LS-SPA job: reduce -> (perms -> lifts -> estimator)* -> epilogue.
+
+This is the host-side mirror of the reference's ``ls_spa`` body
+(ls_spa/ls_spa.py:157-253); all arithmetic happens in the CUDA kernels reached
+through ``ops``.  ``backend`` is the only seam: the product uses ``CudaBackend``;
+the CPU unit tests of the sharding / collective logic inject an oracle-backed
+stand-in (tests/test_distributed_cpu.py).
+
+Multi-GPU (one process per GPU, ``torch.distributed``):
+  * rows of the reduction are sharded; the per-rank triangular factors are
+    all-gathered and merged identically on every rank;
+  * every super-batch of sample batches is cut into contiguous runs of batches, one
+    run per rank; the per-batch partial moments are all-gathered and folded into the
+    (replicated) estimator state in batch order, so every rank takes the same stop
+    decision without a broadcast.
+"""
+
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import ops
+from .samplers import PermutationSource
+
+
+@dataclass
+class JobConfig:
+    p: int
+    batch_size: int
+    max_samples: int | None      # None: run the source to exhaustion
+    tolerance: float
+    seed: int
+    antithetical: bool
+    estimate_errors: bool
+    return_history: bool
+    penultimate_check: bool = False   # the reference's extra estimate at i == max_samples - 1 (:222)
+
+
+def split_batches(start: int, count: int, batch_size: int, extra_cut: int | None = None):
+    """Cut samples [start, start+count) at absolute multiples of batch_size (and at
+    `extra_cut`, the reference's i == max_samples-1 quirk).  Returns [(first, n), ...]."""
+    out = []
+    pos, end = start, start + count
+    while pos < end:
+        nxt = min((pos // batch_size + 1) * batch_size, end)
+        if extra_cut is not None and pos < extra_cut < nxt:
+            nxt = extra_cut
+        out.append((pos, nxt - pos))
+        pos = nxt
+    return out
+
+
+def contiguous_runs(nbatch: int, world: int):
+    """Batches [0,nbatch) -> per-rank half-open runs of (almost) equal length."""
+    per = -(-nbatch // world)
+    return [(min(r * per, nbatch), min((r + 1) * per, nbatch)) for r in range(world)], per
+
+
+def target_samples(p: int) -> int:
+    t = int(8192 * (100.0 / max(p, 1)) ** 2)
+    return max(256, min(t, 131072))
+
+
+class Collective:
+    """Thin wrapper over a torch.distributed process group (None = single process)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.active = dist.is_available() and dist.is_initialized() and (
+            group is not None or dist.get_world_size() > 1)
+        self.world = dist.get_world_size(group) if self.active else 1
+        self.rank = dist.get_rank(group) if self.active else 0
+
+    def all_gather(self, t: torch.Tensor) -> torch.Tensor:
+        """(…)-> (world, …), same shape on every rank."""
+        if not self.active:
+            return t.unsqueeze(0)
+        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        self.dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
+        return out
+
+    def all_reduce_sum_int(self, v: int, device) -> int:
+        if not self.active:
+            return v
+        t = torch.tensor([v], dtype=torch.int64, device=device)
+        self.dist.all_reduce(t, group=self.group)
+        return int(t.item())
+
+
+# ---------------------------------------------------------------------------
+# CUDA backend
+# ---------------------------------------------------------------------------
+class CudaBackend:
+    name = "cuda"
+
+    def __init__(self, device=None):
+        self.device = device if device is not None else ops.require_cuda()
+        self.copy_stream = None
+
+    # -- reduction ----------------------------------------------------------
+    def _row_chunks(self, X, y, lo, hi, p):
+        """Yield device (X_chunk, y_chunk) covering rows [lo, hi); host inputs are streamed
+        through two device buffers so the copy of chunk i+1 overlaps the TSQR of chunk i."""
+        if isinstance(X, torch.Tensor) and X.is_cuda:
+            yv = y if (isinstance(y, torch.Tensor) and y.is_cuda) else torch.as_tensor(y).to(self.device)
+            yield X[lo:hi], yv[lo:hi], None
+            return
+        Xh = X if isinstance(X, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(X))
+        yh = y if isinstance(y, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(y))
+        if Xh.dtype != torch.float64:
+            Xh = Xh.to(torch.float64)
+        if yh.dtype != torch.float64:
+            yh = yh.to(torch.float64)
+        rows = hi - lo
+        chunk = max(1, min(rows, (128 << 20) // (8 * (p + 1))))
+        if self.copy_stream is None:
+            self.copy_stream = torch.cuda.Stream(device=self.device)
+        main = torch.cuda.current_stream()
+        bufs = [(torch.empty((chunk, p), dtype=torch.float64, device=self.device),
+                 torch.empty(chunk, dtype=torch.float64, device=self.device)) for _ in range(2)]
+        free_ev = [None, None]
+        for i, r0 in enumerate(range(lo, hi, chunk)):
+            r1 = min(r0 + chunk, hi)
+            bx, by = bufs[i % 2]
+            with torch.cuda.stream(self.copy_stream):
+                if free_ev[i % 2] is not None:
+                    self.copy_stream.wait_event(free_ev[i % 2])
+                bx[: r1 - r0].copy_(Xh[r0:r1], non_blocking=True)
+                by[: r1 - r0].copy_(yh[r0:r1], non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(self.copy_stream)
+            main.wait_event(ready)
+            done = torch.cuda.Event()
+            yield bx[: r1 - r0], by[: r1 - r0], done
+            done.record(main)
+            free_ev[i % 2] = done
+
+    def reduce_rows(self, X, y, lo, hi, p, divisor):
+        """Rows [lo, hi) of [X|y]/divisor -> one triangular factor in slot layout (device)."""
+        parts = []
+        for Xc, yc, _ in self._row_chunks(X, y, lo, hi, p):
+            if Xc.shape[0] > 0:
+                parts.append(ops.tsqr_rows(Xc, yc, divisor))
+        if not parts:
+            return torch.zeros(ops.tsqr_slot(p), dtype=torch.float64, device=self.device)
+        stacked = parts[0] if len(parts) == 1 else torch.cat(parts, 0)
+        return ops.tsqr_merge(stacked, p)
+
+    def merge_factors(self, factors, p):
+        return ops.tsqr_merge(factors, p, group=max(int(factors.shape[0]), 2))
+
+    def ridge(self, p, reg):
+        return ops.ridge_factor(p, reg, self.device)
+
+    def make_problem(self, train_slot, test_slot, p):
+        R_tr, c_tr, _ = ops.split_factor(train_slot, p)
+        R_te, c_te, ysq = ops.split_factor(test_slot, p)
+        return ops.ReducedProblem(R_tr, c_tr, R_te, c_te, float(ysq.item()))
+
+    # -- sample loop --------------------------------------------------------
+    def lifts(self, prob, perms, antithetical):
+        return ops.lifts(prob, perms, antithetical)
+
+    def make_estimator(self, cfg: JobConfig, max_batches):
+        return ops.Estimator(cfg.p, max_batches, cfg.tolerance, cfg.seed, cfg.estimate_errors, self.device)
+
+    def prefix_means(self, rows, carry_sum, carry_count):
+        out = torch.empty_like(rows)
+        ops.prefix_means(rows, carry_sum, carry_count, out)
+        return out
+
+    def theta_r2(self, prob):
+        theta, r2 = ops.theta_r2(prob)
+        return theta.cpu().numpy(), float(r2.item())
+
+    def zeros(self, *shape):
+        return torch.zeros(shape, dtype=torch.float64, device=self.device)
+
+
+# ---------------------------------------------------------------------------
+# the job
+# ---------------------------------------------------------------------------
+def reduce_problem(backend, coll: Collective, X_train, X_test, y_train, y_test, reg, p,
+                   n_train_global=None, row_sharded=False):
+    """Both tall-skinny reductions, row-sharded over the ranks of `coll`.
+
+    With row_sharded=False every rank was handed the full arrays and reduces its own
+    contiguous slice of rows; with row_sharded=True the inputs ARE the local shards."""
+    def local_range(n):
+        if row_sharded or coll.world == 1:
+            return 0, n
+        per = -(-n // coll.world)
+        return min(coll.rank * per, n), min((coll.rank + 1) * per, n)
+
+    n_tr_local = int(X_train.shape[0])
+    if n_train_global is None:
+        n_train_global = (coll.all_reduce_sum_int(n_tr_local, backend.device)
+                          if row_sharded else n_tr_local)
+    lo, hi = local_range(n_tr_local)
+    # train side: rows scaled by 1/sqrt(N) (reference ls_spa/ls_spa.py:309,311)
+    f_tr = backend.reduce_rows(X_train, y_train, lo, hi, p, math.sqrt(n_train_global))
+    lo, hi = local_range(int(X_test.shape[0]))
+    f_te = backend.reduce_rows(X_test, y_test, lo, hi, p, 1.0)       # :315 unscaled
+    g_tr = coll.all_gather(f_tr)
+    g_te = coll.all_gather(f_te)
+    if reg != 0.0:
+        g_tr = torch.cat([g_tr, backend.ridge(p, reg).unsqueeze(0)], 0)    # :310
+    train_slot = backend.merge_factors(g_tr, p) if g_tr.shape[0] > 1 else g_tr[0]
+    test_slot = backend.merge_factors(g_te, p) if g_te.shape[0] > 1 else g_te[0]
+    return backend.make_problem(train_slot, test_slot, p)
+
+
+def run_samples(backend, coll: Collective, prob, source: PermutationSource, cfg: JobConfig):
+    """The estimator loop.  Returns (estimator_read_dict, history or None, samples_done)."""
+    p, W, rank = cfg.p, coll.world, coll.rank
+    bs = cfg.batch_size
+    limit = cfg.max_samples
+    if source.total is not None:
+        limit = source.total if limit is None else min(limit, source.total)
+    tgt = target_samples(p)
+    if not cfg.estimate_errors:
+        bs_eff = tgt                       # batch boundaries are irrelevant without estimates
+    else:
+        bs_eff = bs
+    g_local = max(1, -(-tgt // bs_eff))
+    sb_samples = g_local * W * bs_eff
+    if limit is not None:
+        max_batches = -(-limit // bs_eff) + 2
+    else:
+        max_batches = 1 << 16
+    est = backend.make_estimator(cfg, max_batches)
+    quirk = (cfg.max_samples - 1) if (cfg.penultimate_check and cfg.max_samples and cfg.estimate_errors) else None
+
+    hist_chunks = [] if cfg.return_history else None
+    carry_sum = backend.zeros(p) if cfg.return_history else None
+    pos = 0
+    can_stop = cfg.estimate_errors and cfg.tolerance > 0.0
+    while limit is None or pos < limit:
+        want = sb_samples if limit is None else min(sb_samples, limit - pos)
+        perms_all = None
+        if not source.random_access:
+            perms_all = source.take(want)        # sequential stream: every rank walks it
+            n_sb = int(perms_all.shape[0])
+        else:
+            n_sb = want
+        if n_sb == 0:
+            break
+        batches = split_batches(pos, n_sb, bs_eff, quirk)
+        runs, per = contiguous_runs(len(batches), W)
+        b0, b1 = runs[rank]
+        mine = batches[b0:b1]
+        my_start = mine[0][0] if mine else pos
+        my_count = sum(n for _, n in mine)
+        if perms_all is not None:
+            perms = perms_all[my_start - pos: my_start - pos + my_count]
+        else:
+            source.position = my_start
+            perms = source.take(my_count)
+            source.position = pos + n_sb
+        rows = backend.lifts(prob, perms, cfg.antithetical) if my_count > 0 else backend.zeros(0, p)
+        desc, off = [], 0
+        for first, n in mine:
+            desc.append((off, n, first))
+            off += n
+        part = est.partials(rows, desc)
+        if W > 1:
+            if part.shape[0] < per:
+                pad = torch.zeros((per - part.shape[0], part.shape[1]), dtype=part.dtype, device=part.device)
+                part = torch.cat([part, pad], 0)
+            gathered = coll.all_gather(part)
+            for r, (rb0, rb1) in enumerate(runs):
+                est.update(gathered[r], rb1 - rb0)
+        else:
+            est.update(part, len(mine))
+        if hist_chunks is not None:
+            if W > 1:
+                per_rows = max(sum(n for _, n in batches[a:b]) for a, b in runs)
+                padded = backend.zeros(per_rows, p)
+                padded[:my_count] = rows
+                allrows = coll.all_gather(padded)
+                rows_in_order = torch.cat(
+                    [allrows[r, :sum(n for _, n in batches[a:b])] for r, (a, b) in enumerate(runs)], 0)
+            else:
+                rows_in_order = rows
+            hist_chunks.append(backend.prefix_means(rows_in_order, carry_sum, pos))
+        pos += n_sb
+        if perms_all is not None and n_sb < want:
+            break                                  # explicit stream ran dry
+        if can_stop:
+            _, stopped = est.peek_stop()
+            if stopped:
+                break
+    if hasattr(source, "check"):
+        source.check()
+    res = est.read()
+    history = None
+    if hist_chunks is not None:
+        history = (torch.cat(hist_chunks, 0)[: res["count"]].cpu().numpy()
+                   if hist_chunks else np.zeros((0, p)))
+    return res, history, pos

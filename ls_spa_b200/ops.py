@@ -1,0 +1,271 @@
+"""Tensor-level wrappers of the C ABI (include/lsspa.h).
+
+PyTorch is used for device memory, streams and (in ``dist.py``) process groups
+only; every computation below is one or more launches of the hand-written
+sm_100a kernels in ``ls_spa_b200/csrc``.  All functions require CUDA tensors and
+raise ``LsSpaCudaError`` otherwise -- there is no CPU path.
+"""
+
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import _cabi
+from ._cabi import LsSpaCudaError, check
+
+ERR_DRAWS = 1024
+
+
+def _lib():
+    return _cabi.load()
+
+
+def require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise LsSpaCudaError("ls_spa_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _ptr(t: torch.Tensor | None) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dev_f64(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise LsSpaCudaError(f"{name} must be a CUDA tensor")
+    if t.dtype != torch.float64:
+        t = t.to(torch.float64)
+    return t
+
+
+# ---------------------------------------------------------------------------
+# reduction
+# ---------------------------------------------------------------------------
+def tsqr_slot(p: int) -> int:
+    return int(_lib().lsspa_tsqr_slot_doubles(p))
+
+
+def tsqr_rows(X: torch.Tensor, y: torch.Tensor, divisor: float = 1.0) -> torch.Tensor:
+    """Per-CTA triangular factors of [X | y] / divisor -> (nparts, slot) float64."""
+    X = _dev_f64(X, "X")
+    y = _dev_f64(y, "y").contiguous()
+    if X.dim() != 2 or y.dim() != 1 or X.shape[0] != y.shape[0]:
+        raise LsSpaCudaError("tsqr_rows: X must be (n, p) and y (n,)")
+    if X.stride(1) != 1:
+        X = X.contiguous()
+    n, p = X.shape
+    lib = _lib()
+    nparts = lib.lsspa_tsqr_num_parts(p, n)
+    parts = torch.empty((nparts, tsqr_slot(p)), dtype=torch.float64, device=X.device)
+    check(lib.lsspa_tsqr_rows(X.data_ptr(), X.stride(0), y.data_ptr(), n, p, float(divisor),
+                              parts.data_ptr(), nparts, _stream()), "lsspa_tsqr_rows")
+    return parts
+
+
+def tsqr_merge(parts: torch.Tensor, p: int, group: int = 8) -> torch.Tensor:
+    """Tree-merge stacked triangular factors (count, slot) down to one (slot,) factor."""
+    lib = _lib()
+    parts = parts.contiguous()
+    while True:
+        count = parts.shape[0]
+        nout = (count + group - 1) // group
+        out = torch.empty((nout, parts.shape[1]), dtype=torch.float64, device=parts.device)
+        check(lib.lsspa_tsqr_merge(parts.data_ptr(), count, group, p, out.data_ptr(), _stream()),
+              "lsspa_tsqr_merge")
+        parts = out
+        if nout == 1:
+            return parts[0]
+
+
+def split_factor(slot: torch.Tensor, p: int):
+    """(slot,) -> R (p,p) row-major upper triangular, c (p,), sum of squares of the y column."""
+    q = p + 1
+    T = slot[: q * q].view(q, q)
+    return T[:p, :p], T[:p, p], slot[q * q]
+
+
+def ridge_factor(p: int, reg: float, device) -> torch.Tensor:
+    """The sqrt(reg) * I rows of the train block (reference ls_spa/ls_spa.py:310) as one more
+    triangular factor in slot layout."""
+    q = p + 1
+    slot = torch.zeros(tsqr_slot(p), dtype=torch.float64, device=device)
+    T = slot[: q * q].view(q, q)
+    T.diagonal()[:p] = math.sqrt(reg)
+    return slot
+
+
+# ---------------------------------------------------------------------------
+# permutation sources
+# ---------------------------------------------------------------------------
+def perms_exact(p: int, first_rank: int, count: int, device) -> torch.Tensor:
+    out = torch.empty((count, p), dtype=torch.int32, device=device)
+    check(_lib().lsspa_perms_exact(p, first_rank, count, out.data_ptr(), _stream()), "lsspa_perms_exact")
+    return out
+
+
+def perms_pcg64(p: int, gen_state: torch.Tensor, count: int, status_flag: torch.Tensor) -> torch.Tensor:
+    """gen_state: int64/uint64 CUDA tensor of 6 words, advanced in place."""
+    lib = _lib()
+    out = torch.empty((count, p), dtype=torch.int32, device=gen_state.device)
+    if count == 0:
+        return out
+    nbytes = lib.lsspa_perms_pcg64_workspace_bytes(p, count)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=gen_state.device)
+    check(lib.lsspa_perms_pcg64(p, gen_state.data_ptr(), count, out.data_ptr(), ws.data_ptr(), nbytes,
+                                status_flag.data_ptr(), _stream()), "lsspa_perms_pcg64")
+    return out
+
+
+def perms_sobol_argsort(p, sv, shift, bits, first_index, count) -> torch.Tensor:
+    out = torch.empty((count, p), dtype=torch.int32, device=sv.device)
+    check(_lib().lsspa_perms_sobol_argsort(p, sv.data_ptr(), shift.data_ptr(), bits, first_index, count,
+                                           out.data_ptr(), _stream()), "lsspa_perms_sobol_argsort")
+    return out
+
+
+def perms_permutohedron(p, sv, shift, bits, first_index, count) -> torch.Tensor:
+    out = torch.empty((count, p), dtype=torch.int32, device=sv.device)
+    check(_lib().lsspa_perms_permutohedron(p, sv.data_ptr(), shift.data_ptr(), bits, first_index, count,
+                                           out.data_ptr(), _stream()), "lsspa_perms_permutohedron")
+    return out
+
+
+# ---------------------------------------------------------------------------
+# per-permutation core
+# ---------------------------------------------------------------------------
+class ReducedProblem:
+    """The p x p reduced factors in the layout the lift kernel wants (column-major)."""
+
+    def __init__(self, R_tr, c_tr, R_te, c_te, y_norm_sq: float):
+        dev = R_tr.device
+        self.p = int(R_tr.shape[0])
+        p = self.p
+        R_te = _dev_f64(R_te, "R_te")
+        if R_te.shape[0] < p:  # M < p: the reference keeps an M x p factor; zero rows change nothing
+            pad = torch.zeros((p - R_te.shape[0], p), dtype=torch.float64, device=dev)
+            R_te = torch.cat([R_te, pad], 0)
+            c_te = torch.cat([_dev_f64(c_te, "c_te"), pad[:, 0]], 0)
+        # row-major (p,p) -> column-major storage == contiguous transpose
+        self.R_tr_cm = _dev_f64(R_tr, "R_tr").t().contiguous()
+        self.R_te_cm = R_te.t().contiguous()
+        self.c_tr = _dev_f64(c_tr, "c_tr").contiguous()
+        self.c_te = _dev_f64(c_te, "c_te").contiguous()
+        self.y_norm_sq = float(y_norm_sq)
+        self._ws = None
+
+    def workspace(self, count: int):
+        nbytes = _lib().lsspa_lifts_workspace_bytes(self.p, count)
+        if nbytes == 0:
+            return None, 0
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.c_tr.device)
+        return self._ws, nbytes
+
+
+def lifts(prob: ReducedProblem, perms: torch.Tensor, antithetical: bool, out: torch.Tensor | None = None):
+    """perms (count, p) int32 CUDA -> lift rows (count, p) float64 (pair means if antithetical)."""
+    if not perms.is_cuda or perms.dtype != torch.int32:
+        raise LsSpaCudaError("perms must be an int32 CUDA tensor")
+    perms = perms.contiguous()
+    count, p = perms.shape
+    if p != prob.p:
+        raise LsSpaCudaError("perms width does not match the reduced problem")
+    if out is None:
+        out = torch.empty((count, p), dtype=torch.float64, device=perms.device)
+    ws, nbytes = prob.workspace(count)
+    check(_lib().lsspa_lifts(p, prob.R_tr_cm.data_ptr(), prob.c_tr.data_ptr(), prob.R_te_cm.data_ptr(),
+                             prob.c_te.data_ptr(), prob.y_norm_sq, perms.data_ptr(), count,
+                             1 if antithetical else 0, out.data_ptr(), _ptr(ws), nbytes, _stream()),
+          "lsspa_lifts")
+    return out
+
+
+def theta_r2(prob: ReducedProblem):
+    out = torch.empty(prob.p + 1, dtype=torch.float64, device=prob.c_tr.device)
+    nbytes = _lib().lsspa_theta_r2_workspace_bytes(prob.p)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=prob.c_tr.device)
+    check(_lib().lsspa_theta_r2(prob.p, prob.R_tr_cm.data_ptr(), prob.c_tr.data_ptr(), prob.R_te_cm.data_ptr(),
+                                prob.c_te.data_ptr(), prob.y_norm_sq, out.data_ptr(), ws.data_ptr(), nbytes,
+                                _stream()), "lsspa_theta_r2")
+    return out[: prob.p], out[prob.p]
+
+
+# ---------------------------------------------------------------------------
+# estimator
+# ---------------------------------------------------------------------------
+class Estimator:
+    """Device-resident (count, mean, cov, error-draw sums, stop flag, error history)."""
+
+    def __init__(self, p: int, max_batches: int, tolerance: float, seed: int, estimate_errors: bool, device):
+        lib = _lib()
+        self.p, self.max_batches = p, max(int(max_batches), 1)
+        self.estimate = bool(estimate_errors)
+        self.seed = int(seed) & ((1 << 64) - 1)
+        self.device = device
+        nbytes = lib.lsspa_estimator_state_bytes(p, self.max_batches)
+        self.state = torch.empty(nbytes // 8, dtype=torch.float64, device=device)
+        check(lib.lsspa_estimator_init(self.state.data_ptr(), p, self.max_batches, float(tolerance),
+                                       1 if self.estimate else 0, _stream()), "lsspa_estimator_init")
+        self.partial_doubles = int(lib.lsspa_estimator_partial_doubles(p))
+
+    def partials(self, lift_rows: torch.Tensor, batch_desc) -> torch.Tensor:
+        """batch_desc: list of (first_row, count, global_first_index) -> (nbatch, partial_doubles)."""
+        nb = len(batch_desc)
+        out = torch.empty((nb, self.partial_doubles), dtype=torch.float64, device=self.device)
+        if nb == 0:
+            return out
+        desc = torch.tensor(batch_desc, dtype=torch.int64).reshape(nb, 3).to(self.device, non_blocking=True)
+        check(_lib().lsspa_estimator_partials(self.p, lift_rows.data_ptr(), desc.data_ptr(), nb, self.seed,
+                                              1 if self.estimate else 0, out.data_ptr(), _stream()),
+              "lsspa_estimator_partials")
+        return out
+
+    def update(self, partials: torch.Tensor, nbatch: int, nranks: int = 1) -> None:
+        if nbatch == 0:
+            return
+        check(_lib().lsspa_estimator_update(self.state.data_ptr(), self.p, self.max_batches,
+                                            partials.data_ptr(), nbatch, nranks,
+                                            1 if self.estimate else 0, _stream()), "lsspa_estimator_update")
+
+    def read(self, want_cov: bool = False):
+        """-> dict(count, stopped, n_history, overall_error, mean, attribution_errors, error_history[, cov])
+        (one device->host sync)."""
+        p, H = self.p, self.max_batches
+        buf = torch.empty(4 + 2 * p + H + (p * p if want_cov else 0), dtype=torch.float64, device=self.device)
+        summary, mean, ferr, hist = buf[:4], buf[4:4 + p], buf[4 + p:4 + 2 * p], buf[4 + 2 * p:4 + 2 * p + H]
+        cov = buf[4 + 2 * p + H:] if want_cov else None
+        check(_lib().lsspa_estimator_read(self.state.data_ptr(), p, H, summary.data_ptr(), mean.data_ptr(),
+                                          ferr.data_ptr(), hist.data_ptr(), _ptr(cov), _stream()),
+              "lsspa_estimator_read")
+        host = buf.cpu().numpy()
+        nh = int(host[2])
+        res = dict(count=int(host[0]), stopped=bool(host[1]), n_history=nh, overall_error=float(host[3]),
+                   mean=host[4:4 + p].copy(), attribution_errors=host[4 + p:4 + 2 * p].copy(),
+                   error_history=host[4 + 2 * p:4 + 2 * p + min(nh, H)].copy())
+        if want_cov:
+            res["cov"] = host[4 + 2 * p + H:].reshape(p, p).copy()
+        return res
+
+    def peek_stop(self):
+        """(count, stopped) with one small device->host copy."""
+        h = self.state[:2].cpu()
+        return int(h[0]), bool(h[1])
+
+
+def prefix_means(lift_rows: torch.Tensor, carry_sum: torch.Tensor, carry_count: int, out: torch.Tensor) -> None:
+    rows, p = lift_rows.shape
+    check(_lib().lsspa_prefix_means(p, lift_rows.data_ptr(), rows, carry_sum.data_ptr(), float(carry_count),
+                                    out.data_ptr(), _stream()), "lsspa_prefix_means")
+
+
+def merge_moments(mean, cov, old_n, new_mean, new_cov, new_n) -> None:
+    """In-place device Chan merge of (mean, biased cov); cov / new_cov may be None."""
+    p = mean.numel()
+    check(_lib().lsspa_merge_moments(p, mean.data_ptr(), _ptr(cov), float(old_n), new_mean.data_ptr(),
+                                     _ptr(new_cov), float(new_n), _stream()), "lsspa_merge_moments")

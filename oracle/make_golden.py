@@ -63,6 +63,10 @@ def toy():
     perms = np.array(list(itertools.permutations(range(3))))
     lifts = np.array([ref_mod.square_shapley(R_tr, R_te, c_tr, c_te, ynsq, pm) for pm in perms])
     out.update(R_tr=R_tr, R_te=R_te, c_tr=c_tr, c_te=c_te, y_norm_sq=ynsq, perms=perms, lifts=lifts)
+    out["default_repr"] = np.array(repr(ref_pkg.ls_spa(Xtr, Xte, ytr, yte)))
+    wide = ref_pkg.ShapleyResults(np.arange(7) / 3.0, -np.arange(7) / 7.0, 1.25e-3, np.zeros(7), 0.5,
+                                  np.zeros(0), None)
+    out["wide_repr"] = np.array(repr(wide))
     np.savez_compressed(os.path.join(OUT, "toy.npz"), **out)
     print("toy attribution", out["default_attribution"])
 
