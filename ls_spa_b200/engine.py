@@ -124,6 +124,9 @@ class CudaBackend:
         main = torch.cuda.current_stream()
         bufs = [(torch.empty((chunk, p), dtype=torch.float64, device=self.device),
                  torch.empty(chunk, dtype=torch.float64, device=self.device)) for _ in range(2)]
+        # the staging buffers come from the main stream's allocator pool: whatever used that
+        # memory before (e.g. the previous reduction's kernels) must finish before we copy
+        self.copy_stream.wait_stream(main)
         free_ev = [None, None]
         for i, r0 in enumerate(range(lo, hi, chunk)):
             r1 = min(r0 + chunk, hi)

@@ -6,13 +6,14 @@ container only: /root/reference does not exist on the GPU box).
 Everything stored is an output of the reference's own functions
 (``ls_spa.ls_spa``, ``square_shapley``, ``reduce_data``) or of the numpy/scipy
 generators its drivers use, on seeded inputs that the tests can regenerate with
-``oracle.samplers_oracle.gen_data``.  Raw data matrices are not stored (size);
-a sha256 of their bytes is, so a test can tell if the regenerated inputs differ.
+``oracle.samplers_oracle.gen_data``.  The synthetic inputs are rounded to float32
+before the reference sees them and are stored as float32 (exactly representable), so
+the tests never have to regenerate them: ``multivariate_normal(method="svd")`` goes through
+LAPACK and is not reproducible across CPUs.
 """
 
 from __future__ import annotations
 
-import hashlib
 import itertools
 import os
 import sys
@@ -30,11 +31,9 @@ from oracle import samplers_oracle as so  # noqa: E402
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
 
-def digest(*arrays):
-    h = hashlib.sha256()
-    for a in arrays:
-        h.update(np.ascontiguousarray(a).tobytes())
-    return h.hexdigest()
+def f32_exact(*arrays):
+    """Round to float32 and return float64 arrays holding exactly those values."""
+    return tuple(np.asarray(a, dtype=np.float32).astype(np.float64) for a in arrays)
 
 
 def results_dict(res, prefix=""):
@@ -74,11 +73,12 @@ def toy():
 def synthetic(tag, p, n, m, reg, k, seed_data=42, seed_perm=42, exact_small=False):
     rng = np.random.default_rng(seed_data)
     conditioning = 20.0 if p >= 20 else float(p)        # keep >=1 latent factor at small p
-    Xtr, Xte, ytr, yte, theta_true, _ = so.gen_data(rng, p, n, m, conditioning=conditioning)
+    Xtr, Xte, ytr, yte = f32_exact(*so.gen_data(rng, p, n, m, conditioning=conditioning)[:4])
     R_tr, R_te, c_tr, c_te = ref_mod.reduce_data(Xtr, Xte, ytr, yte, reg)
     ynsq = np.linalg.norm(yte) ** 2
     out = dict(p=p, n=n, m=m, reg=reg, conditioning=conditioning, seed_data=seed_data,
-               data_sha256=digest(Xtr, Xte, ytr, yte),
+               X_train=Xtr.astype(np.float32), X_test=Xte.astype(np.float32),
+               y_train=ytr.astype(np.float32), y_test=yte.astype(np.float32),
                R_tr=R_tr, R_te=R_te, c_tr=c_tr, c_te=c_te, y_norm_sq=ynsq)
     methods = {}
     methods["random"] = so.perms_random(p, k, seed_perm)
@@ -103,12 +103,13 @@ def exact_p7():
     """The reference's own exact path (p < 9): all 5040 permutations."""
     p, n, m = 7, 400, 300
     rng = np.random.default_rng(7)
-    Xtr, Xte, ytr, yte, _, _ = so.gen_data(rng, p, n, m, conditioning=float(p))
+    Xtr, Xte, ytr, yte = f32_exact(*so.gen_data(rng, p, n, m, conditioning=float(p))[:4])
     res = ref_pkg.ls_spa(Xtr, Xte, ytr, yte, reg=0.05, return_attribution_history=False)
     R_tr, R_te, c_tr, c_te = ref_mod.reduce_data(Xtr, Xte, ytr, yte, 0.05)
     out = dict(p=p, n=n, m=m, reg=0.05, conditioning=float(p), seed_data=7,
-               data_sha256=digest(Xtr, Xte, ytr, yte), R_tr=R_tr, R_te=R_te, c_tr=c_tr,
-               c_te=c_te, y_norm_sq=np.linalg.norm(yte) ** 2)
+               X_train=Xtr.astype(np.float32), X_test=Xte.astype(np.float32),
+               y_train=ytr.astype(np.float32), y_test=yte.astype(np.float32),
+               R_tr=R_tr, R_te=R_te, c_tr=c_tr, c_te=c_te, y_norm_sq=np.linalg.norm(yte) ** 2)
     out.update(results_dict(res, "default_"))
     np.savez_compressed(os.path.join(OUT, "exact_p7.npz"), **out)
     print("exact_p7 attribution", res.attribution)
@@ -137,7 +138,7 @@ if __name__ == "__main__":
     exact_p7()
     synthetic("syn_p10", p=10, n=500, m=400, reg=0.0, k=48, exact_small=True)
     synthetic("syn_p33", p=33, n=600, m=500, reg=1e-2, k=32)
-    synthetic("syn_p100", p=100, n=1500, m=1200, reg=0.0, k=32)
-    synthetic("syn_p100_reg", p=100, n=1000, m=60, reg=1e-2, k=16, seed_data=5, seed_perm=11)
-    synthetic("syn_p160", p=160, n=900, m=700, reg=1e-3, k=8, seed_data=3, seed_perm=3)
+    synthetic("syn_p100", p=100, n=700, m=500, reg=0.0, k=32)
+    synthetic("syn_p100_reg", p=100, n=600, m=60, reg=1e-2, k=16, seed_data=5, seed_perm=11)
+    synthetic("syn_p160", p=160, n=500, m=300, reg=1e-3, k=8, seed_data=3, seed_perm=3)
     streams()
