@@ -81,9 +81,10 @@ class Collective:
         """(…)-> (world, …), same shape on every rank."""
         if not self.active:
             return t.unsqueeze(0)
-        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
-        self.dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
-        return out
+        flat = t.contiguous().reshape(-1)
+        out = torch.empty(self.world * flat.numel(), dtype=t.dtype, device=t.device)
+        self.dist.all_gather_into_tensor(out, flat, group=self.group)
+        return out.view((self.world,) + tuple(t.shape))
 
     def all_reduce_sum_int(self, v: int, device) -> int:
         if not self.active:

@@ -17,6 +17,16 @@ from ._cabi import LsSpaCudaError, check
 
 ERR_DRAWS = 1024
 
+# number of kernels of libls_spa_b200.so launched through this module (bench.py reports it)
+LAUNCHES = 0
+# when set to a list, every lifts() call appends (start_event, end_event, permutations)
+LIFT_TRACE = None
+
+
+def _count(n: int) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
 
 def _lib():
     return _cabi.load()
@@ -65,6 +75,7 @@ def tsqr_rows(X: torch.Tensor, y: torch.Tensor, divisor: float = 1.0) -> torch.T
     parts = torch.empty((nparts, tsqr_slot(p)), dtype=torch.float64, device=X.device)
     check(lib.lsspa_tsqr_rows(X.data_ptr(), X.stride(0), y.data_ptr(), n, p, float(divisor),
                               parts.data_ptr(), nparts, _stream()), "lsspa_tsqr_rows")
+    _count(1)
     return parts
 
 
@@ -78,6 +89,7 @@ def tsqr_merge(parts: torch.Tensor, p: int, group: int = 8) -> torch.Tensor:
         out = torch.empty((nout, parts.shape[1]), dtype=torch.float64, device=parts.device)
         check(lib.lsspa_tsqr_merge(parts.data_ptr(), count, group, p, out.data_ptr(), _stream()),
               "lsspa_tsqr_merge")
+        _count(1)
         parts = out
         if nout == 1:
             return parts[0]
@@ -106,6 +118,7 @@ def ridge_factor(p: int, reg: float, device) -> torch.Tensor:
 def perms_exact(p: int, first_rank: int, count: int, device) -> torch.Tensor:
     out = torch.empty((count, p), dtype=torch.int32, device=device)
     check(_lib().lsspa_perms_exact(p, first_rank, count, out.data_ptr(), _stream()), "lsspa_perms_exact")
+    _count(1)
     return out
 
 
@@ -119,6 +132,7 @@ def perms_pcg64(p: int, gen_state: torch.Tensor, count: int, status_flag: torch.
     ws = torch.empty(nbytes, dtype=torch.uint8, device=gen_state.device)
     check(lib.lsspa_perms_pcg64(p, gen_state.data_ptr(), count, out.data_ptr(), ws.data_ptr(), nbytes,
                                 status_flag.data_ptr(), _stream()), "lsspa_perms_pcg64")
+    _count(3)
     return out
 
 
@@ -126,6 +140,7 @@ def perms_sobol_argsort(p, sv, shift, bits, first_index, count) -> torch.Tensor:
     out = torch.empty((count, p), dtype=torch.int32, device=sv.device)
     check(_lib().lsspa_perms_sobol_argsort(p, sv.data_ptr(), shift.data_ptr(), bits, first_index, count,
                                            out.data_ptr(), _stream()), "lsspa_perms_sobol_argsort")
+    _count(1)
     return out
 
 
@@ -133,6 +148,7 @@ def perms_permutohedron(p, sv, shift, bits, first_index, count) -> torch.Tensor:
     out = torch.empty((count, p), dtype=torch.int32, device=sv.device)
     check(_lib().lsspa_perms_permutohedron(p, sv.data_ptr(), shift.data_ptr(), bits, first_index, count,
                                            out.data_ptr(), _stream()), "lsspa_perms_permutohedron")
+    _count(1)
     return out
 
 
@@ -179,10 +195,18 @@ def lifts(prob: ReducedProblem, perms: torch.Tensor, antithetical: bool, out: to
     if out is None:
         out = torch.empty((count, p), dtype=torch.float64, device=perms.device)
     ws, nbytes = prob.workspace(count)
+    trace = LIFT_TRACE
+    if trace is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     check(_lib().lsspa_lifts(p, prob.R_tr_cm.data_ptr(), prob.c_tr.data_ptr(), prob.R_te_cm.data_ptr(),
                              prob.c_te.data_ptr(), prob.y_norm_sq, perms.data_ptr(), count,
                              1 if antithetical else 0, out.data_ptr(), _ptr(ws), nbytes, _stream()),
           "lsspa_lifts")
+    _count(1)
+    if trace is not None:
+        e1.record()
+        trace.append((e0, e1, count * (2 if antithetical else 1)))
     return out
 
 
@@ -193,6 +217,7 @@ def theta_r2(prob: ReducedProblem):
     check(_lib().lsspa_theta_r2(prob.p, prob.R_tr_cm.data_ptr(), prob.c_tr.data_ptr(), prob.R_te_cm.data_ptr(),
                                 prob.c_te.data_ptr(), prob.y_norm_sq, out.data_ptr(), ws.data_ptr(), nbytes,
                                 _stream()), "lsspa_theta_r2")
+    _count(1)
     return out[: prob.p], out[prob.p]
 
 
@@ -212,6 +237,7 @@ class Estimator:
         self.state = torch.empty(nbytes // 8, dtype=torch.float64, device=device)
         check(lib.lsspa_estimator_init(self.state.data_ptr(), p, self.max_batches, float(tolerance),
                                        1 if self.estimate else 0, _stream()), "lsspa_estimator_init")
+        _count(1)
         self.partial_doubles = int(lib.lsspa_estimator_partial_doubles(p))
 
     def partials(self, lift_rows: torch.Tensor, batch_desc) -> torch.Tensor:
@@ -224,6 +250,7 @@ class Estimator:
         check(_lib().lsspa_estimator_partials(self.p, lift_rows.data_ptr(), desc.data_ptr(), nb, self.seed,
                                               1 if self.estimate else 0, out.data_ptr(), _stream()),
               "lsspa_estimator_partials")
+        _count(3 if self.estimate else 2)
         return out
 
     def update(self, partials: torch.Tensor, nbatch: int, nranks: int = 1) -> None:
@@ -232,6 +259,7 @@ class Estimator:
         check(_lib().lsspa_estimator_update(self.state.data_ptr(), self.p, self.max_batches,
                                             partials.data_ptr(), nbatch, nranks,
                                             1 if self.estimate else 0, _stream()), "lsspa_estimator_update")
+        _count(2 * nbatch)
 
     def read(self, want_cov: bool = False):
         """-> dict(count, stopped, n_history, overall_error, mean, attribution_errors, error_history[, cov])
@@ -243,6 +271,7 @@ class Estimator:
         check(_lib().lsspa_estimator_read(self.state.data_ptr(), p, H, summary.data_ptr(), mean.data_ptr(),
                                           ferr.data_ptr(), hist.data_ptr(), _ptr(cov), _stream()),
               "lsspa_estimator_read")
+        _count(1)
         host = buf.cpu().numpy()
         nh = int(host[2])
         res = dict(count=int(host[0]), stopped=bool(host[1]), n_history=nh, overall_error=float(host[3]),
@@ -262,6 +291,7 @@ def prefix_means(lift_rows: torch.Tensor, carry_sum: torch.Tensor, carry_count: 
     rows, p = lift_rows.shape
     check(_lib().lsspa_prefix_means(p, lift_rows.data_ptr(), rows, carry_sum.data_ptr(), float(carry_count),
                                     out.data_ptr(), _stream()), "lsspa_prefix_means")
+    _count(1)
 
 
 def merge_moments(mean, cov, old_n, new_mean, new_cov, new_n) -> None:
@@ -269,3 +299,4 @@ def merge_moments(mean, cov, old_n, new_mean, new_cov, new_n) -> None:
     p = mean.numel()
     check(_lib().lsspa_merge_moments(p, mean.data_ptr(), _ptr(cov), float(old_n), new_mean.data_ptr(),
                                      _ptr(new_cov), float(new_n), _stream()), "lsspa_merge_moments")
+    _count(2 if cov is not None else 1)

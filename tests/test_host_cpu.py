@@ -1,0 +1,109 @@
+"""CPU: host-side logic and the C-ABI surface (no compute calls; there is no GPU here)."""
+
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from ls_spa_b200 import _cabi
+    header = open(os.path.join(ROOT, "include", "lsspa.h")).read()
+    declared = set(re.findall(r"LSSPA_API[^;(]*?\b(lsspa_\w+)\s*\(", header))
+    assert len(declared) >= 25
+    assert declared == set(_cabi.SIGNATURES), declared ^ set(_cabi.SIGNATURES)
+    lib = ctypes.CDLL(_cabi.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _cabi.load().lsspa_abi_version() == 1
+    assert b"bad argument" in _cabi.load().lsspa_status_string(-1)
+    # pure size queries work without a device
+    assert _cabi.load().lsspa_tsqr_slot_doubles(100) == 101 * 101 + 8
+    assert _cabi.load().lsspa_estimator_partial_doubles(3) == 8 + 3 + 9 + 1024 + 3 * 1024
+
+
+def test_no_cpu_fallback():
+    import torch
+    import ls_spa_b200 as L
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    x = np.random.default_rng(0).standard_normal((20, 3))
+    with pytest.raises(L.LsSpaCudaError):
+        L.ls_spa(x, x, x[:, 0], x[:, 0])
+    with pytest.raises(L.LsSpaCudaError):
+        L.merge_sample_mean(np.zeros(3), np.ones(3), 1, 1)
+
+
+def test_validation_happens_before_any_device_work():
+    import ls_spa_b200 as L
+    with pytest.raises(L.SizeIncompatible) as e:
+        L.ls_spa(np.zeros((5, 3)), np.zeros((5, 4)), np.zeros(5), np.zeros(5))
+    assert "same number of columns" in e.value.message
+    with pytest.raises(L.SizeIncompatible):
+        L.ls_spa(np.zeros((5, 3)), np.zeros((5, 3)), np.zeros(4), np.zeros(5))
+    with pytest.raises(L.SizeIncompatible):
+        L.ls_spa(np.zeros((5, 3)), np.zeros((5, 3)), np.zeros(5), np.zeros(6))
+    with pytest.raises(L.SizeIncompatible):
+        L.ls_spa(np.zeros((2, 3)), np.zeros((5, 3)), np.zeros(2), np.zeros(5))
+    with pytest.raises(TypeError):
+        L.ls_spa(np.zeros((5, 3)), np.zeros((5, 3)), np.zeros(5), np.zeros(5), max_samples=4, num_batches=2)
+    with pytest.raises(ValueError):
+        L.ls_spa(np.zeros((5, 3)), np.zeros((5, 3)), np.zeros(5), np.zeros(5), method="sobol")
+    with pytest.raises(TypeError):
+        L.ls_spa(np.zeros((5, 3)), np.zeros((5, 3)), np.zeros(5), np.zeros(5), return_history=True,
+                 return_attribution_history=True)
+
+
+def test_exported_names_match_reference_package():
+    import ls_spa_b200 as L
+    for name in ("ls_spa", "ShapleyResults", "SizeIncompatible", "validate_data", "merge_sample_mean",
+                 "merge_sample_cov", "square_shapley", "reduce_data", "error_estimates"):
+        assert hasattr(L, name), name
+    import dataclasses
+    assert [f.name for f in dataclasses.fields(L.ShapleyResults)] == [
+        "attribution", "theta", "overall_error", "attribution_errors", "r_squared", "error_history",
+        "attribution_history"]
+
+
+def test_repr_matches_reference_dashboard():
+    import ls_spa_b200 as L
+    from conftest import load_golden
+    g = load_golden("toy")
+    r = L.ShapleyResults(g["default_attribution"], g["default_theta"], 0.0, np.zeros(3),
+                         float(g["default_r_squared"]), np.zeros(0), None)
+    assert repr(r) == str(g["default_repr"])
+    w = L.ShapleyResults(np.arange(7) / 3.0, -np.arange(7) / 7.0, 1.25e-3, np.zeros(7), 0.5, np.zeros(0), None)
+    assert repr(w) == str(g["wide_repr"])
+
+
+def test_split_batches_and_runs():
+    from ls_spa_b200.engine import contiguous_runs, split_batches, target_samples
+    assert split_batches(0, 10, 4) == [(0, 4), (4, 4), (8, 2)]
+    assert split_batches(6, 10, 4) == [(6, 2), (8, 4), (12, 4)]
+    # the reference's extra estimate at i == max_samples - 1 (ls_spa/ls_spa.py:222)
+    assert split_batches(0, 4, 2, extra_cut=3) == [(0, 2), (2, 1), (3, 1)]
+    assert split_batches(0, 2048, 256, extra_cut=2047)[-2:] == [(1792, 255), (2047, 1)]
+    assert len(split_batches(0, 2048, 256, extra_cut=2047)) == 9
+    runs, per = contiguous_runs(10, 4)
+    assert per == 3 and runs == [(0, 3), (3, 6), (6, 9), (9, 10)]
+    runs, per = contiguous_runs(2, 4)
+    assert runs == [(0, 1), (1, 2), (2, 2), (2, 2)]
+    assert target_samples(100) == 8192 and target_samples(1000) == 256 and target_samples(3) == 131072
+
+
+def test_explicit_source_on_cpu_tensors():
+    import torch
+    from ls_spa_b200.samplers import ExplicitSource
+    perms = [np.random.default_rng(i).permutation(6) for i in range(7)]
+    src = ExplicitSource(6, iter(perms), torch.device("cpu"))
+    assert src.total is None
+    a = src.take(4)
+    b = src.take(4)
+    assert a.shape == (4, 6) and b.shape == (3, 6) and src.total == 7 and src.exhausted
+    assert np.array_equal(torch.cat([a, b]).numpy(), np.array(perms))
+    src = ExplicitSource(6, np.array(perms), torch.device("cpu"))
+    assert src.total == 7 and src.take(100).shape == (7, 6)
