@@ -49,4 +49,10 @@ struct DeviceInfo {
 // cached per process (device of the first call); 0 on failure
 const DeviceInfo &device_info();
 
+// DMMA lift kernel (lifts_mma.cu), used by lsspa_lifts for 9 <= p <= 128
+bool lifts_mma_supported(int p);
+int lifts_mma_launch(int p, const double *R_tr_cm, const double *c_tr, const double *R_te_cm, const double *c_te,
+                     double y_norm_sq, const int32_t *perms, int64_t count, int antithetical, double *lifts_out,
+                     cudaStream_t st);
+
 }  // namespace lsspa

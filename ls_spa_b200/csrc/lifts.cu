@@ -24,6 +24,8 @@
 
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace lsspa {
 
 struct LiftParams {
@@ -232,9 +234,18 @@ static int lifts_threads(int p) {
 
 using namespace lsspa;
 
+// LSSPA_LIFTS_IMPL=v1 forces the scalar kernel of this file (debugging / A-B timing)
+static bool use_mma(int p) {
+  static const bool forced_v1 = [] {
+    const char *e = getenv("LSSPA_LIFTS_IMPL");
+    return e && e[0] == 'v' && e[1] == '1';
+  }();
+  return !forced_v1 && lifts_mma_supported(p);
+}
+
 extern "C" size_t lsspa_lifts_workspace_bytes(int p, int64_t count) {
   if (p < 1 || count < 1) return 0;
-  if (tiles_fit_smem(p)) return 0;
+  if (use_mma(p) || tiles_fit_smem(p)) return 0;
   return (size_t)lifts_grid(p, count) * 2 * (size_t)(p + 1) * padded_ld(p) * sizeof(double);
 }
 
@@ -246,6 +257,9 @@ extern "C" int lsspa_lifts(int p, const double *R_tr_cm, const double *c_tr, con
     return LSSPA_E_BADARG;
   if (count == 0) return LSSPA_OK;
   if (count < 0) return LSSPA_E_BADARG;
+  if (use_mma(p))
+    return lifts_mma_launch(p, R_tr_cm, c_tr, R_te_cm, c_te, y_norm_sq, perms, count, antithetical, lifts_out,
+                            as_stream(stream));
   LiftParams a;
   a.p = p;
   a.ld = padded_ld(p);

@@ -1,0 +1,485 @@
+// Per-permutation core of LS-SPA, tensor-pipe version (mma.sync m8n8k4 f64 = DMMA on sm_100a;
+// tcgen05 has no fp64, so this is the tensor path the FP64 pipe offers).
+//
+// Replaces square_shapley (reference ls_spa/ls_spa.py:256-287) and the antithetic pair average
+// (:205-208) for 9 <= p <= 128.  Same mathematics as lifts.cu, reorganised so that almost all
+// flops are 8x8x4 matrix products and the number of block-wide barriers drops from 2p to 2p/8:
+//
+//  phase 1  blocked Householder QR of A = [R_tr[:, perm] | c_tr] (shared memory, column-major,
+//           ld % 16 == 8).  Per panel of 8 columns: warp 0 factors the panel in registers
+//           (reflectors V, compact-WY factor T from G = V^T V), then every warp takes whole
+//           trailing column tiles:  W^T = (A2^T V) T  and  A2^T -= W^T V^T, all DMMA.
+//  phase 2  elimination of X = R_te[:, perm] against the rows of R, one warp per 8-row tile of
+//           X held entirely in registers (rows of X are independent):  M_J = X_J R_JJ^-1,
+//           X_L -= M_J R_JL.  The multipliers M are the columns of W = X R^-1 (reference :279),
+//           so the prefix residuals / costs (:282-283) come from a running residual per row.
+//
+// Fragment conventions (lane = 4c + q):  A[m=c][k=q], B[k=q][n=c], C[m=c][n=2q+e].
+// "tile access": lane touches the 16 bytes M[i0+2q .. i0+2q+1][j0+c] of a column-major matrix;
+// with ld % 16 == 8 the 32 lanes hit 512 distinct bytes in 4 conflict-free wavefronts.  Such a
+// fragment is at once the B operand of the tile, the A operand of its transpose and the C
+// operand of its transpose (k index <-> row 2q+e in both k-steps), and a C result is reused as
+// the A operand of the next product without leaving the registers.
+// The lane-level Python model of this file is tests/lifts_v2_model.py.
+
+#include "common.cuh"
+
+namespace lsspa {
+
+struct LiftParams2 {
+  int p;
+  int ld;       // leading dimension of A and Vb (>= 8*RT, ld % 16 == 8)
+  int rt;       // row tiles      ceil(p / 8)
+  int pt;       // column tiles   ceil((p + 1) / 8)
+  const double *Rtr;  // column-major p x p
+  const double *ctr;
+  const double *Rte;  // column-major p x p
+  const double *cte;
+  double inv_ynsq;
+  const int32_t *perms;
+  int64_t count;
+  int anti;
+  double *out;
+};
+
+__device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(d0), "+d"(d1)
+      : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ double2 ld_tile(const double *M, int ld, int i0, int j0, int c, int q) {
+  return *reinterpret_cast<const double2 *>(M + (size_t)(j0 + c) * ld + i0 + 2 * q);
+}
+__device__ __forceinline__ void st_tile(double *M, int ld, int i0, int j0, int c, int q, double2 v) {
+  *reinterpret_cast<double2 *>(M + (size_t)(j0 + c) * ld + i0 + 2 * q) = v;
+}
+
+// ---------------------------------------------------------------- panel factorisation (warp 0)
+template <int MAXT>
+__device__ __forceinline__ void panel_factor(double *A, double *Vb, double *Vt, double *Tb, double *Gs,
+                                             int ld, int p, int RT, int s, int lane) {
+  const int c = lane >> 2, q = lane & 3;
+  const int j0 = 8 * s;
+  const int nf = (p - j0 < 8) ? p - j0 : 8;
+  double vr[MAXT][2];
+#pragma unroll
+  for (int t = 0; t < MAXT; ++t) {
+    vr[t][0] = 0.0;
+    vr[t][1] = 0.0;
+    if (t >= s && t < RT) {
+      const double2 v = ld_tile(A, ld, 8 * t, j0, c, q);
+      vr[t][0] = v.x;
+      vr[t][1] = v.y;
+    }
+  }
+  double tau_r[8];
+  double dg = 0.0;  // diagonal entry (beta) of this lane's column
+#pragma unroll
+  for (int cc = 0; cc < 8; ++cc) {
+    tau_r[cc] = 0.0;
+    const bool own = (c == cc);
+    if (cc < nf) {
+      // |column cc below the pivot|^2 and the pivot itself
+      double part = 0.0, pv = 0.0;
+#pragma unroll
+      for (int t = 0; t < MAXT; ++t) {
+        if (t >= s && t < RT) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const bool below = (t > s) || (2 * q + e > cc);
+            if (below) part = fma(vr[t][e], vr[t][e], part);
+          }
+          if (t == s) pv = (cc & 1) ? vr[t][1] : vr[t][0];
+        }
+      }
+      part = quad_sum(part);
+      const double sig = __shfl_sync(kFull, part, 4 * cc);
+      const double x0 = __shfl_sync(kFull, pv, 4 * cc + (cc >> 1));
+      double tau = 0.0, scale = 0.0, beta = x0;
+      if (sig != 0.0) {
+        const double nrm = sqrt(fma(x0, x0, sig));
+        beta = (x0 >= 0.0) ? -nrm : nrm;
+        tau = (beta - x0) / beta;
+        scale = 1.0 / (x0 - beta);
+      }
+      tau_r[cc] = tau;
+      if (own) {
+        dg = beta;
+#pragma unroll
+        for (int t = 0; t < MAXT; ++t) {
+          if (t >= s && t < RT) {
+            double2 v;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int lr = 2 * q + e;
+              const bool below = (t > s) || (lr > cc);
+              if (below) vr[t][e] *= scale;
+              const double val = below ? vr[t][e] : ((lr == cc) ? 1.0 : 0.0);
+              if (e == 0) v.x = val; else v.y = val;
+              Vt[(size_t)(8 * t + lr) * 8 + cc] = val;
+            }
+            *reinterpret_cast<double2 *>(Vb + (size_t)cc * ld + 8 * t + 2 * q) = v;
+          }
+        }
+      }
+      __syncwarp();
+      // apply H_cc to the later columns of the panel tile
+      double w = 0.0;
+#pragma unroll
+      for (int t = 0; t < MAXT; ++t) {
+        if (t >= s && t < RT) {
+          const double2 vv = *reinterpret_cast<const double2 *>(Vb + (size_t)cc * ld + 8 * t + 2 * q);
+          w = fma(vv.x, vr[t][0], w);
+          w = fma(vv.y, vr[t][1], w);
+        }
+      }
+      w = quad_sum(w) * tau;
+      if (c > cc) {
+#pragma unroll
+        for (int t = 0; t < MAXT; ++t) {
+          if (t >= s && t < RT) {
+            const double2 vv = *reinterpret_cast<const double2 *>(Vb + (size_t)cc * ld + 8 * t + 2 * q);
+            vr[t][0] = fma(-w, vv.x, vr[t][0]);
+            vr[t][1] = fma(-w, vv.y, vr[t][1]);
+          }
+        }
+      }
+    } else if (own) {
+      // no reflector for this column (beyond the last feature): V column = 0
+#pragma unroll
+      for (int t = 0; t < MAXT; ++t) {
+        if (t >= s && t < RT) {
+          *reinterpret_cast<double2 *>(Vb + (size_t)cc * ld + 8 * t + 2 * q) = make_double2(0.0, 0.0);
+          Vt[(size_t)(8 * t + 2 * q) * 8 + cc] = 0.0;
+          Vt[(size_t)(8 * t + 2 * q + 1) * 8 + cc] = 0.0;
+        }
+      }
+    }
+  }
+  // write the strip back: R entries of the top tile, zeros below it for factored columns,
+  // the updated values for the columns without a reflector (c >= nf, e.g. the c_tr column)
+#pragma unroll
+  for (int t = 0; t < MAXT; ++t) {
+    if (t >= s && t < RT) {
+      double2 v = make_double2(vr[t][0], vr[t][1]);
+      if (c < nf) {
+        if (t == s) {
+          const int l0 = 2 * q, l1 = 2 * q + 1;
+          v.x = (l0 < c) ? vr[t][0] : ((l0 == c) ? dg : 0.0);
+          v.y = (l1 < c) ? vr[t][1] : ((l1 == c) ? dg : 0.0);
+        } else {
+          v = make_double2(0.0, 0.0);
+        }
+      }
+      st_tile(A, ld, 8 * t, j0, c, q, v);
+    }
+  }
+  __syncwarp();
+  // G = V^T V: the same fragment is the A operand (V^T) and the B operand (V)
+  double ga0 = 0.0, ga1 = 0.0, gb0 = 0.0, gb1 = 0.0;
+#pragma unroll
+  for (int t = 0; t < MAXT; ++t) {
+    if (t >= s && t < RT) {
+      const double2 v = ld_tile(Vb, ld, 8 * t, 0, c, q);
+      if (t & 1) {
+        dmma(gb0, gb1, v.x, v.x);
+        dmma(gb0, gb1, v.y, v.y);
+      } else {
+        dmma(ga0, ga1, v.x, v.x);
+        dmma(ga0, ga1, v.y, v.y);
+      }
+    }
+  }
+  *reinterpret_cast<double2 *>(Gs + c * 8 + 2 * q) = make_double2(ga0 + gb0, ga1 + gb1);  // Gs[m][n] row-major
+  __syncwarp();
+  // T (dlarft, forward / columnwise): lane u owns row u; stored column-major for ld_tile
+  if (lane < 8) {
+    const int u = lane;
+    double tr[8];
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) {
+      double val = 0.0;
+      if (cc == u) {
+        val = tau_r[cc];
+      } else if (cc > u) {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (k >= u && k < cc) acc = fma(tr[k], Gs[k * 8 + cc], acc);
+        val = -tau_r[cc] * acc;
+      }
+      tr[cc] = val;
+      Tb[cc * 8 + u] = val;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- trailing column tile j
+__device__ __forceinline__ void trailing_tile(double *A, const double *Vb, const double *Vt, const double *Tb,
+                                              int ld, int RT, int s, int j, int lane) {
+  const int c = lane >> 2, q = lane & 3;
+  double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+  int t = s;
+  for (; t + 1 < RT; t += 2) {
+    const double2 x = ld_tile(A, ld, 8 * t, 8 * j, c, q);
+    const double2 v = ld_tile(Vb, ld, 8 * t, 0, c, q);
+    const double2 x2 = ld_tile(A, ld, 8 * t + 8, 8 * j, c, q);
+    const double2 v2 = ld_tile(Vb, ld, 8 * t + 8, 0, c, q);
+    dmma(a0, a1, x.x, v.x);
+    dmma(b0, b1, x2.x, v2.x);
+    dmma(a0, a1, x.y, v.y);
+    dmma(b0, b1, x2.y, v2.y);
+  }
+  if (t < RT) {
+    const double2 x = ld_tile(A, ld, 8 * t, 8 * j, c, q);
+    const double2 v = ld_tile(Vb, ld, 8 * t, 0, c, q);
+    dmma(a0, a1, x.x, v.x);
+    dmma(a0, a1, x.y, v.y);
+  }
+  a0 += b0;  // C layout of Wraw^T: lane (m = column of the tile, n = reflector 2q+e)
+  a1 += b1;
+  const double2 tt = ld_tile(Tb, 8, 0, 0, c, q);
+  double w0 = 0.0, w1 = 0.0;  // W'^T = Wraw^T T
+  dmma(w0, w1, a0, tt.x);
+  dmma(w0, w1, a1, tt.y);
+  w0 = -w0;
+  w1 = -w1;
+  for (t = s; t < RT; ++t) {
+    double2 cf = ld_tile(A, ld, 8 * t, 8 * j, c, q);
+    const double2 vt = *reinterpret_cast<const double2 *>(Vt + (size_t)(8 * t + c) * 8 + 2 * q);
+    dmma(cf.x, cf.y, w0, vt.x);
+    dmma(cf.x, cf.y, w1, vt.y);
+    st_tile(A, ld, 8 * t, 8 * j, c, q, cf);
+  }
+}
+
+// ---------------------------------------------------------------- kernel
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(256, MINB) lifts_mma_kernel(LiftParams2 a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int p = a.p, ld = a.ld, RT = a.rt, PT = a.pt;
+  const int NR = 8 * RT, NC = 8 * PT;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c = lane >> 2, q = lane & 3;
+
+  double *A = reinterpret_cast<double *>(smem_raw);
+  double *Vb = A + (size_t)NC * ld;      // 8 x ld          (phase 2: Dbuf, RT x 64)
+  double *Vt = Vb + (size_t)8 * ld;      // NR x 8          (phase 2: per-warp cost partials, 8 x NR)
+  double *Tb = Vt + (size_t)NR * 8;      // 64
+  double *Gs = Tb + 64;                  // 64
+  double *cost = Gs + 64;                // p + 1
+  double *acc = cost + (p + 2);          // p
+  int *perm_s = reinterpret_cast<int *>(acc + p + (p & 1));
+  double *Dbuf = Vb;
+  double *wcost = Vt;
+
+  const int halves = a.anti ? 2 : 1;
+  const double weight = a.anti ? 0.5 : 1.0;
+
+  for (int64_t sidx = blockIdx.x; sidx < a.count; sidx += gridDim.x) {
+    for (int h = 0; h < halves; ++h) {
+      __syncthreads();
+      for (int k = tid; k < p; k += 256) perm_s[k] = a.perms[sidx * p + (h == 0 ? k : p - 1 - k)];
+      __syncthreads();
+      // ---- phase 0: gather A = [R_tr[:, perm] | c_tr], zero padding
+      for (int e = tid; e < NC * (NR / 2); e += 256) {
+        const int k = e / (NR / 2), i = 2 * (e - k * (NR / 2));
+        double2 v = make_double2(0.0, 0.0);
+        if (k < p) {
+          const int col = perm_s[k];
+          const double *src = a.Rtr + (size_t)col * p;
+          if (i <= col) v.x = src[i];
+          if (i + 1 <= col) v.y = src[i + 1];
+        } else if (k == p) {
+          if (i < p) v.x = a.ctr[i];
+          if (i + 1 < p) v.y = a.ctr[i + 1];
+        }
+        *reinterpret_cast<double2 *>(A + (size_t)k * ld + i) = v;
+      }
+      if (warp == 7) {
+        double s0 = 0.0;
+        for (int i = lane; i < p; i += 32) s0 = fma(a.cte[i], a.cte[i], s0);
+        s0 = warp_sum(s0);
+        if (lane == 0) cost[0] = s0;
+      }
+      __syncthreads();
+
+      // ---- phase 1: blocked Householder
+      for (int s = 0; s < RT; ++s) {
+        if (warp == 0) panel_factor<MAXT>(A, Vb, Vt, Tb, Gs, ld, p, RT, s, lane);
+        __syncthreads();
+        for (int j = s + 1 + warp; j < PT; j += 8) trailing_tile(A, Vb, Vt, Tb, ld, RT, s, j, lane);
+        __syncthreads();
+      }
+
+      // ---- phase 1.5: inverses of the 8x8 diagonal blocks of R (column-major 8x8 each), zero the
+      //      per-warp cost partials (they overlay Vt)
+      if (tid < RT * 8) {
+        const int J = tid >> 3, jj = tid & 7;
+        double x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) x[u] = 0.0;
+        if (8 * J + jj < p) {
+          const double *D = A + (size_t)(8 * J) * ld + 8 * J;  // D[u][k] = D[k * ld + u]
+#pragma unroll
+          for (int u = 7; u >= 0; --u) {
+            if (u == jj) {
+              x[u] = 1.0 / D[(size_t)u * ld + u];
+            } else if (u < jj) {
+              double sacc = 0.0;
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                if (k > u && k <= jj) sacc = fma(D[(size_t)k * ld + u], x[k], sacc);
+              x[u] = -sacc / D[(size_t)u * ld + u];
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) Dbuf[J * 64 + jj * 8 + u] = x[u];
+      }
+      for (int e = tid; e < 8 * NR; e += 256) wcost[e] = 0.0;
+      __syncthreads();
+
+      // ---- phase 2: X = R_te[:, perm] eliminated against R, one warp per 8-row tile, registers only
+      double *wc = wcost + (size_t)warp * NR;
+      const double *cvec = A + (size_t)p * ld;
+      for (int it = warp; it < RT; it += 8) {
+        const int row = 8 * it + c;  // C layout: lane (m = row, n = columns 2q+e)
+        double xr[MAXT][2];
+#pragma unroll
+        for (int L = 0; L < MAXT; ++L) {
+          xr[L][0] = 0.0;
+          xr[L][1] = 0.0;
+          if (L < RT) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int l = 8 * L + 2 * q + e;
+              if (l < p) {
+                const int col = perm_s[l];
+                if (row <= col) xr[L][e] = a.Rte[(size_t)col * p + row];
+              }
+            }
+          }
+        }
+        double r_in = (row < p) ? a.cte[row] : 0.0;
+#pragma unroll
+        for (int J = 0; J < MAXT; ++J) {
+          if (J < RT) {
+            const double2 dv = ld_tile(Dbuf + J * 64, 8, 0, 0, c, q);
+            double m0 = 0.0, m1 = 0.0;  // M_J = X_J R_JJ^-1, C layout (row, column 2q+e of the panel)
+            dmma(m0, m1, xr[J][0], dv.x);
+            dmma(m0, m1, xr[J][1], dv.y);
+            // running test residual of this row after each of the 8 columns of the panel
+            const double2 cv = *reinterpret_cast<const double2 *>(cvec + 8 * J + 2 * q);
+            const double t0 = m0 * cv.x, t1 = m1 * cv.y;
+            const double sl = t0 + t1;
+            double P = sl;
+            double up = __shfl_up_sync(kFull, P, 1, 4);
+            if (q >= 1) P += up;
+            up = __shfl_up_sync(kFull, P, 2, 4);
+            if (q >= 2) P += up;
+            const double ra = r_in - (P - sl) - t0;
+            const double rb = r_in - P;
+            double d0 = ra * ra, d1 = rb * rb;
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+              d0 += __shfl_xor_sync(kFull, d0, o);
+              d1 += __shfl_xor_sync(kFull, d1, o);
+            }
+            if (c == 0) {
+              const int k0 = 8 * J + 2 * q;
+              if (k0 < p) wc[k0] += d0;          // wc[k] collects cost_{k+1}
+              if (k0 + 1 < p) wc[k0 + 1] += d1;
+            }
+            r_in -= __shfl_sync(kFull, P, 3, 4);
+            m0 = -m0;
+            m1 = -m1;
+#pragma unroll
+            for (int L = 0; L < MAXT; ++L) {
+              if (L > J && L < RT) {
+                const double2 rt = ld_tile(A, ld, 8 * J, 8 * L, c, q);
+                dmma(xr[L][0], xr[L][1], m0, rt.x);
+                dmma(xr[L][0], xr[L][1], m1, rt.y);
+              }
+            }
+          }
+        }
+      }
+      __syncthreads();
+      for (int k = tid; k < p; k += 256) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sacc += wcost[(size_t)w * NR + k];
+        cost[k + 1] = sacc;
+      }
+      __syncthreads();
+      for (int k = tid; k < p; k += 256) {
+        const double lift = (cost[k] - cost[k + 1]) * a.inv_ynsq;
+        const int f = perm_s[k];
+        acc[f] = (h == 0 ? 0.0 : acc[f]) + weight * lift;
+      }
+    }
+    __syncthreads();
+    for (int f = tid; f < p; f += 256) a.out[sidx * p + f] = acc[f];
+  }
+}
+
+static int mma_ld(int rt) {
+  int n = 8 * rt;
+  return (n % 16 == 8) ? n : n + 8;
+}
+
+static size_t mma_smem_bytes(int p) {
+  const int rt = (p + 7) / 8, pt = (p + 8) / 8;
+  const int ld = mma_ld(rt);
+  size_t d = (size_t)8 * pt * ld + (size_t)8 * ld + (size_t)8 * rt * 8 + 128 + (size_t)(p + 2) + (size_t)(p + 1);
+  return d * sizeof(double) + (size_t)p * sizeof(int) + 32;
+}
+
+template <int MAXT, int MINB>
+static int launch_mma(const LiftParams2 &a, int grid, size_t smem, cudaStream_t st) {
+  LSSPA_CUDA_TRY(cudaFuncSetAttribute(lifts_mma_kernel<MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+  LSSPA_CUDA_TRY(cudaFuncSetAttribute(lifts_mma_kernel<MAXT, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared));
+  lifts_mma_kernel<MAXT, MINB><<<grid, 256, smem, st>>>(a);
+  LSSPA_LAUNCH_CHECK();
+  return LSSPA_OK;
+}
+
+// below ~48 features the scalar kernel (many small CTAs per SM) is faster (profiles/r01_quick_bench_v2.log)
+bool lifts_mma_supported(int p) { return p >= 49 && p <= 128; }
+
+int lifts_mma_launch(int p, const double *R_tr_cm, const double *c_tr, const double *R_te_cm, const double *c_te,
+                     double y_norm_sq, const int32_t *perms, int64_t count, int antithetical, double *lifts_out,
+                     cudaStream_t st) {
+  LiftParams2 a;
+  a.p = p;
+  a.rt = (p + 7) / 8;
+  a.pt = (p + 8) / 8;
+  a.ld = mma_ld(a.rt);
+  a.Rtr = R_tr_cm;
+  a.ctr = c_tr;
+  a.Rte = R_te_cm;
+  a.cte = c_te;
+  a.inv_ynsq = 1.0 / y_norm_sq;
+  a.perms = perms;
+  a.count = count;
+  a.anti = antithetical ? 1 : 0;
+  a.out = lifts_out;
+  const size_t smem = mma_smem_bytes(p);
+  const DeviceInfo &d = device_info();
+  const int sms = d.sm_count > 0 ? d.sm_count : 148;
+  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 8) per_sm = 8;
+  int64_t grid = (int64_t)per_sm * sms;
+  if (grid > count) grid = count;
+  if (a.rt <= 4) return launch_mma<4, 3>(a, (int)grid, smem, st);
+  if (a.rt <= 8) return launch_mma<8, 2>(a, (int)grid, smem, st);
+  if (a.rt <= 13) return launch_mma<13, 2>(a, (int)grid, smem, st);
+  return launch_mma<16, 1>(a, (int)grid, smem, st);
+}
+
+}  // namespace lsspa
