@@ -55,22 +55,36 @@ __device__ __forceinline__ void st_tile(double *M, int ld, int i0, int j0, int c
   *reinterpret_cast<double2 *>(M + (size_t)(j0 + c) * ld + i0 + 2 * q) = v;
 }
 
-// ---------------------------------------------------------------- panel factorisation (warp 0)
+constexpr int kVS = 10;  // row stride (doubles) of the row-major V buffers: rows 2q hit banks 8q
+
+// V fragment for the tile access pattern (rows 2q+e of the tile, column c): B operand of V /
+// A operand of V^T.  Two 8-byte loads, conflict-free with kVS = 10.
+__device__ __forceinline__ double2 ld_vfrag(const double *V, int r0, int c, int q) {
+  const double *ptr = V + (size_t)(r0 + 2 * q) * kVS + c;
+  return make_double2(ptr[0], ptr[kVS]);
+}
+
+// ---------------------------------------------------------------- panel factorisation (one warp)
+// Strip = column tile s, row tiles s..RT-1, held in registers relative to the top tile
+// (vr[k] = tile s+k).  Writes R (top tile) back to A, V (unit lower trapezoid, explicit ones and
+// zeros) row-major into V[row][0..7], and the compact-WY factor T (column-major 8x8) into Tb.
 template <int MAXT>
-__device__ __forceinline__ void panel_factor(double *A, double *Vb, double *Vt, double *Tb, double *Gs,
-                                             int ld, int p, int RT, int s, int lane) {
+__device__ __forceinline__ void panel_factor(double *A, double *V, double *Tb, double *Gs, int ld, int p,
+                                             int RT, int s, int lane) {
   const int c = lane >> 2, q = lane & 3;
   const int j0 = 8 * s;
   const int nf = (p - j0 < 8) ? p - j0 : 8;
+  const int nt = RT - s;  // tiles in the strip
+  const int r0 = 8 * s;
   double vr[MAXT][2];
 #pragma unroll
-  for (int t = 0; t < MAXT; ++t) {
-    vr[t][0] = 0.0;
-    vr[t][1] = 0.0;
-    if (t >= s && t < RT) {
-      const double2 v = ld_tile(A, ld, 8 * t, j0, c, q);
-      vr[t][0] = v.x;
-      vr[t][1] = v.y;
+  for (int k = 0; k < MAXT; ++k) {
+    vr[k][0] = 0.0;
+    vr[k][1] = 0.0;
+    if (k < nt) {
+      const double2 v = ld_tile(A, ld, r0 + 8 * k, j0, c, q);
+      vr[k][0] = v.x;
+      vr[k][1] = v.y;
     }
   }
   double tau_r[8];
@@ -80,20 +94,19 @@ __device__ __forceinline__ void panel_factor(double *A, double *Vb, double *Vt, 
     tau_r[cc] = 0.0;
     const bool own = (c == cc);
     if (cc < nf) {
-      // |column cc below the pivot|^2 and the pivot itself
-      double part = 0.0, pv = 0.0;
+      // |column cc below the pivot|^2 (rows of the top tile above / on the pivot excluded)
+      double pa = 0.0, pb = 0.0;
+      if (2 * q > cc) pa = vr[0][0] * vr[0][0];
+      if (2 * q + 1 > cc) pb = vr[0][1] * vr[0][1];
 #pragma unroll
-      for (int t = 0; t < MAXT; ++t) {
-        if (t >= s && t < RT) {
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const bool below = (t > s) || (2 * q + e > cc);
-            if (below) part = fma(vr[t][e], vr[t][e], part);
-          }
-          if (t == s) pv = (cc & 1) ? vr[t][1] : vr[t][0];
+      for (int k = 1; k < MAXT; ++k) {
+        if (k < nt) {
+          pa = fma(vr[k][0], vr[k][0], pa);
+          pb = fma(vr[k][1], vr[k][1], pb);
         }
       }
-      part = quad_sum(part);
+      const double part = quad_sum(pa + pb);
+      const double pv = (cc & 1) ? vr[0][1] : vr[0][0];
       const double sig = __shfl_sync(kFull, part, 4 * cc);
       const double x0 = __shfl_sync(kFull, pv, 4 * cc + (cc >> 1));
       double tau = 0.0, scale = 0.0, beta = x0;
@@ -106,83 +119,83 @@ __device__ __forceinline__ void panel_factor(double *A, double *Vb, double *Vt, 
       tau_r[cc] = tau;
       if (own) {
         dg = beta;
+        // top tile: zeros above the pivot, one on it, scaled entries below
+        {
+          const int l0 = 2 * q, l1 = 2 * q + 1;
+          if (l0 > cc) vr[0][0] *= scale;
+          if (l1 > cc) vr[0][1] *= scale;
+          V[(size_t)(r0 + l0) * kVS + cc] = (l0 > cc) ? vr[0][0] : ((l0 == cc) ? 1.0 : 0.0);
+          V[(size_t)(r0 + l1) * kVS + cc] = (l1 > cc) ? vr[0][1] : ((l1 == cc) ? 1.0 : 0.0);
+        }
 #pragma unroll
-        for (int t = 0; t < MAXT; ++t) {
-          if (t >= s && t < RT) {
-            double2 v;
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int lr = 2 * q + e;
-              const bool below = (t > s) || (lr > cc);
-              if (below) vr[t][e] *= scale;
-              const double val = below ? vr[t][e] : ((lr == cc) ? 1.0 : 0.0);
-              if (e == 0) v.x = val; else v.y = val;
-              Vt[(size_t)(8 * t + lr) * 8 + cc] = val;
-            }
-            *reinterpret_cast<double2 *>(Vb + (size_t)cc * ld + 8 * t + 2 * q) = v;
+        for (int k = 1; k < MAXT; ++k) {
+          if (k < nt) {
+            vr[k][0] *= scale;
+            vr[k][1] *= scale;
+            V[(size_t)(r0 + 8 * k + 2 * q) * kVS + cc] = vr[k][0];
+            V[(size_t)(r0 + 8 * k + 2 * q + 1) * kVS + cc] = vr[k][1];
           }
         }
       }
       __syncwarp();
-      // apply H_cc to the later columns of the panel tile
-      double w = 0.0;
+      // apply H_cc to the later columns of the panel tile: w = tau * v^T a, a -= w v
+      double wa = 0.0, wb = 0.0;
 #pragma unroll
-      for (int t = 0; t < MAXT; ++t) {
-        if (t >= s && t < RT) {
-          const double2 vv = *reinterpret_cast<const double2 *>(Vb + (size_t)cc * ld + 8 * t + 2 * q);
-          w = fma(vv.x, vr[t][0], w);
-          w = fma(vv.y, vr[t][1], w);
+      for (int k = 0; k < MAXT; ++k) {
+        if (k < nt) {
+          const double *vp = V + (size_t)(r0 + 8 * k + 2 * q) * kVS + cc;
+          wa = fma(vp[0], vr[k][0], wa);
+          wb = fma(vp[kVS], vr[k][1], wb);
         }
       }
-      w = quad_sum(w) * tau;
+      const double w = quad_sum(wa + wb) * tau;
       if (c > cc) {
 #pragma unroll
-        for (int t = 0; t < MAXT; ++t) {
-          if (t >= s && t < RT) {
-            const double2 vv = *reinterpret_cast<const double2 *>(Vb + (size_t)cc * ld + 8 * t + 2 * q);
-            vr[t][0] = fma(-w, vv.x, vr[t][0]);
-            vr[t][1] = fma(-w, vv.y, vr[t][1]);
+        for (int k = 0; k < MAXT; ++k) {
+          if (k < nt) {
+            const double *vp = V + (size_t)(r0 + 8 * k + 2 * q) * kVS + cc;
+            vr[k][0] = fma(-w, vp[0], vr[k][0]);
+            vr[k][1] = fma(-w, vp[kVS], vr[k][1]);
           }
         }
       }
     } else if (own) {
       // no reflector for this column (beyond the last feature): V column = 0
 #pragma unroll
-      for (int t = 0; t < MAXT; ++t) {
-        if (t >= s && t < RT) {
-          *reinterpret_cast<double2 *>(Vb + (size_t)cc * ld + 8 * t + 2 * q) = make_double2(0.0, 0.0);
-          Vt[(size_t)(8 * t + 2 * q) * 8 + cc] = 0.0;
-          Vt[(size_t)(8 * t + 2 * q + 1) * 8 + cc] = 0.0;
+      for (int k = 0; k < MAXT; ++k) {
+        if (k < nt) {
+          V[(size_t)(r0 + 8 * k + 2 * q) * kVS + cc] = 0.0;
+          V[(size_t)(r0 + 8 * k + 2 * q + 1) * kVS + cc] = 0.0;
         }
       }
     }
   }
   // write the strip back: R entries of the top tile, zeros below it for factored columns,
   // the updated values for the columns without a reflector (c >= nf, e.g. the c_tr column)
+  {
+    double2 v = make_double2(vr[0][0], vr[0][1]);
+    if (c < nf) {
+      const int l0 = 2 * q, l1 = 2 * q + 1;
+      v.x = (l0 < c) ? vr[0][0] : ((l0 == c) ? dg : 0.0);
+      v.y = (l1 < c) ? vr[0][1] : ((l1 == c) ? dg : 0.0);
+    }
+    st_tile(A, ld, r0, j0, c, q, v);
+  }
 #pragma unroll
-  for (int t = 0; t < MAXT; ++t) {
-    if (t >= s && t < RT) {
-      double2 v = make_double2(vr[t][0], vr[t][1]);
-      if (c < nf) {
-        if (t == s) {
-          const int l0 = 2 * q, l1 = 2 * q + 1;
-          v.x = (l0 < c) ? vr[t][0] : ((l0 == c) ? dg : 0.0);
-          v.y = (l1 < c) ? vr[t][1] : ((l1 == c) ? dg : 0.0);
-        } else {
-          v = make_double2(0.0, 0.0);
-        }
-      }
-      st_tile(A, ld, 8 * t, j0, c, q, v);
+  for (int k = 1; k < MAXT; ++k) {
+    if (k < nt) {
+      const double2 v = (c < nf) ? make_double2(0.0, 0.0) : make_double2(vr[k][0], vr[k][1]);
+      st_tile(A, ld, r0 + 8 * k, j0, c, q, v);
     }
   }
   __syncwarp();
   // G = V^T V: the same fragment is the A operand (V^T) and the B operand (V)
   double ga0 = 0.0, ga1 = 0.0, gb0 = 0.0, gb1 = 0.0;
 #pragma unroll
-  for (int t = 0; t < MAXT; ++t) {
-    if (t >= s && t < RT) {
-      const double2 v = ld_tile(Vb, ld, 8 * t, 0, c, q);
-      if (t & 1) {
+  for (int k = 0; k < MAXT; ++k) {
+    if (k < nt) {
+      const double2 v = ld_vfrag(V, r0 + 8 * k, c, q);
+      if (k & 1) {
         dmma(gb0, gb1, v.x, v.x);
         dmma(gb0, gb1, v.y, v.y);
       } else {
@@ -213,19 +226,21 @@ __device__ __forceinline__ void panel_factor(double *A, double *Vb, double *Vt, 
       Tb[cc * 8 + u] = val;
     }
   }
+  __syncwarp();
 }
 
 // ---------------------------------------------------------------- trailing column tile j
-__device__ __forceinline__ void trailing_tile(double *A, const double *Vb, const double *Vt, const double *Tb,
-                                              int ld, int RT, int s, int j, int lane) {
+// A2[:, tile j] -= V T^T (V^T A2[:, tile j]) for the reflectors of panel s
+__device__ __forceinline__ void trailing_tile(double *A, const double *V, const double *Tb, int ld, int RT,
+                                              int s, int j, int lane) {
   const int c = lane >> 2, q = lane & 3;
   double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
   int t = s;
   for (; t + 1 < RT; t += 2) {
     const double2 x = ld_tile(A, ld, 8 * t, 8 * j, c, q);
-    const double2 v = ld_tile(Vb, ld, 8 * t, 0, c, q);
+    const double2 v = ld_vfrag(V, 8 * t, c, q);
     const double2 x2 = ld_tile(A, ld, 8 * t + 8, 8 * j, c, q);
-    const double2 v2 = ld_tile(Vb, ld, 8 * t + 8, 0, c, q);
+    const double2 v2 = ld_vfrag(V, 8 * t + 8, c, q);
     dmma(a0, a1, x.x, v.x);
     dmma(b0, b1, x2.x, v2.x);
     dmma(a0, a1, x.y, v.y);
@@ -233,7 +248,7 @@ __device__ __forceinline__ void trailing_tile(double *A, const double *Vb, const
   }
   if (t < RT) {
     const double2 x = ld_tile(A, ld, 8 * t, 8 * j, c, q);
-    const double2 v = ld_tile(Vb, ld, 8 * t, 0, c, q);
+    const double2 v = ld_vfrag(V, 8 * t, c, q);
     dmma(a0, a1, x.x, v.x);
     dmma(a0, a1, x.y, v.y);
   }
@@ -247,7 +262,8 @@ __device__ __forceinline__ void trailing_tile(double *A, const double *Vb, const
   w1 = -w1;
   for (t = s; t < RT; ++t) {
     double2 cf = ld_tile(A, ld, 8 * t, 8 * j, c, q);
-    const double2 vt = *reinterpret_cast<const double2 *>(Vt + (size_t)(8 * t + c) * 8 + 2 * q);
+    // B[k <-> reflector 2q+e][n = row c] = V[row][2q+e]: 16 contiguous bytes of a V row
+    const double2 vt = *reinterpret_cast<const double2 *>(V + (size_t)(8 * t + c) * kVS + 2 * q);
     dmma(cf.x, cf.y, w0, vt.x);
     dmma(cf.x, cf.y, w1, vt.y);
     st_tile(A, ld, 8 * t, 8 * j, c, q, cf);
@@ -264,15 +280,15 @@ __global__ void __launch_bounds__(256, MINB) lifts_mma_kernel(LiftParams2 a) {
   const int c = lane >> 2, q = lane & 3;
 
   double *A = reinterpret_cast<double *>(smem_raw);
-  double *Vb = A + (size_t)NC * ld;      // 8 x ld          (phase 2: Dbuf, RT x 64)
-  double *Vt = Vb + (size_t)8 * ld;      // NR x 8          (phase 2: per-warp cost partials, 8 x NR)
-  double *Tb = Vt + (size_t)NR * 8;      // 64
-  double *Gs = Tb + 64;                  // 64
-  double *cost = Gs + 64;                // p + 1
-  double *acc = cost + (p + 2);          // p
+  double *V0 = A + (size_t)NC * ld;        // NR x kVS, double-buffered   (phase 2: Dbuf, RT x 64)
+  double *V1 = V0 + (size_t)NR * kVS;      //                             (phase 2: cost partials, 8 x NR)
+  double *Tb = V1 + (size_t)NR * kVS;      // 2 x 64
+  double *Gs = Tb + 128;                   // 64
+  double *cost = Gs + 64;                  // p + 1
+  double *acc = cost + (p + 2);            // p
   int *perm_s = reinterpret_cast<int *>(acc + p + (p & 1));
-  double *Dbuf = Vb;
-  double *wcost = Vt;
+  double *Dbuf = V0;
+  double *wcost = V1;
 
   const int halves = a.anti ? 2 : 1;
   const double weight = a.anti ? 0.5 : 1.0;
@@ -305,16 +321,30 @@ __global__ void __launch_bounds__(256, MINB) lifts_mma_kernel(LiftParams2 a) {
       }
       __syncthreads();
 
-      // ---- phase 1: blocked Householder
+      // ---- phase 1: blocked Householder with one panel of look-ahead.  In step s warp 0 first
+      // brings column tile s+1 up to date and factors it (into the other V/T buffer) while
+      // warps 1..7 apply panel s to the remaining tiles: one barrier per panel.
+      if (warp == 0) panel_factor<MAXT>(A, V0, Tb, Gs, ld, p, RT, 0, lane);
+      __syncthreads();
       for (int s = 0; s < RT; ++s) {
-        if (warp == 0) panel_factor<MAXT>(A, Vb, Vt, Tb, Gs, ld, p, RT, s, lane);
-        __syncthreads();
-        for (int j = s + 1 + warp; j < PT; j += 8) trailing_tile(A, Vb, Vt, Tb, ld, RT, s, j, lane);
+        const double *Vc = (s & 1) ? V1 : V0;
+        double *Vn = (s & 1) ? V0 : V1;
+        const double *Tc = Tb + 64 * (s & 1);
+        double *Tn = Tb + 64 * ((s + 1) & 1);
+        if (warp == 0) {
+          if (s + 1 < PT) trailing_tile(A, Vc, Tc, ld, RT, s, s + 1, lane);
+          if (s + 1 < RT) {
+            __syncwarp();
+            panel_factor<MAXT>(A, Vn, Tn, Gs, ld, p, RT, s + 1, lane);
+          }
+        } else {
+          for (int j = s + 2 + (warp - 1); j < PT; j += 7) trailing_tile(A, Vc, Tc, ld, RT, s, j, lane);
+        }
         __syncthreads();
       }
 
       // ---- phase 1.5: inverses of the 8x8 diagonal blocks of R (column-major 8x8 each), zero the
-      //      per-warp cost partials (they overlay Vt)
+      //      per-warp cost partials (both overlay the V buffers)
       if (tid < RT * 8) {
         const int J = tid >> 3, jj = tid & 7;
         double x[8];
@@ -433,7 +463,7 @@ static int mma_ld(int rt) {
 static size_t mma_smem_bytes(int p) {
   const int rt = (p + 7) / 8, pt = (p + 8) / 8;
   const int ld = mma_ld(rt);
-  size_t d = (size_t)8 * pt * ld + (size_t)8 * ld + (size_t)8 * rt * 8 + 128 + (size_t)(p + 2) + (size_t)(p + 1);
+  size_t d = (size_t)8 * pt * ld + 2 * (size_t)8 * rt * 10 + 192 + (size_t)(p + 2) + (size_t)(p + 1);
   return d * sizeof(double) + (size_t)p * sizeof(int) + 32;
 }
 
