@@ -66,17 +66,22 @@ __device__ __forceinline__ double2 ld_vfrag(const double *V, int r0, int c, int 
 
 // ---------------------------------------------------------------- panel factorisation (one warp)
 // Strip = column tile s, row tiles s..RT-1, held in registers relative to the top tile
-// (vr[k] = tile s+k).  Writes R (top tile) back to A, V (unit lower trapezoid, explicit ones and
-// zeros) row-major into V[row][0..7], and the compact-WY factor T (column-major 8x8) into Tb.
+// (vr[k] = tile s+k).  Reflectors are kept UNNORMALISED: H = I - tt u u^T with u = x - beta e1,
+// tt = -1 / (beta u1), so no scaling pass is needed; u is broadcast to the other columns through a
+// contiguous scratch column (16-byte accesses) and the norm of the next column is accumulated
+// while the current reflector is applied.  Outputs: R (top tile) back to A, U row-major into
+// V[row][0..7] (explicit zeros above the diagonal), compact-WY factor T (column-major 8x8) in Tb.
 template <int MAXT>
-__device__ __forceinline__ void panel_factor(double *A, double *V, double *Tb, double *Gs, int ld, int p,
-                                             int RT, int s, int lane) {
+__device__ __forceinline__ void panel_factor(double *A, double *V, double *Tb, double *Gs, double *vs, int ld,
+                                             int p, int RT, int s, int lane) {
   const int c = lane >> 2, q = lane & 3;
   const int j0 = 8 * s;
   const int nf = (p - j0 < 8) ? p - j0 : 8;
   const int nt = RT - s;  // tiles in the strip
   const int r0 = 8 * s;
+  const int l0 = 2 * q, l1 = 2 * q + 1;
   double vr[MAXT][2];
+  double na = 0.0, nb = 0.0;  // |own column below own pivot row c|^2, partial over this lane's rows
 #pragma unroll
   for (int k = 0; k < MAXT; ++k) {
     vr[k][0] = 0.0;
@@ -85,111 +90,101 @@ __device__ __forceinline__ void panel_factor(double *A, double *V, double *Tb, d
       const double2 v = ld_tile(A, ld, r0 + 8 * k, j0, c, q);
       vr[k][0] = v.x;
       vr[k][1] = v.y;
+      if (k > 0) {
+        na = fma(v.x, v.x, na);
+        nb = fma(v.y, v.y, nb);
+      } else {
+        if (l0 > c) na = v.x * v.x;
+        if (l1 > c) nb = v.y * v.y;
+      }
     }
   }
   double tau_r[8];
-  double dg = 0.0;  // diagonal entry (beta) of this lane's column
+  double dg = 0.0, du = 0.0;  // beta (diagonal of R) and u1 of this lane's column
+  double2 *vs2 = reinterpret_cast<double2 *>(vs);
 #pragma unroll
   for (int cc = 0; cc < 8; ++cc) {
     tau_r[cc] = 0.0;
-    const bool own = (c == cc);
     if (cc < nf) {
-      // |column cc below the pivot|^2 (rows of the top tile above / on the pivot excluded)
-      double pa = 0.0, pb = 0.0;
-      if (2 * q > cc) pa = vr[0][0] * vr[0][0];
-      if (2 * q + 1 > cc) pb = vr[0][1] * vr[0][1];
-#pragma unroll
-      for (int k = 1; k < MAXT; ++k) {
-        if (k < nt) {
-          pa = fma(vr[k][0], vr[k][0], pa);
-          pb = fma(vr[k][1], vr[k][1], pb);
-        }
-      }
-      const double part = quad_sum(pa + pb);
+      const double sig = __shfl_sync(kFull, quad_sum(na + nb), 4 * cc);
       const double pv = (cc & 1) ? vr[0][1] : vr[0][0];
-      const double sig = __shfl_sync(kFull, part, 4 * cc);
       const double x0 = __shfl_sync(kFull, pv, 4 * cc + (cc >> 1));
-      double tau = 0.0, scale = 0.0, beta = x0;
-      if (sig != 0.0) {
+      if (sig != 0.0) {  // warp-uniform
         const double nrm = sqrt(fma(x0, x0, sig));
-        beta = (x0 >= 0.0) ? -nrm : nrm;
-        tau = (beta - x0) / beta;
-        scale = 1.0 / (x0 - beta);
-      }
-      tau_r[cc] = tau;
-      if (own) {
-        dg = beta;
-        // top tile: zeros above the pivot, one on it, scaled entries below
-        {
-          const int l0 = 2 * q, l1 = 2 * q + 1;
-          if (l0 > cc) vr[0][0] *= scale;
-          if (l1 > cc) vr[0][1] *= scale;
-          V[(size_t)(r0 + l0) * kVS + cc] = (l0 > cc) ? vr[0][0] : ((l0 == cc) ? 1.0 : 0.0);
-          V[(size_t)(r0 + l1) * kVS + cc] = (l1 > cc) ? vr[0][1] : ((l1 == cc) ? 1.0 : 0.0);
-        }
+        const double beta = (x0 >= 0.0) ? -nrm : nrm;
+        const double u1 = x0 - beta;
+        const double tt = -1.0 / (beta * u1);
+        tau_r[cc] = tt;
+        if (c == cc) {
+          dg = beta;
+          du = u1;
+          // publish u: zeros above the pivot, u1 on it, the raw entries below
+          vs2[q] = make_double2((l0 < cc) ? 0.0 : ((l0 == cc) ? u1 : vr[0][0]),
+                                (l1 < cc) ? 0.0 : ((l1 == cc) ? u1 : vr[0][1]));
 #pragma unroll
-        for (int k = 1; k < MAXT; ++k) {
-          if (k < nt) {
-            vr[k][0] *= scale;
-            vr[k][1] *= scale;
-            V[(size_t)(r0 + 8 * k + 2 * q) * kVS + cc] = vr[k][0];
-            V[(size_t)(r0 + 8 * k + 2 * q + 1) * kVS + cc] = vr[k][1];
-          }
+          for (int k = 1; k < MAXT; ++k)
+            if (k < nt) vs2[4 * k + q] = make_double2(vr[k][0], vr[k][1]);
         }
-      }
-      __syncwarp();
-      // apply H_cc to the later columns of the panel tile: w = tau * v^T a, a -= w v
-      double wa = 0.0, wb = 0.0;
-#pragma unroll
-      for (int k = 0; k < MAXT; ++k) {
-        if (k < nt) {
-          const double *vp = V + (size_t)(r0 + 8 * k + 2 * q) * kVS + cc;
-          wa = fma(vp[0], vr[k][0], wa);
-          wb = fma(vp[kVS], vr[k][1], wb);
-        }
-      }
-      const double w = quad_sum(wa + wb) * tau;
-      if (c > cc) {
+        __syncwarp();
+        double wa = 0.0, wb = 0.0;
 #pragma unroll
         for (int k = 0; k < MAXT; ++k) {
           if (k < nt) {
-            const double *vp = V + (size_t)(r0 + 8 * k + 2 * q) * kVS + cc;
-            vr[k][0] = fma(-w, vp[0], vr[k][0]);
-            vr[k][1] = fma(-w, vp[kVS], vr[k][1]);
+            const double2 u = vs2[4 * k + q];
+            wa = fma(u.x, vr[k][0], wa);
+            wb = fma(u.y, vr[k][1], wb);
           }
         }
-      }
-    } else if (own) {
-      // no reflector for this column (beyond the last feature): V column = 0
+        const double w = quad_sum(wa + wb) * tt;
+        if (c > cc) {
+          na = 0.0;
+          nb = 0.0;
 #pragma unroll
-      for (int k = 0; k < MAXT; ++k) {
-        if (k < nt) {
-          V[(size_t)(r0 + 8 * k + 2 * q) * kVS + cc] = 0.0;
-          V[(size_t)(r0 + 8 * k + 2 * q + 1) * kVS + cc] = 0.0;
+          for (int k = 0; k < MAXT; ++k) {
+            if (k < nt) {
+              const double2 u = vs2[4 * k + q];
+              vr[k][0] = fma(-w, u.x, vr[k][0]);
+              vr[k][1] = fma(-w, u.y, vr[k][1]);
+              if (k > 0) {
+                na = fma(vr[k][0], vr[k][0], na);
+                nb = fma(vr[k][1], vr[k][1], nb);
+              } else {
+                if (l0 > c) na = vr[0][0] * vr[0][0];
+                if (l1 > c) nb = vr[0][1] * vr[0][1];
+              }
+            }
+          }
         }
+        __syncwarp();
+      } else if (c == cc) {
+        dg = x0;  // column already zero below the pivot: H = I
+        du = 0.0;
       }
     }
   }
-  // write the strip back: R entries of the top tile, zeros below it for factored columns,
-  // the updated values for the columns without a reflector (c >= nf, e.g. the c_tr column)
+  // U (row-major) for the trailing updates and R / untouched columns back to A
   {
+    const bool refl = (c < nf) && (du != 0.0);
     double2 v = make_double2(vr[0][0], vr[0][1]);
+    V[(size_t)(r0 + l0) * kVS + c] = refl ? ((l0 < c) ? 0.0 : ((l0 == c) ? du : vr[0][0])) : 0.0;
+    V[(size_t)(r0 + l1) * kVS + c] = refl ? ((l1 < c) ? 0.0 : ((l1 == c) ? du : vr[0][1])) : 0.0;
     if (c < nf) {
-      const int l0 = 2 * q, l1 = 2 * q + 1;
       v.x = (l0 < c) ? vr[0][0] : ((l0 == c) ? dg : 0.0);
       v.y = (l1 < c) ? vr[0][1] : ((l1 == c) ? dg : 0.0);
     }
     st_tile(A, ld, r0, j0, c, q, v);
-  }
 #pragma unroll
-  for (int k = 1; k < MAXT; ++k) {
-    if (k < nt) {
-      const double2 v = (c < nf) ? make_double2(0.0, 0.0) : make_double2(vr[k][0], vr[k][1]);
-      st_tile(A, ld, r0 + 8 * k, j0, c, q, v);
+    for (int k = 1; k < MAXT; ++k) {
+      if (k < nt) {
+        V[(size_t)(r0 + 8 * k + l0) * kVS + c] = refl ? vr[k][0] : 0.0;
+        V[(size_t)(r0 + 8 * k + l1) * kVS + c] = refl ? vr[k][1] : 0.0;
+        st_tile(A, ld, r0 + 8 * k, j0, c, q,
+                (c < nf) ? make_double2(0.0, 0.0) : make_double2(vr[k][0], vr[k][1]));
+      }
     }
   }
   __syncwarp();
-  // G = V^T V: the same fragment is the A operand (V^T) and the B operand (V)
+  // G = U^T U: the same fragment is the A operand (U^T) and the B operand (U)
   double ga0 = 0.0, ga1 = 0.0, gb0 = 0.0, gb1 = 0.0;
 #pragma unroll
   for (int k = 0; k < MAXT; ++k) {
@@ -284,7 +279,8 @@ __global__ void __launch_bounds__(256, MINB) lifts_mma_kernel(LiftParams2 a) {
   double *V1 = V0 + (size_t)NR * kVS;      //                             (phase 2: cost partials, 8 x NR)
   double *Tb = V1 + (size_t)NR * kVS;      // 2 x 64
   double *Gs = Tb + 128;                   // 64
-  double *cost = Gs + 64;                  // p + 1
+  double *vs = Gs + 64;                    // NR  (scratch column of the panel warp)
+  double *cost = vs + NR;                  // p + 1
   double *acc = cost + (p + 2);            // p
   int *perm_s = reinterpret_cast<int *>(acc + p + (p & 1));
   double *Dbuf = V0;
@@ -324,7 +320,7 @@ __global__ void __launch_bounds__(256, MINB) lifts_mma_kernel(LiftParams2 a) {
       // ---- phase 1: blocked Householder with one panel of look-ahead.  In step s warp 0 first
       // brings column tile s+1 up to date and factors it (into the other V/T buffer) while
       // warps 1..7 apply panel s to the remaining tiles: one barrier per panel.
-      if (warp == 0) panel_factor<MAXT>(A, V0, Tb, Gs, ld, p, RT, 0, lane);
+      if (warp == 0) panel_factor<MAXT>(A, V0, Tb, Gs, vs, ld, p, RT, 0, lane);
       __syncthreads();
       for (int s = 0; s < RT; ++s) {
         const double *Vc = (s & 1) ? V1 : V0;
@@ -335,7 +331,7 @@ __global__ void __launch_bounds__(256, MINB) lifts_mma_kernel(LiftParams2 a) {
           if (s + 1 < PT) trailing_tile(A, Vc, Tc, ld, RT, s, s + 1, lane);
           if (s + 1 < RT) {
             __syncwarp();
-            panel_factor<MAXT>(A, Vn, Tn, Gs, ld, p, RT, s + 1, lane);
+            panel_factor<MAXT>(A, Vn, Tn, Gs, vs, ld, p, RT, s + 1, lane);
           }
         } else {
           for (int j = s + 2 + (warp - 1); j < PT; j += 7) trailing_tile(A, Vc, Tc, ld, RT, s, j, lane);
@@ -463,7 +459,7 @@ static int mma_ld(int rt) {
 static size_t mma_smem_bytes(int p) {
   const int rt = (p + 7) / 8, pt = (p + 8) / 8;
   const int ld = mma_ld(rt);
-  size_t d = (size_t)8 * pt * ld + 2 * (size_t)8 * rt * 10 + 192 + (size_t)(p + 2) + (size_t)(p + 1);
+  size_t d = (size_t)8 * pt * ld + 2 * (size_t)8 * rt * 10 + 192 + (size_t)8 * rt + (size_t)(p + 2) + (size_t)(p + 1);
   return d * sizeof(double) + (size_t)p * sizeof(int) + 32;
 }
 
