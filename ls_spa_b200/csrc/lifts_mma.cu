@@ -66,42 +66,43 @@ __device__ __forceinline__ double2 ld_vfrag(const double *V, int r0, int c, int 
 
 // ---------------------------------------------------------------- panel factorisation (one warp)
 // Strip = column tile s, row tiles s..RT-1, held in registers relative to the top tile
-// (vr[k] = tile s+k).  Reflectors are kept UNNORMALISED: H = I - tt u u^T with u = x - beta e1,
-// tt = -1 / (beta u1), so no scaling pass is needed; u is broadcast to the other columns through a
-// contiguous scratch column (16-byte accesses) and the norm of the next column is accumulated
-// while the current reflector is applied.  Outputs: R (top tile) back to A, U row-major into
-// V[row][0..7] (explicit zeros above the diagonal), compact-WY factor T (column-major 8x8) in Tb.
-template <int MAXT>
-__device__ __forceinline__ void panel_factor(double *A, double *V, double *Tb, double *Gs, double *vs, int ld,
-                                             int p, int RT, int s, int lane) {
+// (vr[k] = tile s+k, k < KT).  KT is a compile-time bound >= nt = RT - s: tiles k >= nt are kept
+// identically zero (registers and scratch), so the arithmetic loops carry no per-tile guard
+// (a guarded `k < nt` loop costs ~2x the instructions); the kernel picks the smallest KT variant.
+// Reflectors are kept UNNORMALISED: H = I - tt u u^T with u = x - beta e1, tt = -1 / (beta u1), so
+// no scaling pass is needed; u is broadcast to the other columns through a contiguous scratch
+// column (16-byte accesses) and the norm of the next column is accumulated while the current
+// reflector is applied.  Outputs: R (top tile) back to A, U row-major into V[row][0..7] (explicit
+// zeros above the diagonal), compact-WY factor T (column-major 8x8) in Tb.
+template <int KT>
+__device__ __noinline__ void panel_factor(double *A, double *V, double *Tb, double *Gs, double *vs, int ld,
+                                          int p, int RT, int s, int lane) {
   const int c = lane >> 2, q = lane & 3;
   const int j0 = 8 * s;
   const int nf = (p - j0 < 8) ? p - j0 : 8;
-  const int nt = RT - s;  // tiles in the strip
+  const int nt = RT - s;  // tiles in the strip, 1 <= nt <= KT
   const int r0 = 8 * s;
   const int l0 = 2 * q, l1 = 2 * q + 1;
-  double vr[MAXT][2];
+  double vr[KT][2];
   double na = 0.0, nb = 0.0;  // |own column below own pivot row c|^2, partial over this lane's rows
+  const double *Acol = A + (size_t)(j0 + c) * ld + r0 + 2 * q;
 #pragma unroll
-  for (int k = 0; k < MAXT; ++k) {
-    vr[k][0] = 0.0;
-    vr[k][1] = 0.0;
-    if (k < nt) {
-      const double2 v = ld_tile(A, ld, r0 + 8 * k, j0, c, q);
-      vr[k][0] = v.x;
-      vr[k][1] = v.y;
-      if (k > 0) {
-        na = fma(v.x, v.x, na);
-        nb = fma(v.y, v.y, nb);
-      } else {
-        if (l0 > c) na = v.x * v.x;
-        if (l1 > c) nb = v.y * v.y;
-      }
+  for (int k = 0; k < KT; ++k) {
+    double2 v = make_double2(0.0, 0.0);
+    if (k < nt) v = *reinterpret_cast<const double2 *>(Acol + 8 * k);
+    vr[k][0] = v.x;
+    vr[k][1] = v.y;
+    if (k > 0) {
+      na = fma(v.x, v.x, na);
+      nb = fma(v.y, v.y, nb);
+    } else {
+      if (l0 > c) na = v.x * v.x;
+      if (l1 > c) nb = v.y * v.y;
     }
   }
   double tau_r[8];
   double dg = 0.0, du = 0.0;  // beta (diagonal of R) and u1 of this lane's column
-  double2 *vs2 = reinterpret_cast<double2 *>(vs);
+  double2 *vs2 = reinterpret_cast<double2 *>(vs) + q;
 #pragma unroll
   for (int cc = 0; cc < 8; ++cc) {
     tau_r[cc] = 0.0;
@@ -119,41 +120,47 @@ __device__ __forceinline__ void panel_factor(double *A, double *V, double *Tb, d
           dg = beta;
           du = u1;
           // publish u: zeros above the pivot, u1 on it, the raw entries below
-          vs2[q] = make_double2((l0 < cc) ? 0.0 : ((l0 == cc) ? u1 : vr[0][0]),
+          vs2[0] = make_double2((l0 < cc) ? 0.0 : ((l0 == cc) ? u1 : vr[0][0]),
                                 (l1 < cc) ? 0.0 : ((l1 == cc) ? u1 : vr[0][1]));
 #pragma unroll
-          for (int k = 1; k < MAXT; ++k)
-            if (k < nt) vs2[4 * k + q] = make_double2(vr[k][0], vr[k][1]);
+          for (int k = 1; k < KT; ++k) vs2[4 * k] = make_double2(vr[k][0], vr[k][1]);
         }
         __syncwarp();
-        double wa = 0.0, wb = 0.0;
+        double wa = 0.0, wb = 0.0, wc = 0.0, wd = 0.0;
 #pragma unroll
-        for (int k = 0; k < MAXT; ++k) {
-          if (k < nt) {
-            const double2 u = vs2[4 * k + q];
+        for (int k = 0; k < KT; ++k) {
+          const double2 u = vs2[4 * k];
+          if (k & 1) {
+            wc = fma(u.x, vr[k][0], wc);
+            wd = fma(u.y, vr[k][1], wd);
+          } else {
             wa = fma(u.x, vr[k][0], wa);
             wb = fma(u.y, vr[k][1], wb);
           }
         }
-        const double w = quad_sum(wa + wb) * tt;
+        const double w = quad_sum((wa + wb) + (wc + wd)) * tt;
         if (c > cc) {
+          double nc = 0.0, nd = 0.0;
           na = 0.0;
           nb = 0.0;
 #pragma unroll
-          for (int k = 0; k < MAXT; ++k) {
-            if (k < nt) {
-              const double2 u = vs2[4 * k + q];
-              vr[k][0] = fma(-w, u.x, vr[k][0]);
-              vr[k][1] = fma(-w, u.y, vr[k][1]);
-              if (k > 0) {
-                na = fma(vr[k][0], vr[k][0], na);
-                nb = fma(vr[k][1], vr[k][1], nb);
-              } else {
-                if (l0 > c) na = vr[0][0] * vr[0][0];
-                if (l1 > c) nb = vr[0][1] * vr[0][1];
-              }
+          for (int k = 0; k < KT; ++k) {
+            const double2 u = vs2[4 * k];
+            vr[k][0] = fma(-w, u.x, vr[k][0]);
+            vr[k][1] = fma(-w, u.y, vr[k][1]);
+            if (k == 0) {
+              if (l0 > c) na = vr[0][0] * vr[0][0];
+              if (l1 > c) nb = vr[0][1] * vr[0][1];
+            } else if (k & 1) {
+              nc = fma(vr[k][0], vr[k][0], nc);
+              nd = fma(vr[k][1], vr[k][1], nd);
+            } else {
+              na = fma(vr[k][0], vr[k][0], na);
+              nb = fma(vr[k][1], vr[k][1], nb);
             }
           }
+          na += nc;
+          nb += nd;
         }
         __syncwarp();
       } else if (c == cc) {
@@ -165,37 +172,44 @@ __device__ __forceinline__ void panel_factor(double *A, double *V, double *Tb, d
   // U (row-major) for the trailing updates and R / untouched columns back to A
   {
     const bool refl = (c < nf) && (du != 0.0);
+    const bool fact = c < nf;
+    double *Vc = V + (size_t)(r0 + l0) * kVS + c;
+    double *Aw = A + (size_t)(j0 + c) * ld + r0 + 2 * q;
+    Vc[0] = refl ? ((l0 < c) ? 0.0 : ((l0 == c) ? du : vr[0][0])) : 0.0;
+    Vc[kVS] = refl ? ((l1 < c) ? 0.0 : ((l1 == c) ? du : vr[0][1])) : 0.0;
     double2 v = make_double2(vr[0][0], vr[0][1]);
-    V[(size_t)(r0 + l0) * kVS + c] = refl ? ((l0 < c) ? 0.0 : ((l0 == c) ? du : vr[0][0])) : 0.0;
-    V[(size_t)(r0 + l1) * kVS + c] = refl ? ((l1 < c) ? 0.0 : ((l1 == c) ? du : vr[0][1])) : 0.0;
-    if (c < nf) {
+    if (fact) {
       v.x = (l0 < c) ? vr[0][0] : ((l0 == c) ? dg : 0.0);
       v.y = (l1 < c) ? vr[0][1] : ((l1 == c) ? dg : 0.0);
     }
-    st_tile(A, ld, r0, j0, c, q, v);
+    *reinterpret_cast<double2 *>(Aw) = v;
 #pragma unroll
-    for (int k = 1; k < MAXT; ++k) {
+    for (int k = 1; k < KT; ++k) {
       if (k < nt) {
-        V[(size_t)(r0 + 8 * k + l0) * kVS + c] = refl ? vr[k][0] : 0.0;
-        V[(size_t)(r0 + 8 * k + l1) * kVS + c] = refl ? vr[k][1] : 0.0;
-        st_tile(A, ld, r0 + 8 * k, j0, c, q,
-                (c < nf) ? make_double2(0.0, 0.0) : make_double2(vr[k][0], vr[k][1]));
+        Vc[(size_t)8 * k * kVS] = refl ? vr[k][0] : 0.0;
+        Vc[(size_t)8 * k * kVS + kVS] = refl ? vr[k][1] : 0.0;
+        *reinterpret_cast<double2 *>(Aw + 8 * k) =
+            fact ? make_double2(0.0, 0.0) : make_double2(vr[k][0], vr[k][1]);
       }
     }
   }
   __syncwarp();
   // G = U^T U: the same fragment is the A operand (U^T) and the B operand (U)
   double ga0 = 0.0, ga1 = 0.0, gb0 = 0.0, gb1 = 0.0;
+  {
+    const double *Vf = V + (size_t)(r0 + 2 * q) * kVS + c;
 #pragma unroll
-  for (int k = 0; k < MAXT; ++k) {
-    if (k < nt) {
-      const double2 v = ld_vfrag(V, r0 + 8 * k, c, q);
-      if (k & 1) {
-        dmma(gb0, gb1, v.x, v.x);
-        dmma(gb0, gb1, v.y, v.y);
-      } else {
-        dmma(ga0, ga1, v.x, v.x);
-        dmma(ga0, ga1, v.y, v.y);
+    for (int k = 0; k < KT; ++k) {
+      if (k < nt) {
+        const double vx = Vf[(size_t)8 * k * kVS];
+        const double vy = Vf[(size_t)8 * k * kVS + kVS];
+        if (k & 1) {
+          dmma(gb0, gb1, vx, vx);
+          dmma(gb0, gb1, vy, vy);
+        } else {
+          dmma(ga0, ga1, vx, vx);
+          dmma(ga0, ga1, vy, vy);
+        }
       }
     }
   }
@@ -222,6 +236,24 @@ __device__ __forceinline__ void panel_factor(double *A, double *V, double *Tb, d
     }
   }
   __syncwarp();
+}
+
+// smallest compiled strip height that holds nt tiles
+template <int MAXT>
+__device__ __forceinline__ void panel_dispatch(double *A, double *V, double *Tb, double *Gs, double *vs, int ld,
+                                               int p, int RT, int s, int lane) {
+  const int nt = RT - s;
+  if (MAXT > 10 && nt > 10) {
+    panel_factor<MAXT>(A, V, Tb, Gs, vs, ld, p, RT, s, lane);
+  } else if (MAXT > 7 && nt > 7) {
+    panel_factor<(MAXT < 10 ? MAXT : 10)>(A, V, Tb, Gs, vs, ld, p, RT, s, lane);
+  } else if (MAXT > 4 && nt > 4) {
+    panel_factor<(MAXT < 7 ? MAXT : 7)>(A, V, Tb, Gs, vs, ld, p, RT, s, lane);
+  } else if (nt > 2) {
+    panel_factor<(MAXT < 4 ? MAXT : 4)>(A, V, Tb, Gs, vs, ld, p, RT, s, lane);
+  } else {
+    panel_factor<2>(A, V, Tb, Gs, vs, ld, p, RT, s, lane);
+  }
 }
 
 // ---------------------------------------------------------------- trailing column tile j
@@ -280,7 +312,7 @@ __global__ void __launch_bounds__(256, MINB) lifts_mma_kernel(LiftParams2 a) {
   double *Tb = V1 + (size_t)NR * kVS;      // 2 x 64
   double *Gs = Tb + 128;                   // 64
   double *vs = Gs + 64;                    // NR  (scratch column of the panel warp)
-  double *cost = vs + NR;                  // p + 1
+  double *cost = vs + 128;                 // p + 1
   double *acc = cost + (p + 2);            // p
   int *perm_s = reinterpret_cast<int *>(acc + p + (p & 1));
   double *Dbuf = V0;
@@ -320,7 +352,7 @@ __global__ void __launch_bounds__(256, MINB) lifts_mma_kernel(LiftParams2 a) {
       // ---- phase 1: blocked Householder with one panel of look-ahead.  In step s warp 0 first
       // brings column tile s+1 up to date and factors it (into the other V/T buffer) while
       // warps 1..7 apply panel s to the remaining tiles: one barrier per panel.
-      if (warp == 0) panel_factor<MAXT>(A, V0, Tb, Gs, vs, ld, p, RT, 0, lane);
+      if (warp == 0) panel_dispatch<MAXT>(A, V0, Tb, Gs, vs, ld, p, RT, 0, lane);
       __syncthreads();
       for (int s = 0; s < RT; ++s) {
         const double *Vc = (s & 1) ? V1 : V0;
@@ -331,7 +363,7 @@ __global__ void __launch_bounds__(256, MINB) lifts_mma_kernel(LiftParams2 a) {
           if (s + 1 < PT) trailing_tile(A, Vc, Tc, ld, RT, s, s + 1, lane);
           if (s + 1 < RT) {
             __syncwarp();
-            panel_factor<MAXT>(A, Vn, Tn, Gs, vs, ld, p, RT, s + 1, lane);
+            panel_dispatch<MAXT>(A, Vn, Tn, Gs, vs, ld, p, RT, s + 1, lane);
           }
         } else {
           for (int j = s + 2 + (warp - 1); j < PT; j += 7) trailing_tile(A, Vc, Tc, ld, RT, s, j, lane);
@@ -459,7 +491,7 @@ static int mma_ld(int rt) {
 static size_t mma_smem_bytes(int p) {
   const int rt = (p + 7) / 8, pt = (p + 8) / 8;
   const int ld = mma_ld(rt);
-  size_t d = (size_t)8 * pt * ld + 2 * (size_t)8 * rt * 10 + 192 + (size_t)8 * rt + (size_t)(p + 2) + (size_t)(p + 1);
+  size_t d = (size_t)8 * pt * ld + 2 * (size_t)8 * rt * 10 + 192 + 128 + (size_t)(p + 2) + (size_t)(p + 1);
   return d * sizeof(double) + (size_t)p * sizeof(int) + 32;
 }
 
