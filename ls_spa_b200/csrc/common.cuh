@@ -18,6 +18,10 @@ namespace lsspa {
 
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;
+// A column whose sub-pivot part has squared norm below this is treated as already zero (no
+// reflector): such values are round-off residue, and squaring them again would underflow and
+// turn 1 / (beta * u1) into inf.
+constexpr double kTinySig = 1e-280;
 
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

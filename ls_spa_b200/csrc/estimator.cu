@@ -21,7 +21,7 @@ namespace lsspa {
 constexpr int kDraws = LSSPA_ERR_DRAWS;  // 1024
 constexpr int kHdr = 16;
 // header slots (doubles)
-enum { H_N = 0, H_STOP, H_NHIST, H_OVERALL, H_TOL, H_CUR, H_EST, H_MAXH, H_OVERALL_TMP, H_N_TMP };
+enum { H_N = 0, H_STOP, H_NHIST, H_OVERALL, H_TOL, H_CUR, H_EST, H_MAXH };
 
 struct StateView {
   double *hdr;
@@ -32,11 +32,13 @@ struct StateView {
   double *feat_err;
   double *feat_err_tmp;
   double *err_hist;
+  double *zsq;      // [p][kDraws] scratch of squared draws (overall-error reduction)
+  double *ticket;   // 8 bytes used as an unsigned counter
 };
 
 __host__ __device__ inline size_t state_doubles(int p, int max_batches) {
   return kHdr + 2 * (size_t)p + 2 * (size_t)p * p + 2 * (size_t)kDraws + 2 * (size_t)p * kDraws +
-         2 * (size_t)p + (size_t)max_batches + 8;
+         2 * (size_t)p + (size_t)max_batches + 8 + (size_t)p * kDraws + 8;
 }
 
 __host__ __device__ inline StateView view_state(double *base, int p, int max_batches) {
@@ -53,8 +55,9 @@ __host__ __device__ inline StateView view_state(double *base, int p, int max_bat
   v.S[1] = c; c += (size_t)p * kDraws;
   v.feat_err = c; c += p;
   v.feat_err_tmp = c; c += p;
-  v.err_hist = c;
-  (void)max_batches;
+  v.err_hist = c; c += max_batches + 8;
+  v.zsq = c; c += (size_t)p * kDraws;
+  v.ticket = c;
   return v;
 }
 
@@ -213,11 +216,16 @@ __device__ __forceinline__ double quantile95_sorted(const double *buf) {
   return b - (b - a) * (1.0 - t);
 }
 
-// grid = p (+1 when errors are estimated); block = 1024
+// One launch per batch: grid = p CTAs of 1024 threads.  CTA f merges row f of the covariance,
+// re-centres column f of the draw sums, takes the 0.95 quantile of |z_sf| and leaves z_sf^2 in a
+// scratch column.  The CTA that finishes last (atomic ticket) adds the scratch columns in feature
+// order (deterministic: every rank of a multi-GPU job must take the same stop decision), takes the
+// quantile of the norms and commits the batch: count, buffer flip, error history, stop flag.
 __global__ void __launch_bounds__(1024) est_step_kernel(double *state, int p, int max_batches,
                                                          const double *partials, size_t rank_stride,
-                                                         int nranks) {
+                                                         int nranks, double *zsq, unsigned int *ticket) {
   extern __shared__ double smem[];
+  __shared__ bool s_last;
   double *sortbuf = smem;            // kDraws
   double *mrun = smem + kDraws;      // (nranks+1) x p running means
   double *nrun = mrun + (size_t)(nranks + 1) * p;  // nranks+1 running counts
@@ -249,27 +257,24 @@ __global__ void __launch_bounds__(1024) est_step_kernel(double *state, int p, in
   }
   __syncthreads();
   const double ntot = nrun[nranks];
+  const double scale = 1.0 / sqrt(ntot * (ntot - 1.0));
 
-  if (f < p) {
-    // ---- covariance row f (biased), Chan merge rank by rank
-    for (int j = tid; j < p; j += blockDim.x) {
-      double c = st.cov[cur][(size_t)f * p + j];
-      for (int r = 0; r < nranks; ++r) {
-        const PartView pv = view_part(partials + (size_t)r * rank_stride, p);
-        const double n1 = nrun[r], n2 = pv.hdr[0], nn = nrun[r + 1];
-        if (n2 > 0.0) {
-          const double df = mrun[(size_t)r * p + f] - pv.mean[f];
-          const double dj = mrun[(size_t)r * p + j] - pv.mean[j];
-          c = (n1 / nn) * c + pv.m2[(size_t)f * p + j] / nn + (n1 / nn) * (n2 / nn) * df * dj;
-        }
+  // ---- covariance row f (biased), Chan merge rank by rank
+  for (int j = tid; j < p; j += blockDim.x) {
+    double c = st.cov[cur][(size_t)f * p + j];
+    for (int r = 0; r < nranks; ++r) {
+      const PartView pv = view_part(partials + (size_t)r * rank_stride, p);
+      const double n1 = nrun[r], n2 = pv.hdr[0], nn = nrun[r + 1];
+      if (n2 > 0.0) {
+        const double df = mrun[(size_t)r * p + f] - pv.mean[f];
+        const double dj = mrun[(size_t)r * p + j] - pv.mean[j];
+        c = (n1 / nn) * c + pv.m2[(size_t)f * p + j] / nn + (n1 / nn) * (n2 / nn) * df * dj;
       }
-      st.cov[nxt][(size_t)f * p + j] = c;
     }
-    if (tid == 0) {
-      st.mean[nxt][f] = mrun[(size_t)nranks * p + f];
-      if (f == 0) st.hdr[H_N_TMP] = ntot;
-    }
-    if (!est) return;
+    st.cov[nxt][(size_t)f * p + j] = c;
+  }
+  if (tid == 0) st.mean[nxt][f] = mrun[(size_t)nranks * p + f];
+  if (est) {
     // ---- S column f and G, re-centred on the moving mean
     double s = st.S[cur][(size_t)f * kDraws + tid];
     double gr = st.G[cur][tid];
@@ -284,48 +289,34 @@ __global__ void __launch_bounds__(1024) est_step_kernel(double *state, int p, in
     }
     st.S[nxt][(size_t)f * kDraws + tid] = s;
     if (f == 0) st.G[nxt][tid] = gr;
-    const double scale = 1.0 / sqrt(ntot * (ntot - 1.0));
-    sortbuf[tid] = fabs(s * scale);
+    const double z = s * scale;
+    zsq[(size_t)f * kDraws + tid] = z * z;
+    sortbuf[tid] = fabs(z);
     bitonic_sort_1024(sortbuf, tid);
     if (tid == 0) st.feat_err_tmp[f] = quantile95_sorted(sortbuf);
-  } else {
-    // ---- overall error: 0.95 quantile of |z_s|_2 over the draws (thread = draw)
-    double gr = st.G[cur][tid];
-    double ss = 0.0;
-    // G after each rank is the same for all features: precompute per-rank increments
-    for (int ff = 0; ff < p; ++ff) {
-      double s = st.S[cur][(size_t)ff * kDraws + tid];
-      double g = gr;
-      for (int r = 0; r < nranks; ++r) {
-        const PartView pv = view_part(partials + (size_t)r * rank_stride, p);
-        if (pv.hdr[0] > 0.0) {
-          const double m_old = mrun[(size_t)r * p + ff], m_new = mrun[(size_t)(r + 1) * p + ff];
-          const double g2 = pv.G[tid];
-          s += (m_old - m_new) * g + pv.S[(size_t)ff * kDraws + tid] + (pv.mean[ff] - m_new) * g2;
-          g += g2;
-        }
-      }
-      ss = fma(s, s, ss);
-    }
-    const double scale = 1.0 / sqrt(ntot * (ntot - 1.0));
-    sortbuf[tid] = sqrt(ss) * scale;
-    bitonic_sort_1024(sortbuf, tid);
-    if (tid == 0) st.hdr[H_OVERALL_TMP] = quantile95_sorted(sortbuf);
   }
-}
-
-__global__ void est_commit_kernel(double *state, int p, int max_batches) {
-  StateView st = view_state(state, p, max_batches);
-  if (st.hdr[H_STOP] != 0.0) return;
-  const bool est = st.hdr[H_EST] != 0.0;
-  if (est)
-    for (int j = threadIdx.x; j < p; j += blockDim.x) st.feat_err[j] = st.feat_err_tmp[j];
+  // ---- last CTA: overall error + commit
+  __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) {
-    st.hdr[H_N] = st.hdr[H_N_TMP];
-    st.hdr[H_CUR] = (double)(((int)st.hdr[H_CUR]) ^ 1);
+  if (tid == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double overall = 0.0;
+  if (est) {
+    double ss = 0.0;
+    for (int ff = 0; ff < p; ++ff) ss += __ldcg(zsq + (size_t)ff * kDraws + tid);
+    sortbuf[tid] = sqrt(ss);
+    bitonic_sort_1024(sortbuf, tid);
+    overall = quantile95_sorted(sortbuf);
+    for (int j = tid; j < p; j += blockDim.x) st.feat_err[j] = __ldcg(st.feat_err_tmp + j);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    *ticket = 0;
+    st.hdr[H_N] = ntot;
+    st.hdr[H_CUR] = (double)nxt;
     if (est) {
-      const double overall = st.hdr[H_OVERALL_TMP];
       st.hdr[H_OVERALL] = overall;
       const int nh = (int)st.hdr[H_NHIST];
       if (nh < (int)st.hdr[H_MAXH]) st.err_hist[nh] = overall;
@@ -404,13 +395,15 @@ __global__ void merge_mean_kernel(int p, double *mean, double n1, const double *
 // One CTA; A (copy of R_tr, column-major) and V live in the global workspace (L2-resident).
 __global__ void __launch_bounds__(512) theta_r2_kernel(int p, const double *Rtr, const double *ctr,
                                                         const double *Rte, const double *cte, double ynsq,
-                                                        double *out, double *ws) {
+                                                        double *out, double *ws, int in_smem) {
   extern __shared__ double sm[];
   double *coef = sm, *theta = sm + p, *red = sm + 2 * p;  // red[64]
   __shared__ int s_rot;
   const int tid = threadIdx.x, nt = blockDim.x;
   const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
-  double *A = ws, *V = ws + (size_t)p * p;
+  // Jacobi work matrices: shared memory when 2 p^2 doubles fit (p <= ~118), else the workspace
+  double *A = in_smem ? red + 64 : ws;
+  double *V = A + (size_t)p * p;
   for (int e = tid; e < p * p; e += nt) {
     const int j = e / p, i = e - j * p;
     A[e] = (i <= j) ? Rtr[e] : 0.0;
@@ -575,11 +568,12 @@ extern "C" int lsspa_estimator_update(void *state, int p, int max_batches, const
   const size_t rank_stride = (size_t)nbatch * pstride;
   const size_t smem = ((size_t)kDraws + (size_t)(nranks + 1) * p + (nranks + 1) + 8) * sizeof(double);
   LSSPA_CUDA_TRY(cudaFuncSetAttribute(est_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  (void)estimate_errors;
+  StateView sv = view_state(reinterpret_cast<double *>(state), p, max_batches);
   for (int b = 0; b < nbatch; ++b) {
-    est_step_kernel<<<p + (estimate_errors ? 1 : 0), kDraws, smem, st>>>(
-        reinterpret_cast<double *>(state), p, max_batches, partials + (size_t)b * pstride, rank_stride, nranks);
-    LSSPA_LAUNCH_CHECK();
-    est_commit_kernel<<<1, 256, 0, st>>>(reinterpret_cast<double *>(state), p, max_batches);
+    est_step_kernel<<<p, kDraws, smem, st>>>(reinterpret_cast<double *>(state), p, max_batches,
+                                             partials + (size_t)b * pstride, rank_stride, nranks, sv.zsq,
+                                             reinterpret_cast<unsigned int *>(sv.ticket));
     LSSPA_LAUNCH_CHECK();
   }
   return LSSPA_OK;
@@ -631,10 +625,14 @@ extern "C" int lsspa_theta_r2(int p, const double *R_tr_cm, const double *c_tr, 
                               size_t workspace_bytes, void *stream) {
   if (p < 1 || !R_tr_cm || !c_tr || !R_te_cm || !c_te || !out) return LSSPA_E_BADARG;
   if (!workspace || workspace_bytes < lsspa_theta_r2_workspace_bytes(p)) return LSSPA_E_WORKSPACE;
-  const size_t smem = (size_t)(2 * p + 64) * sizeof(double);
+  size_t smem = (size_t)(2 * p + 64) * sizeof(double);
+  const size_t big = smem + 2 * (size_t)p * p * sizeof(double);
+  const DeviceInfo &d = device_info();
+  const int in_smem = big <= (size_t)(d.smem_optin > 0 ? d.smem_optin : 227 * 1024) ? 1 : 0;
+  if (in_smem) smem = big;
   LSSPA_CUDA_TRY(cudaFuncSetAttribute(theta_r2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   theta_r2_kernel<<<1, 512, smem, as_stream(stream)>>>(p, R_tr_cm, c_tr, R_te_cm, c_te, y_norm_sq, out,
-                                                        reinterpret_cast<double *>(workspace));
+                                                        reinterpret_cast<double *>(workspace), in_smem);
   LSSPA_LAUNCH_CHECK();
   return LSSPA_OK;
 }

@@ -55,7 +55,7 @@ __device__ __forceinline__ void hh_vector(double *A, int ld, int p, int k, int l
   sig = warp_sum(sig);
   double x0 = col[k];
   double tau = 0.0, scale = 0.0, beta = x0;
-  if (sig != 0.0) {
+  if (sig > kTinySig) {
     double nrm = sqrt(fma(x0, x0, sig));
     beta = (x0 >= 0.0) ? -nrm : nrm;
     tau = (beta - x0) / beta;

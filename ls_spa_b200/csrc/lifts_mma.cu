@@ -110,7 +110,7 @@ __device__ __noinline__ void panel_factor(double *A, double *V, double *Tb, doub
       const double sig = __shfl_sync(kFull, quad_sum(na + nb), 4 * cc);
       const double pv = (cc & 1) ? vr[0][1] : vr[0][0];
       const double x0 = __shfl_sync(kFull, pv, 4 * cc + (cc >> 1));
-      if (sig != 0.0) {  // warp-uniform
+      if (sig > kTinySig) {  // warp-uniform
         const double nrm = sqrt(fma(x0, x0, sig));
         const double beta = (x0 >= 0.0) ? -nrm : nrm;
         const double u1 = x0 - beta;

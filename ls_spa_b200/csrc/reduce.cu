@@ -69,7 +69,7 @@ __device__ __forceinline__ void absorb_block(double *T, double *B, double *v, do
       const double sig = warp_sum(x * x);
       const double x0 = T[(size_t)k * q + k];
       double tau = 0.0, scale = 0.0, beta = x0;
-      if (sig != 0.0) {
+      if (sig > kTinySig) {
         const double nrm = sqrt(fma(x0, x0, sig));
         beta = (x0 >= 0.0) ? -nrm : nrm;
         tau = (beta - x0) / beta;
@@ -210,6 +210,189 @@ __global__ void tsqr_merge_kernel(MergeParams a) {
   if (tid < kSlotExtra) slot[(size_t)q * q + tid] = (tid == 0) ? extra : 0.0;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Register-resident variant (q <= 512; 128 registers per thread cap the CTA at 512 threads): thread (j, h) keeps 32 rows of column j of the current
+// block in registers (h = which half of a 64-row block when two threads share a column), so the
+// block never touches shared memory.  Per reflector k the owner threads of column k compute
+// u = x - beta e1 and tt = -1/(beta u1) themselves (no scaling pass) and publish u through a
+// double-buffered 64-entry scratch: ONE barrier per reflector instead of two, 16-byte broadcast
+// loads only.  T stays row-major (shared memory when it fits, else the output slot in L2).
+template <int HALVES>
+__device__ __forceinline__ void absorb_regs(double *T, double (&b)[32], double *us, int q, int j, int h,
+                                            bool active, int kstart, int kend) {
+  // us: 2 x (64 + 8) doubles: [u(0..63), u1, tt] per buffer
+  for (int k = kstart; k < kend; ++k) {
+    double *ub = us + (k & 1) * 72;
+    if (active && j == k) {
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        s0 = fma(b[i], b[i], s0);
+        s1 = fma(b[i + 1], b[i + 1], s1);
+        s2 = fma(b[i + 2], b[i + 2], s2);
+        s3 = fma(b[i + 3], b[i + 3], s3);
+      }
+      double sig = (s0 + s1) + (s2 + s3);
+      if (HALVES == 2) sig += __shfl_xor_sync(__activemask(), sig, 1);
+      const double x0 = T[(size_t)k * q + k];
+      double u1 = 0.0, tt = 0.0, beta = x0;
+      if (sig > kTinySig) {
+        const double nrm = sqrt(fma(x0, x0, sig));
+        beta = (x0 >= 0.0) ? -nrm : nrm;
+        u1 = x0 - beta;
+        tt = -1.0 / (beta * u1);
+      }
+      double2 *dst = reinterpret_cast<double2 *>(ub + 32 * h);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) dst[i] = make_double2(b[2 * i], b[2 * i + 1]);
+      if (h == 0) {
+        ub[64] = u1;
+        ub[65] = tt;
+        T[(size_t)k * q + k] = beta;
+      }
+    }
+    __syncthreads();
+    const double tt = ub[65];
+    if (active && j > k && tt != 0.0) {
+      const double2 *src = reinterpret_cast<const double2 *>(ub + 32 * h);
+      double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+#pragma unroll
+      for (int i = 0; i < 16; i += 2) {
+        const double2 a = src[i], c = src[i + 1];
+        d0 = fma(a.x, b[2 * i], d0);
+        d1 = fma(a.y, b[2 * i + 1], d1);
+        d2 = fma(c.x, b[2 * i + 2], d2);
+        d3 = fma(c.y, b[2 * i + 3], d3);
+      }
+      double d = (d0 + d1) + (d2 + d3);
+      if (HALVES == 2) d += __shfl_xor_sync(__activemask(), d, 1);
+      const double u1 = ub[64];
+      const double tkj = T[(size_t)k * q + j];
+      const double w = tt * fma(u1, tkj, d);
+      if (h == 0) T[(size_t)k * q + j] = fma(-w, u1, tkj);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const double2 a = src[i];
+        b[2 * i] = fma(-w, a.x, b[2 * i]);
+        b[2 * i + 1] = fma(-w, a.y, b[2 * i + 1]);
+      }
+    }
+  }
+  __syncthreads();  // the scratch buffers may be reused by the next block
+}
+
+template <int HALVES>
+__global__ void __launch_bounds__(512) tsqr_rows_regs_kernel(RowsParams a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int q = a.p + 1;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  double *sm = reinterpret_cast<double *>(smem_raw);
+  double *slot = a.parts + (size_t)blockIdx.x * a.slot;
+  double *us = sm;                 // 144 doubles
+  double *s_acc = sm + 144;        // 32 doubles (per-warp partial sums of y^2)
+  double *T = a.t_in_smem ? sm + 176 : slot;
+  const int j = tid / HALVES, h = tid % HALVES;
+  const bool active = j < q;
+  constexpr int RB = 32 * HALVES;
+
+  for (int e = tid; e < q * q; e += nt) T[e] = 0.0;
+  const int64_t per = ceil_div(ceil_div(a.nrows, (int64_t)a.nparts), (int64_t)RB) * RB;
+  const int64_t r_begin = (int64_t)blockIdx.x * per;
+  const int64_t r_end = (r_begin + per < a.nrows) ? r_begin + per : a.nrows;
+  double ysq = 0.0;
+  __syncthreads();
+  double b[32];
+  for (int64_t r0 = r_begin; r0 < r_end; r0 += RB) {
+    const int64_t rbase = r0 + 32 * h;
+    if (active) {
+      if (j < a.p) {
+        const double *src = a.X + rbase * a.ldx + j;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) b[i] = (rbase + i < r_end) ? src[(int64_t)i * a.ldx] / a.divisor : 0.0;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          b[i] = (rbase + i < r_end) ? a.y[rbase + i] / a.divisor : 0.0;
+          ysq = fma(b[i], b[i], ysq);
+        }
+      }
+    }
+    absorb_regs<HALVES>(T, b, us, q, j, h, active, 0, q);
+  }
+  // sum of squares of the scaled targets (held by the threads of column p)
+  if (tid < 32) s_acc[tid] = 0.0;
+  __syncthreads();
+  if (active && j == a.p) atomicAdd(&s_acc[0], ysq);
+  __syncthreads();
+  if (a.t_in_smem)
+    for (int e = tid; e < q * q; e += nt) slot[e] = T[e];
+  if (tid < kSlotExtra) slot[(size_t)q * q + tid] = (tid == 0) ? s_acc[0] : 0.0;
+}
+
+template <int HALVES>
+__global__ void __launch_bounds__(512) tsqr_merge_regs_kernel(MergeParams a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int q = a.p + 1;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  double *sm = reinterpret_cast<double *>(smem_raw);
+  double *slot = a.out + (size_t)blockIdx.x * a.slot;
+  double *us = sm;
+  double *T = a.t_in_smem ? sm + 176 : slot;
+  const int j = tid / HALVES, h = tid % HALVES;
+  const bool active = j < q;
+  constexpr int RB = 32 * HALVES;
+
+  const int first = blockIdx.x * a.group;
+  const int last = (first + a.group < a.count) ? first + a.group : a.count;
+  const double *src0 = a.parts + (size_t)first * a.slot;
+  for (int e = tid; e < q * q; e += nt) {
+    const int i = e / q, jj = e - i * q;
+    T[e] = (jj >= i) ? src0[e] : 0.0;
+  }
+  double extra = (tid == 0) ? src0[(size_t)q * q] : 0.0;
+  __syncthreads();
+  double b[32];
+  for (int t = first + 1; t < last; ++t) {
+    const double *src = a.parts + (size_t)t * a.slot;
+    if (tid == 0) extra += src[(size_t)q * q];
+    for (int r0 = 0; r0 < q; r0 += RB) {
+      const int rbase = r0 + 32 * h;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int r = rbase + i;
+        b[i] = (active && r < q && j >= r) ? src[(size_t)r * q + j] : 0.0;
+      }
+      // rows r0.. of a triangle are zero left of column r0; nothing below row q
+      absorb_regs<HALVES>(T, b, us, q, j, h, active, r0, q);
+    }
+  }
+  if (a.t_in_smem)
+    for (int e = tid; e < q * q; e += nt) slot[e] = T[e];
+  if (tid < kSlotExtra) slot[(size_t)q * q + tid] = (tid == 0) ? extra : 0.0;
+}
+
+struct RegsGeom {
+  int halves;   // 0 = not applicable
+  int threads;
+  bool t_in_smem;
+  size_t smem;
+};
+
+static RegsGeom regs_geom(int p) {
+  RegsGeom g{0, 0, false, 0};
+  const int q = p + 1;
+  if (q > 512) return g;
+  g.halves = (q <= 256) ? 2 : 1;
+  g.threads = ((q * g.halves + 31) / 32) * 32;
+  const DeviceInfo &d = device_info();
+  const size_t limit = (size_t)(d.smem_optin > 0 ? d.smem_optin : 227 * 1024);
+  const size_t tbytes = (size_t)q * q * sizeof(double);
+  g.t_in_smem = tbytes + 176 * sizeof(double) <= limit;
+  g.smem = 176 * sizeof(double) + (g.t_in_smem ? tbytes : 0);
+  return g;
+}
+
 }  // namespace lsspa
 
 using namespace lsspa;
@@ -221,7 +404,14 @@ extern "C" int64_t lsspa_tsqr_slot_doubles(int p) {
 
 extern "C" int lsspa_tsqr_num_parts(int p, int64_t nrows) {
   if (p < 1 || nrows < 1) return 0;
-  const TsqrGeom g = tsqr_geom(p);
+  const TsqrGeom g0 = tsqr_geom(p);
+  const RegsGeom rg = regs_geom(p);
+  TsqrGeom g = g0;
+  if (rg.halves) {
+    g.rb = 32 * rg.halves;
+    g.smem = rg.smem;
+    g.t_in_smem = rg.t_in_smem;
+  }
   const DeviceInfo &d = device_info();
   const int sms = d.sm_count > 0 ? d.sm_count : 148;
   int64_t cap = g.t_in_smem ? (int64_t)sms * ((g.smem * 2 + 2048 <= 227 * 1024) ? 2 : 1) : sms;
@@ -247,6 +437,21 @@ extern "C" int lsspa_tsqr_rows(const double *X, int64_t ldx, const double *y, in
   a.nparts = nparts;
   a.rb = g.rb;
   a.t_in_smem = g.t_in_smem ? 1 : 0;
+  const RegsGeom rg = regs_geom(p);
+  if (rg.halves) {
+    a.t_in_smem = rg.t_in_smem ? 1 : 0;
+    if (rg.halves == 2) {
+      LSSPA_CUDA_TRY(cudaFuncSetAttribute(tsqr_rows_regs_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)rg.smem));
+      tsqr_rows_regs_kernel<2><<<nparts, rg.threads, rg.smem, as_stream(stream)>>>(a);
+    } else {
+      LSSPA_CUDA_TRY(cudaFuncSetAttribute(tsqr_rows_regs_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)rg.smem));
+      tsqr_rows_regs_kernel<1><<<nparts, rg.threads, rg.smem, as_stream(stream)>>>(a);
+    }
+    LSSPA_LAUNCH_CHECK();
+    return LSSPA_OK;
+  }
   LSSPA_CUDA_TRY(cudaFuncSetAttribute(tsqr_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)g.smem));
   tsqr_rows_kernel<<<nparts, g.threads, g.smem, as_stream(stream)>>>(a);
@@ -268,6 +473,21 @@ extern "C" int lsspa_tsqr_merge(const double *parts, int count, int group, int p
   a.rb = g.rb;
   a.t_in_smem = g.t_in_smem ? 1 : 0;
   const int nout = (int)ceil_div(count, group);
+  const RegsGeom rg = regs_geom(p);
+  if (rg.halves) {
+    a.t_in_smem = rg.t_in_smem ? 1 : 0;
+    if (rg.halves == 2) {
+      LSSPA_CUDA_TRY(cudaFuncSetAttribute(tsqr_merge_regs_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)rg.smem));
+      tsqr_merge_regs_kernel<2><<<nout, rg.threads, rg.smem, as_stream(stream)>>>(a);
+    } else {
+      LSSPA_CUDA_TRY(cudaFuncSetAttribute(tsqr_merge_regs_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)rg.smem));
+      tsqr_merge_regs_kernel<1><<<nout, rg.threads, rg.smem, as_stream(stream)>>>(a);
+    }
+    LSSPA_LAUNCH_CHECK();
+    return LSSPA_OK;
+  }
   LSSPA_CUDA_TRY(cudaFuncSetAttribute(tsqr_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)g.smem));
   tsqr_merge_kernel<<<nout, g.threads, g.smem, as_stream(stream)>>>(a);

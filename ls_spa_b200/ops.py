@@ -259,7 +259,7 @@ class Estimator:
         check(_lib().lsspa_estimator_update(self.state.data_ptr(), self.p, self.max_batches,
                                             partials.data_ptr(), nbatch, nranks,
                                             1 if self.estimate else 0, _stream()), "lsspa_estimator_update")
-        _count(2 * nbatch)
+        _count(nbatch)
 
     def read(self, want_cov: bool = False):
         """-> dict(count, stopped, n_history, overall_error, mean, attribution_errors, error_history[, cov])
