@@ -117,36 +117,39 @@ LSSPA_API int lsspa_lifts(int p, const double *R_tr_cm, const double *c_tr, cons
  * 4. Estimator                        replaces ls_spa/ls_spa.py:186-236
  *    (merge_sample_mean/cov :103-119, error_estimates :321-341, stop test :229).
  *
- * State lives in one device buffer of lsspa_estimator_state_bytes(p, max_batches)
- * bytes, zero-initialised by lsspa_estimator_init.  One lsspa_estimator_update call
- * consumes `nbatch` consecutive batches of `batch` lift rows each (the last may be
- * short: total_rows), in order; for every batch it Chan-merges the batch moments into
- * (count, mean, biased cov), draws LSSPA_ERR_DRAWS Gaussian vectors with covariance
- * unbiased_cov / count (factor-free: z_s = sum_k g_ks (l_k - mean) / sqrt(n(n-1))),
- * takes the 0.95 quantiles, appends the overall error to the history and raises the
- * stop flag when it is < tolerance.  Batches after the stop are ignored, exactly as the
- * reference's `break`.
- * With nranks > 1 `partials` holds, per batch, nranks partial moment blocks gathered
- * from the ranks (layout lsspa_estimator_partial_doubles) and lifts may be NULL.
+ * Work is organised per super-batch (a run of consecutive batches of lift rows):
+ *   lsspa_estimator_partials   per-batch partial moments of the rows this rank computed:
+ *                              {n, mean, sum (l-mean)(l-mean)^T, G = sum_k g_k, S = sum_k g_k (l_k - mean)}
+ *                              with g the counter-based N(0,1) stream keyed by the GLOBAL sample index
+ *                              (so the result does not depend on how batches are sharded over GPUs);
+ *   lsspa_estimator_absorb     folds nb consecutive batches (blocks partials[slot_map[b]]) into the
+ *                              state (mean, biased cov, draw sums) with the Chan merge of
+ *                              merge_sample_mean/cov, in order, and for the batches [own0, own1) writes
+ *                              the squared error draws z_sf^2, z_s = sum_k g_ks (l_k - mean) / sqrt(n (n-1)),
+ *                              which have exactly the covariance unbiased_cov / n that error_estimates
+ *                              samples from (factor-free: that covariance is singular);
+ *   lsspa_estimator_quantiles  0.95 quantiles of |z_sf| per feature and of |z_s|_2 for every owned batch.
+ * The caller scans the per-batch errors for the first one below the tolerance (the reference's `break`);
+ * if it falls inside a super-batch it restores its snapshot of the state and replays absorb up to it.
+ * State = lsspa_estimator_state_bytes(p) bytes, zero-initialised by the caller:
+ * mean[2][p] and G[2][1024] ping-pong (`cur` selects the live copy; absorb writes the other one),
+ * cov[p][p], S[p][1024].
  * ------------------------------------------------------------------------ */
-LSSPA_API size_t lsspa_estimator_state_bytes(int p, int max_batches);
+LSSPA_API size_t lsspa_estimator_state_bytes(int p);
 LSSPA_API int64_t lsspa_estimator_partial_doubles(int p);
-LSSPA_API int lsspa_estimator_init(void *state, int p, int max_batches, double tolerance, int estimate_errors,
-                         void *stream);
-/* Partial moments of this rank's rows of each batch.  batch_desc (device, int64[nbatch][3]) =
- * {first row in `lifts`, row count (may be 0), global index of the first sample}; the global
- * index keys the counter-based Gaussian stream, so results do not depend on the sharding.
- * partials[nbatch][partial_doubles] = {n, mean[p], sum (l-mean)(l-mean)^T [p][p],
- * G[1024] = sum_k g_ks, S[p][1024] = sum_k g_ks (l_k - mean)}. */
+/* largest nb one absorb call accepts (running means of all its batches sit in shared memory) */
+LSSPA_API int lsspa_estimator_max_batches(int p);
+/* batch_desc (device, int64[nbatch][3]) = {first row in `lifts`, row count (may be 0), global index of the
+ * first sample}; partials[nbatch][partial_doubles] */
 LSSPA_API int lsspa_estimator_partials(int p, const double *lifts, const int64_t *batch_desc, int nbatch,
                              uint64_t seed, int estimate_errors, double *partials, void *stream);
-/* partials laid out [nranks][nbatch][partial_doubles] (what an all-gather produces) */
-LSSPA_API int lsspa_estimator_update(void *state, int p, int max_batches, const double *partials, int nbatch,
-                           int nranks, int estimate_errors, void *stream);
-/* copies {count, stopped, n_history, overall_error} to 4 doubles, mean[p],
- * attribution_errors[p], error_history[n_history<=max_batches] (device -> device) */
-LSSPA_API int lsspa_estimator_read(const void *state, int p, int max_batches, double *summary4, double *mean,
-                         double *feat_err, double *err_hist, double *cov_or_null, void *stream);
+/* zsq: device [own1-own0][p][1024] doubles, or NULL when no error draws are wanted; with_draws = 0
+ * skips the draw sums altogether (partials made with estimate_errors = 0 carry none) */
+LSSPA_API int lsspa_estimator_absorb(void *state, int p, int cur, double n_before, const double *partials,
+                           const int32_t *slot_map, int nb, int own0, int own1, double *zsq, int with_draws,
+                           void *stream);
+LSSPA_API int lsspa_estimator_quantiles(int p, const double *zsq, int nown, double *overall_out,
+                              double *feat_out, void *stream);
 /* running means after each sample (attribution_history, :217-219): hist[k] =
  * (carry_sum + sum_{r<=k} lifts[r]) / (carry_count + k + 1); carry is updated */
 LSSPA_API int lsspa_prefix_means(int p, const double *lifts, int64_t rows, double *carry_sum,

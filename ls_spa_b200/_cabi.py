@@ -33,12 +33,12 @@ SIGNATURES = {
     "lsspa_perms_permutohedron": (c_i32, [c_i32, vp, vp, c_i32, c_u64, c_i64, vp, vp]),
     "lsspa_lifts_workspace_bytes": (sz, [c_i32, c_i64]),
     "lsspa_lifts": (c_i32, [c_i32, vp, vp, vp, vp, c_f64, vp, c_i64, c_i32, vp, vp, sz, vp]),
-    "lsspa_estimator_state_bytes": (sz, [c_i32, c_i32]),
+    "lsspa_estimator_state_bytes": (sz, [c_i32]),
     "lsspa_estimator_partial_doubles": (c_i64, [c_i32]),
-    "lsspa_estimator_init": (c_i32, [vp, c_i32, c_i32, c_f64, c_i32, vp]),
+    "lsspa_estimator_max_batches": (c_i32, [c_i32]),
     "lsspa_estimator_partials": (c_i32, [c_i32, vp, vp, c_i32, c_u64, c_i32, vp, vp]),
-    "lsspa_estimator_update": (c_i32, [vp, c_i32, c_i32, vp, c_i32, c_i32, c_i32, vp]),
-    "lsspa_estimator_read": (c_i32, [vp, c_i32, c_i32, vp, vp, vp, vp, vp, vp]),
+    "lsspa_estimator_absorb": (c_i32, [vp, c_i32, c_i32, c_f64, vp, vp, c_i32, c_i32, c_i32, vp, c_i32, vp]),
+    "lsspa_estimator_quantiles": (c_i32, [c_i32, vp, c_i32, vp, vp, vp]),
     "lsspa_prefix_means": (c_i32, [c_i32, vp, c_i64, vp, c_f64, vp, vp]),
     "lsspa_merge_moments": (c_i32, [c_i32, vp, vp, c_f64, vp, vp, c_f64, vp]),
     "lsspa_theta_r2_workspace_bytes": (sz, [c_i32]),

@@ -266,9 +266,9 @@ def error_estimates(rng, cov):
     a = (v * torch.sqrt(torch.clamp(w, min=0.0))).t().contiguous()        # rows a_k
     n = 2 * p
     rows = torch.cat([a, -a], 0) * np.sqrt((n - 1) / 2.0)                 # mean 0, unbiased cov/n... = cov/n*n
-    est = ops.Estimator(p, 2, -1.0, seed, True, device)
+    est = ops.Estimator(p, seed, True, device)
     part = est.partials(rows, [(0, n, 0)])
-    est.update(part, 1)
-    out = est.read()
+    overall, feat = est.absorb(part, [0], [n], own=(0, 1), emit=True)
+    out = {"attribution_errors": feat[0].cpu().numpy(), "overall_error": float(overall[0].item())}
     scale = np.sqrt(n)        # the estimator reports draws of N(0, unbiased_cov / n)
     return out["attribution_errors"] * scale, out["overall_error"] * scale

@@ -7,6 +7,13 @@
 //   attribution_history (:217-219)                    -> prefix means
 //   theta / r_squared epilogue (:240-243)             -> triangular solve + residual
 //
+// Work is organised per SUPER-BATCH (a run of consecutive batches): one launch folds all its
+// batches into the state in order and emits the squared error draws of the batches this rank
+// owns, one launch takes all their quantiles in parallel.  The host (engine.py) scans the
+// per-batch errors for the first one below the tolerance and, if the stop falls inside the
+// super-batch, restores the snapshot and replays the merges up to that batch -- the merges are
+// deterministic, so this is exactly the reference's `break`.
+//
 // error_estimates draws 1024 vectors from N(0, unbiased_cov / n).  The lift covariance is
 // exactly singular (every lift vector sums to the full-model R^2), so instead of
 // factorising it we use z_s = sum_k g_ks (l_k - mean) / sqrt(n (n-1)), g iid N(0,1), which
@@ -19,45 +26,27 @@
 namespace lsspa {
 
 constexpr int kDraws = LSSPA_ERR_DRAWS;  // 1024
-constexpr int kHdr = 16;
-// header slots (doubles)
-enum { H_N = 0, H_STOP, H_NHIST, H_OVERALL, H_TOL, H_CUR, H_EST, H_MAXH };
-
-struct StateView {
-  double *hdr;
-  double *mean[2];
-  double *cov[2];
-  double *G[2];
-  double *S[2];  // feature-major [p][kDraws]
-  double *feat_err;
-  double *feat_err_tmp;
-  double *err_hist;
-  double *zsq;      // [p][kDraws] scratch of squared draws (overall-error reduction)
-  double *ticket;   // 8 bytes used as an unsigned counter
-};
-
-__host__ __device__ inline size_t state_doubles(int p, int max_batches) {
-  return kHdr + 2 * (size_t)p + 2 * (size_t)p * p + 2 * (size_t)kDraws + 2 * (size_t)p * kDraws +
-         2 * (size_t)p + (size_t)max_batches + 8 + (size_t)p * kDraws + 8;
+// State (doubles): mean[2][p] (ping-pong), G[2][kDraws] (ping-pong), cov[p][p] (biased),
+// S[p][kDraws] feature-major.  Row f of cov and column f of S are owned by CTA f of the absorb
+// kernel and updated in place; mean and G are read by every CTA, hence double-buffered.
+__host__ __device__ inline size_t state_doubles(int p) {
+  return 2 * (size_t)p + 2 * (size_t)kDraws + (size_t)p * p + (size_t)p * kDraws;
 }
-
-__host__ __device__ inline StateView view_state(double *base, int p, int max_batches) {
+struct StateView {
+  double *mean[2];
+  double *G[2];
+  double *cov;
+  double *S;
+};
+__host__ __device__ inline StateView view_state(double *base, int p) {
   StateView v;
   double *c = base;
-  v.hdr = c; c += kHdr;
   v.mean[0] = c; c += p;
   v.mean[1] = c; c += p;
-  v.cov[0] = c; c += (size_t)p * p;
-  v.cov[1] = c; c += (size_t)p * p;
   v.G[0] = c; c += kDraws;
   v.G[1] = c; c += kDraws;
-  v.S[0] = c; c += (size_t)p * kDraws;
-  v.S[1] = c; c += (size_t)p * kDraws;
-  v.feat_err = c; c += p;
-  v.feat_err_tmp = c; c += p;
-  v.err_hist = c; c += max_batches + 8;
-  v.zsq = c; c += (size_t)p * kDraws;
-  v.ticket = c;
+  v.cov = c; c += (size_t)p * p;
+  v.S = c;
   return v;
 }
 
@@ -207,152 +196,106 @@ __device__ __forceinline__ void bitonic_sort_1024(double *buf, int tid) {
   __syncthreads();
 }
 
-__device__ __forceinline__ double quantile95_sorted(const double *buf) {
-  // numpy.quantile(..., 0.95), default 'linear' method on n = 1024 sorted values
-  const double pos = (double)(kDraws - 1) * 0.95;
-  const int lo = (int)floor(pos);
-  const double t = pos - (double)lo;
-  const double a = buf[lo], b = buf[lo + 1];
-  return b - (b - a) * (1.0 - t);
-}
-
-// One launch per batch: grid = p CTAs of 1024 threads.  CTA f merges row f of the covariance,
-// re-centres column f of the draw sums, takes the 0.95 quantile of |z_sf| and leaves z_sf^2 in a
-// scratch column.  The CTA that finishes last (atomic ticket) adds the scratch columns in feature
-// order (deterministic: every rank of a multi-GPU job must take the same stop decision), takes the
-// quantile of the norms and commits the batch: count, buffer flip, error history, stop flag.
-__global__ void __launch_bounds__(1024) est_step_kernel(double *state, int p, int max_batches,
-                                                         const double *partials, size_t rank_stride,
-                                                         int nranks, double *zsq, unsigned int *ticket) {
+// Fold `nb` consecutive batches (partial blocks partials[slot_map[b]]) into the state, in order.
+// grid = p CTAs of 1024 threads; CTA f owns covariance row f and draw-sum column f.  For the
+// batches b in [own0, own1) the squared error draws z_sf^2 (covariance unbiased_cov / n after
+// batch b) are written to zsq[b - own0][f][s].
+__global__ void __launch_bounds__(1024) est_absorb_kernel(double *state, int p, int cur, double n_before,
+                                                           const double *partials, size_t pstride,
+                                                           const int *slot_map, int nb, int own0, int own1,
+                                                           double *zsq, int with_draws) {
   extern __shared__ double smem[];
-  __shared__ bool s_last;
-  double *sortbuf = smem;            // kDraws
-  double *mrun = smem + kDraws;      // (nranks+1) x p running means
-  double *nrun = mrun + (size_t)(nranks + 1) * p;  // nranks+1 running counts
-  StateView st = view_state(state, p, max_batches);
-  if (st.hdr[H_STOP] != 0.0) return;
-  const int cur = (int)st.hdr[H_CUR], nxt = cur ^ 1;
-  const bool est = st.hdr[H_EST] != 0.0;
+  double *mrun = smem;                           // (nb+1) x p running means
+  double *nrun = mrun + (size_t)(nb + 1) * p;    // nb+1 running counts
+  StateView st = view_state(state, p);
+  const int nxt = cur ^ 1;
   const int tid = threadIdx.x;
   const int f = blockIdx.x;
-
-  // running means / counts after merging 0..r partials (every CTA recomputes them)
   if (tid == 0) {
-    double n = st.hdr[H_N];
+    double n = n_before;
     nrun[0] = n;
-    for (int r = 0; r < nranks; ++r) {
-      n += partials[(size_t)r * rank_stride];
-      nrun[r + 1] = n;
+    for (int b = 0; b < nb; ++b) {
+      n += partials[(size_t)slot_map[b] * pstride];
+      nrun[b + 1] = n;
     }
   }
   for (int j = tid; j < p; j += blockDim.x) mrun[j] = st.mean[cur][j];
   __syncthreads();
-  for (int r = 0; r < nranks; ++r) {
-    const PartView pv = view_part(partials + (size_t)r * rank_stride, p);
-    const double n1 = nrun[r], n2 = pv.hdr[0], nn = nrun[r + 1];
-    for (int j = tid; j < p; j += blockDim.x) {
-      const double m1 = mrun[(size_t)r * p + j];
-      mrun[(size_t)(r + 1) * p + j] = (nn > 0.0) ? (n1 / nn) * m1 + (n2 / nn) * pv.mean[j] : m1;
+  for (int j = tid; j < p; j += blockDim.x) {
+    double m = mrun[j];
+    for (int b = 0; b < nb; ++b) {
+      const PartView pv = view_part(partials + (size_t)slot_map[b] * pstride, p);
+      const double n1 = nrun[b], n2 = pv.hdr[0], nn = nrun[b + 1];
+      if (n2 > 0.0) m = (n1 / nn) * m + (n2 / nn) * pv.mean[j];
+      mrun[(size_t)(b + 1) * p + j] = m;
     }
   }
   __syncthreads();
-  const double ntot = nrun[nranks];
-  const double scale = 1.0 / sqrt(ntot * (ntot - 1.0));
-
-  // ---- covariance row f (biased), Chan merge rank by rank
+  // ---- covariance row f (biased): Chan merge batch by batch (reference merge_sample_cov)
   for (int j = tid; j < p; j += blockDim.x) {
-    double c = st.cov[cur][(size_t)f * p + j];
-    for (int r = 0; r < nranks; ++r) {
-      const PartView pv = view_part(partials + (size_t)r * rank_stride, p);
-      const double n1 = nrun[r], n2 = pv.hdr[0], nn = nrun[r + 1];
+    double c = st.cov[(size_t)f * p + j];
+    for (int b = 0; b < nb; ++b) {
+      const PartView pv = view_part(partials + (size_t)slot_map[b] * pstride, p);
+      const double n1 = nrun[b], n2 = pv.hdr[0], nn = nrun[b + 1];
       if (n2 > 0.0) {
-        const double df = mrun[(size_t)r * p + f] - pv.mean[f];
-        const double dj = mrun[(size_t)r * p + j] - pv.mean[j];
+        const double df = mrun[(size_t)b * p + f] - pv.mean[f];
+        const double dj = mrun[(size_t)b * p + j] - pv.mean[j];
         c = (n1 / nn) * c + pv.m2[(size_t)f * p + j] / nn + (n1 / nn) * (n2 / nn) * df * dj;
       }
     }
-    st.cov[nxt][(size_t)f * p + j] = c;
+    st.cov[(size_t)f * p + j] = c;
   }
-  if (tid == 0) st.mean[nxt][f] = mrun[(size_t)nranks * p + f];
-  if (est) {
-    // ---- S column f and G, re-centred on the moving mean
-    double s = st.S[cur][(size_t)f * kDraws + tid];
+  if (tid == 0) st.mean[nxt][f] = mrun[(size_t)nb * p + f];
+  // ---- draw sums: S column f and G, re-centred on the moving mean
+  if (with_draws) {
+    double s = st.S[(size_t)f * kDraws + tid];
     double gr = st.G[cur][tid];
-    for (int r = 0; r < nranks; ++r) {
-      const PartView pv = view_part(partials + (size_t)r * rank_stride, p);
+    for (int b = 0; b < nb; ++b) {
+      const PartView pv = view_part(partials + (size_t)slot_map[b] * pstride, p);
       if (pv.hdr[0] > 0.0) {
-        const double m_old = mrun[(size_t)r * p + f], m_new = mrun[(size_t)(r + 1) * p + f];
+        const double m_old = mrun[(size_t)b * p + f], m_new = mrun[(size_t)(b + 1) * p + f];
         const double g2 = pv.G[tid];
         s += (m_old - m_new) * gr + pv.S[(size_t)f * kDraws + tid] + (pv.mean[f] - m_new) * g2;
         gr += g2;
       }
+      if (zsq != nullptr && b >= own0 && b < own1) {
+        const double nn = nrun[b + 1];
+        const double z = s / sqrt(nn * (nn - 1.0));
+        zsq[((size_t)(b - own0) * p + f) * kDraws + tid] = z * z;
+      }
     }
-    st.S[nxt][(size_t)f * kDraws + tid] = s;
+    st.S[(size_t)f * kDraws + tid] = s;
     if (f == 0) st.G[nxt][tid] = gr;
-    const double z = s * scale;
-    zsq[(size_t)f * kDraws + tid] = z * z;
-    sortbuf[tid] = fabs(z);
-    bitonic_sort_1024(sortbuf, tid);
-    if (tid == 0) st.feat_err_tmp[f] = quantile95_sorted(sortbuf);
   }
-  // ---- last CTA: overall error + commit
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  double overall = 0.0;
-  if (est) {
-    double ss = 0.0;
-    for (int ff = 0; ff < p; ++ff) ss += __ldcg(zsq + (size_t)ff * kDraws + tid);
-    sortbuf[tid] = sqrt(ss);
-    bitonic_sort_1024(sortbuf, tid);
-    overall = quantile95_sorted(sortbuf);
-    for (int j = tid; j < p; j += blockDim.x) st.feat_err[j] = __ldcg(st.feat_err_tmp + j);
+}
+
+// 0.95 quantiles of the error draws of `nown` batches: grid (p + 1, nown), block 1024.
+// CTA (f < p, b): |z_sf| over the draws -> feat_out[b][f];  CTA (p, b): |z_s|_2 -> overall_out[b].
+// Sorting z^2 and taking the square root of the two order statistics before interpolating is the
+// same as numpy.quantile(|z|, 0.95).
+__global__ void __launch_bounds__(1024) est_quantile_kernel(int p, const double *zsq, double *overall_out,
+                                                             double *feat_out) {
+  __shared__ double sortbuf[kDraws];
+  const int f = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const double *zb = zsq + (size_t)b * p * kDraws;
+  double v;
+  if (f < p) {
+    v = zb[(size_t)f * kDraws + tid];
+  } else {
+    v = 0.0;
+    for (int ff = 0; ff < p; ++ff) v += zb[(size_t)ff * kDraws + tid];
   }
-  __syncthreads();
+  sortbuf[tid] = v;
+  bitonic_sort_1024(sortbuf, tid);
   if (tid == 0) {
-    *ticket = 0;
-    st.hdr[H_N] = ntot;
-    st.hdr[H_CUR] = (double)nxt;
-    if (est) {
-      st.hdr[H_OVERALL] = overall;
-      const int nh = (int)st.hdr[H_NHIST];
-      if (nh < (int)st.hdr[H_MAXH]) st.err_hist[nh] = overall;
-      st.hdr[H_NHIST] = (double)(nh + 1);
-      if (overall < st.hdr[H_TOL]) st.hdr[H_STOP] = 1.0;
-    }
+    const double pos = (double)(kDraws - 1) * 0.95;
+    const int lo = (int)floor(pos);
+    const double t = pos - (double)lo;
+    const double a = sqrt(sortbuf[lo]), c = sqrt(sortbuf[lo + 1]);
+    const double q = c - (c - a) * (1.0 - t);
+    if (f < p) feat_out[(size_t)b * p + f] = q;
+    else overall_out[b] = q;
   }
-}
-
-__global__ void est_init_kernel(double *state, size_t total, int max_batches, double tol, int est) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  double v = 0.0;
-  if (i == H_TOL) v = tol;
-  if (i == H_EST) v = est ? 1.0 : 0.0;
-  if (i == H_MAXH) v = (double)max_batches;
-  state[i] = v;
-}
-
-__global__ void est_read_kernel(const double *state, int p, int max_batches, double *summary4,
-                                double *mean, double *feat_err, double *err_hist, double *cov) {
-  StateView st = view_state(const_cast<double *>(state), p, max_batches);
-  const int cur = (int)st.hdr[H_CUR];
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) {
-    summary4[0] = st.hdr[H_N];
-    summary4[1] = st.hdr[H_STOP];
-    summary4[2] = st.hdr[H_NHIST];
-    summary4[3] = st.hdr[H_OVERALL];
-  }
-  if (i < (size_t)p) {
-    mean[i] = st.mean[cur][i];
-    feat_err[i] = st.feat_err[i];
-  }
-  if (i < (size_t)max_batches) err_hist[i] = st.err_hist[i];
-  if (cov && i < (size_t)p * p) cov[i] = st.cov[cur][i];
 }
 
 // ---------------------------------------------------------------- history / merge / epilogue
@@ -411,6 +354,9 @@ __global__ void __launch_bounds__(512) theta_r2_kernel(int p, const double *Rtr,
   }
   __syncthreads();
   const int n = p + (p & 1);
+  // stop when every pair is orthogonal to ~sqrt(p) eps (the dgesvj criterion); a tighter bound
+  // sits below the round-off of the dot products and the sweeps never end
+  const double jtol = 4.0 * 2.220446049250313e-16 * sqrt((double)p);
   for (int sweep = 0; sweep < 40; ++sweep) {
     if (tid == 0) s_rot = 0;
     __syncthreads();
@@ -431,7 +377,7 @@ __global__ void __launch_bounds__(512) theta_r2_kernel(int p, const double *Rtr,
         al = warp_sum(al);
         be = warp_sum(be);
         ga = warp_sum(ga);
-        if (fabs(ga) > 1e-15 * sqrt(al * be) && ga != 0.0) {
+        if (fabs(ga) > jtol * sqrt(al * be) && ga != 0.0) {
           const double zeta = (be - al) / (2.0 * ga);
           const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
           const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
@@ -517,23 +463,13 @@ __global__ void __launch_bounds__(512) theta_r2_kernel(int p, const double *Rtr,
 
 using namespace lsspa;
 
-extern "C" size_t lsspa_estimator_state_bytes(int p, int max_batches) {
-  if (p < 1 || max_batches < 0) return 0;
-  return state_doubles(p, max_batches) * sizeof(double);
+extern "C" size_t lsspa_estimator_state_bytes(int p) {
+  if (p < 1) return 0;
+  return state_doubles(p) * sizeof(double);
 }
 
 extern "C" int64_t lsspa_estimator_partial_doubles(int p) {
   return p < 1 ? 0 : (int64_t)partial_doubles(p);
-}
-
-extern "C" int lsspa_estimator_init(void *state, int p, int max_batches, double tolerance, int estimate_errors,
-                                    void *stream) {
-  if (!state || p < 1 || max_batches < 0) return LSSPA_E_BADARG;
-  const size_t total = state_doubles(p, max_batches);
-  est_init_kernel<<<(unsigned)ceil_div((int64_t)total, 256), 256, 0, as_stream(stream)>>>(
-      reinterpret_cast<double *>(state), total, max_batches, tolerance, estimate_errors);
-  LSSPA_LAUNCH_CHECK();
-  return LSSPA_OK;
 }
 
 extern "C" int lsspa_estimator_partials(int p, const double *lifts, const int64_t *batch_desc, int nbatch,
@@ -559,35 +495,35 @@ extern "C" int lsspa_estimator_partials(int p, const double *lifts, const int64_
   return LSSPA_OK;
 }
 
-extern "C" int lsspa_estimator_update(void *state, int p, int max_batches, const double *partials,
-                                      int nbatch, int nranks, int estimate_errors, void *stream) {
-  if (!state || !partials || p < 1 || nbatch < 0 || nranks < 1) return LSSPA_E_BADARG;
-  cudaStream_t st = as_stream(stream);
-  const size_t pstride = partial_doubles(p);
-  // gathered layout: partials[rank][batch][block]
-  const size_t rank_stride = (size_t)nbatch * pstride;
-  const size_t smem = ((size_t)kDraws + (size_t)(nranks + 1) * p + (nranks + 1) + 8) * sizeof(double);
-  LSSPA_CUDA_TRY(cudaFuncSetAttribute(est_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  (void)estimate_errors;
-  StateView sv = view_state(reinterpret_cast<double *>(state), p, max_batches);
-  for (int b = 0; b < nbatch; ++b) {
-    est_step_kernel<<<p, kDraws, smem, st>>>(reinterpret_cast<double *>(state), p, max_batches,
-                                             partials + (size_t)b * pstride, rank_stride, nranks, sv.zsq,
-                                             reinterpret_cast<unsigned int *>(sv.ticket));
-    LSSPA_LAUNCH_CHECK();
-  }
+extern "C" int lsspa_estimator_max_batches(int p) {
+  // running means of all batches of one absorb call live in shared memory: (nb + 1) * (p + 1) doubles
+  const DeviceInfo &d = device_info();
+  const size_t limit = (size_t)(d.smem_optin > 0 ? d.smem_optin : 227 * 1024) - 1024;
+  long nb = (long)(limit / ((size_t)(p + 1) * sizeof(double))) - 1;
+  if (nb > 4096) nb = 4096;
+  return nb < 1 ? 0 : (int)nb;
+}
+
+extern "C" int lsspa_estimator_absorb(void *state, int p, int cur, double n_before, const double *partials,
+                                      const int32_t *slot_map, int nb, int own0, int own1, double *zsq,
+                                      int with_draws, void *stream) {
+  if (!state || !partials || !slot_map || p < 1 || nb < 0 || (cur != 0 && cur != 1)) return LSSPA_E_BADARG;
+  if (nb == 0) return LSSPA_OK;
+  if (nb > lsspa_estimator_max_batches(p)) return LSSPA_E_UNSUPPORTED;
+  const size_t smem = ((size_t)(nb + 1) * p + (nb + 1) + 8) * sizeof(double);
+  LSSPA_CUDA_TRY(cudaFuncSetAttribute(est_absorb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  est_absorb_kernel<<<p, kDraws, smem, as_stream(stream)>>>(reinterpret_cast<double *>(state), p, cur, n_before,
+                                                            partials, partial_doubles(p), slot_map, nb, own0,
+                                                            own1, zsq, with_draws);
+  LSSPA_LAUNCH_CHECK();
   return LSSPA_OK;
 }
 
-extern "C" int lsspa_estimator_read(const void *state, int p, int max_batches, double *summary4, double *mean,
-                                    double *feat_err, double *err_hist, double *cov_or_null, void *stream) {
-  if (!state || !summary4 || !mean || !feat_err || p < 1) return LSSPA_E_BADARG;
-  if (max_batches > 0 && !err_hist) return LSSPA_E_BADARG;
-  size_t n = (size_t)p;
-  if ((size_t)max_batches > n) n = (size_t)max_batches;
-  if (cov_or_null && (size_t)p * p > n) n = (size_t)p * p;
-  est_read_kernel<<<(unsigned)ceil_div((int64_t)n, 256), 256, 0, as_stream(stream)>>>(
-      reinterpret_cast<const double *>(state), p, max_batches, summary4, mean, feat_err, err_hist, cov_or_null);
+extern "C" int lsspa_estimator_quantiles(int p, const double *zsq, int nown, double *overall_out,
+                                         double *feat_out, void *stream) {
+  if (!zsq || !overall_out || !feat_out || p < 1 || nown < 0) return LSSPA_E_BADARG;
+  if (nown == 0) return LSSPA_OK;
+  est_quantile_kernel<<<dim3(p + 1, nown), kDraws, 0, as_stream(stream)>>>(p, zsq, overall_out, feat_out);
   LSSPA_LAUNCH_CHECK();
   return LSSPA_OK;
 }

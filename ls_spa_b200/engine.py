@@ -171,8 +171,8 @@ class CudaBackend:
     def lifts(self, prob, perms, antithetical):
         return ops.lifts(prob, perms, antithetical)
 
-    def make_estimator(self, cfg: JobConfig, max_batches):
-        return ops.Estimator(cfg.p, max_batches, cfg.tolerance, cfg.seed, cfg.estimate_errors, self.device)
+    def make_estimator(self, cfg: JobConfig):
+        return ops.Estimator(cfg.p, cfg.seed, cfg.estimate_errors, self.device)
 
     def prefix_means(self, rows, carry_sum, carry_count):
         out = torch.empty_like(rows)
@@ -221,31 +221,28 @@ def reduce_problem(backend, coll: Collective, X_train, X_test, y_train, y_test, 
 
 
 def run_samples(backend, coll: Collective, prob, source: PermutationSource, cfg: JobConfig):
-    """The estimator loop.  Returns (estimator_read_dict, history or None, samples_done)."""
+    """The estimator loop (reference ls_spa/ls_spa.py:196-236), one super-batch at a time.
+
+    Returns (result dict, history or None, samples drawn).  result: count, mean, overall_error,
+    attribution_errors, error_history (numpy)."""
     p, W, rank = cfg.p, coll.world, coll.rank
-    bs = cfg.batch_size
     limit = cfg.max_samples
     if source.total is not None:
         limit = source.total if limit is None else min(limit, source.total)
     tgt = target_samples(p)
-    if not cfg.estimate_errors:
-        bs_eff = tgt                       # batch boundaries are irrelevant without estimates
-    else:
-        bs_eff = bs
+    bs_eff = cfg.batch_size if cfg.estimate_errors else tgt   # no estimates -> boundaries are irrelevant
     g_local = max(1, -(-tgt // bs_eff))
     sb_samples = g_local * W * bs_eff
-    if limit is not None:
-        max_batches = -(-limit // bs_eff) + 2
-    else:
-        max_batches = 1 << 16
-    est = backend.make_estimator(cfg, max_batches)
+    est = backend.make_estimator(cfg)
     quirk = (cfg.max_samples - 1) if (cfg.penultimate_check and cfg.max_samples and cfg.estimate_errors) else None
+    can_stop = cfg.estimate_errors and cfg.tolerance > 0.0
 
     hist_chunks = [] if cfg.return_history else None
     carry_sum = backend.zeros(p) if cfg.return_history else None
-    pos = 0
-    can_stop = cfg.estimate_errors and cfg.tolerance > 0.0
-    while limit is None or pos < limit:
+    err_parts, feat_last = [], None        # device tensors of per-batch errors (read at the end)
+    err_hist = []                          # host copy, filled eagerly only when a stop is possible
+    pos, stopped = 0, False
+    while (limit is None or pos < limit) and not stopped:
         want = sb_samples if limit is None else min(sb_samples, limit - pos)
         perms_all = None
         if not source.random_access:
@@ -256,7 +253,8 @@ def run_samples(backend, coll: Collective, prob, source: PermutationSource, cfg:
         if n_sb == 0:
             break
         batches = split_batches(pos, n_sb, bs_eff, quirk)
-        runs, per = contiguous_runs(len(batches), W)
+        nb = len(batches)
+        runs, per = contiguous_runs(nb, W)
         b0, b1 = runs[rank]
         mine = batches[b0:b1]
         my_start = mine[0][0] if mine else pos
@@ -275,13 +273,16 @@ def run_samples(backend, coll: Collective, prob, source: PermutationSource, cfg:
         part = est.partials(rows, desc)
         if W > 1:
             if part.shape[0] < per:
-                pad = torch.zeros((per - part.shape[0], part.shape[1]), dtype=part.dtype, device=part.device)
+                pad = backend.zeros(per - part.shape[0], part.shape[1])
                 part = torch.cat([part, pad], 0)
-            gathered = coll.all_gather(part)
-            for r, (rb0, rb1) in enumerate(runs):
-                est.update(gathered[r], rb1 - rb0)
+            gathered = coll.all_gather(part)                     # (W, per, PD)
+            slots = [r * per + i for r, (a, b) in enumerate(runs) for i in range(b - a)]
         else:
-            est.update(part, len(mine))
+            gathered, slots = part, list(range(nb))
+        counts = [n for _, n in batches]
+        snap = est.snapshot() if can_stop else None
+        overall, feat = est.absorb(gathered, slots, counts, own=(b0, b1), emit=cfg.estimate_errors)
+        rows_in_order = None
         if hist_chunks is not None:
             if W > 1:
                 per_rows = max(sum(n for _, n in batches[a:b]) for a, b in runs)
@@ -292,19 +293,47 @@ def run_samples(backend, coll: Collective, prob, source: PermutationSource, cfg:
                     [allrows[r, :sum(n for _, n in batches[a:b])] for r, (a, b) in enumerate(runs)], 0)
             else:
                 rows_in_order = rows
-            hist_chunks.append(backend.prefix_means(rows_in_order, carry_sum, pos))
+        keep = nb
+        if cfg.estimate_errors:
+            if W > 1:
+                ov = backend.zeros(per)
+                ft = backend.zeros(per, p)
+                if overall is not None:
+                    ov[: b1 - b0] = overall
+                    ft[: b1 - b0] = feat
+                ov_all, ft_all = coll.all_gather(ov), coll.all_gather(ft)
+                overall = torch.cat([ov_all[r, : b - a] for r, (a, b) in enumerate(runs)], 0)
+                feat = torch.cat([ft_all[r, : b - a] for r, (a, b) in enumerate(runs)], 0)
+            if can_stop:
+                errs = overall.cpu().numpy()                      # the only host sync of the super-batch
+                hit = np.nonzero(errs < cfg.tolerance)[0]         # strict <, reference :229
+                if hit.size:
+                    keep = int(hit[0]) + 1
+                    stopped = True
+                    if keep < nb:                                 # stop inside the super-batch: replay
+                        est.restore(snap)
+                        est.absorb(gathered, slots[:keep], counts[:keep], emit=False)
+                err_hist.extend(errs[:keep].tolist())
+                feat_last = feat[keep - 1]
+            else:
+                err_parts.append(overall)
+                feat_last = feat[nb - 1]
+        if hist_chunks is not None:
+            kept_rows = sum(counts[:keep])
+            hist_chunks.append(backend.prefix_means(rows_in_order[:kept_rows].contiguous(), carry_sum, pos))
         pos += n_sb
         if perms_all is not None and n_sb < want:
             break                                  # explicit stream ran dry
-        if can_stop:
-            _, stopped = est.peek_stop()
-            if stopped:
-                break
     if hasattr(source, "check"):
         source.check()
     res = est.read()
+    if err_parts:
+        err_hist = torch.cat(err_parts).cpu().numpy().tolist()
+    res["error_history"] = np.asarray(err_hist, dtype=np.float64)
+    res["n_history"] = len(err_hist)
+    res["overall_error"] = float(err_hist[-1]) if err_hist else 0.0
+    res["attribution_errors"] = (feat_last.cpu().numpy().copy() if feat_last is not None else np.zeros(p))
     history = None
     if hist_chunks is not None:
-        history = (torch.cat(hist_chunks, 0)[: res["count"]].cpu().numpy()
-                   if hist_chunks else np.zeros((0, p)))
+        history = (torch.cat(hist_chunks, 0)[: res["count"]].cpu().numpy() if hist_chunks else np.zeros((0, p)))
     return res, history, pos

@@ -225,20 +225,21 @@ def theta_r2(prob: ReducedProblem):
 # estimator
 # ---------------------------------------------------------------------------
 class Estimator:
-    """Device-resident (count, mean, cov, error-draw sums, stop flag, error history)."""
+    """Device-resident running statistics of the lift vectors: count, mean, biased covariance and
+    the draw sums behind the error estimate.  The host side keeps the sample count, the error
+    history and the stop decision (see engine.run_samples)."""
 
-    def __init__(self, p: int, max_batches: int, tolerance: float, seed: int, estimate_errors: bool, device):
+    def __init__(self, p: int, seed: int, estimate_errors: bool, device):
         lib = _lib()
-        self.p, self.max_batches = p, max(int(max_batches), 1)
+        self.p = p
         self.estimate = bool(estimate_errors)
         self.seed = int(seed) & ((1 << 64) - 1)
         self.device = device
-        nbytes = lib.lsspa_estimator_state_bytes(p, self.max_batches)
-        self.state = torch.empty(nbytes // 8, dtype=torch.float64, device=device)
-        check(lib.lsspa_estimator_init(self.state.data_ptr(), p, self.max_batches, float(tolerance),
-                                       1 if self.estimate else 0, _stream()), "lsspa_estimator_init")
-        _count(1)
+        self.state = torch.zeros(lib.lsspa_estimator_state_bytes(p) // 8, dtype=torch.float64, device=device)
+        self.cur = 0              # which mean / G buffer is live
+        self.count = 0            # samples folded in so far
         self.partial_doubles = int(lib.lsspa_estimator_partial_doubles(p))
+        self.max_batches = int(lib.lsspa_estimator_max_batches(p))
 
     def partials(self, lift_rows: torch.Tensor, batch_desc) -> torch.Tensor:
         """batch_desc: list of (first_row, count, global_first_index) -> (nbatch, partial_doubles)."""
@@ -253,38 +254,58 @@ class Estimator:
         _count(3 if self.estimate else 2)
         return out
 
-    def update(self, partials: torch.Tensor, nbatch: int, nranks: int = 1) -> None:
-        if nbatch == 0:
-            return
-        check(_lib().lsspa_estimator_update(self.state.data_ptr(), self.p, self.max_batches,
-                                            partials.data_ptr(), nbatch, nranks,
-                                            1 if self.estimate else 0, _stream()), "lsspa_estimator_update")
-        _count(nbatch)
+    def snapshot(self):
+        return self.state.clone(), self.cur, self.count
+
+    def restore(self, snap) -> None:
+        self.state.copy_(snap[0])
+        self.cur, self.count = snap[1], snap[2]
+
+    def absorb(self, partials: torch.Tensor, slots, counts, own=(0, 0), emit: bool = False):
+        """Fold the batches whose partial blocks are partials[slots[b]] (counts[b] samples each), in
+        order.  With emit=True returns (overall[own1-own0], per_feature[own1-own0, p]) device tensors
+        holding the 0.95-quantile error estimates after each batch b in [own0, own1)."""
+        lib = _lib()
+        nb = len(slots)
+        own0, own1 = own
+        emit = emit and self.estimate and own1 > own0
+        overall = feat = None
+        if emit:
+            overall = torch.empty(own1 - own0, dtype=torch.float64, device=self.device)
+            feat = torch.empty((own1 - own0, self.p), dtype=torch.float64, device=self.device)
+        pos = 0
+        flat = partials.reshape(-1, self.partial_doubles)
+        while pos < nb:
+            n = min(self.max_batches, nb - pos)
+            smap = torch.tensor(slots[pos:pos + n], dtype=torch.int32).to(self.device, non_blocking=True)
+            o0, o1 = max(own0, pos) - pos, min(own1, pos + n) - pos
+            zsq = None
+            if emit and o1 > o0:
+                zsq = torch.empty((o1 - o0, self.p, ERR_DRAWS), dtype=torch.float64, device=self.device)
+            check(lib.lsspa_estimator_absorb(self.state.data_ptr(), self.p, self.cur, float(self.count),
+                                             flat.data_ptr(), smap.data_ptr(), n, max(o0, 0), max(o1, 0),
+                                             _ptr(zsq), 1 if self.estimate else 0, _stream()),
+                  "lsspa_estimator_absorb")
+            _count(1)
+            if zsq is not None:
+                lo = pos + o0 - own0
+                check(lib.lsspa_estimator_quantiles(self.p, zsq.data_ptr(), o1 - o0, overall[lo:].data_ptr(),
+                                                    feat[lo:].data_ptr(), _stream()), "lsspa_estimator_quantiles")
+                _count(1)
+            self.cur ^= 1
+            self.count += int(sum(counts[pos:pos + n]))
+            pos += n
+        return overall, feat
 
     def read(self, want_cov: bool = False):
-        """-> dict(count, stopped, n_history, overall_error, mean, attribution_errors, error_history[, cov])
-        (one device->host sync)."""
-        p, H = self.p, self.max_batches
-        buf = torch.empty(4 + 2 * p + H + (p * p if want_cov else 0), dtype=torch.float64, device=self.device)
-        summary, mean, ferr, hist = buf[:4], buf[4:4 + p], buf[4 + p:4 + 2 * p], buf[4 + 2 * p:4 + 2 * p + H]
-        cov = buf[4 + 2 * p + H:] if want_cov else None
-        check(_lib().lsspa_estimator_read(self.state.data_ptr(), p, H, summary.data_ptr(), mean.data_ptr(),
-                                          ferr.data_ptr(), hist.data_ptr(), _ptr(cov), _stream()),
-              "lsspa_estimator_read")
-        _count(1)
-        host = buf.cpu().numpy()
-        nh = int(host[2])
-        res = dict(count=int(host[0]), stopped=bool(host[1]), n_history=nh, overall_error=float(host[3]),
-                   mean=host[4:4 + p].copy(), attribution_errors=host[4 + p:4 + 2 * p].copy(),
-                   error_history=host[4 + 2 * p:4 + 2 * p + min(nh, H)].copy())
+        """-> dict(count, mean[, cov]) as numpy (one device->host sync)."""
+        p = self.p
+        mean = self.state[self.cur * p:(self.cur + 1) * p].cpu().numpy().copy()
+        res = dict(count=self.count, mean=mean)
         if want_cov:
-            res["cov"] = host[4 + 2 * p + H:].reshape(p, p).copy()
+            off = 2 * p + 2 * ERR_DRAWS
+            res["cov"] = self.state[off:off + p * p].reshape(p, p).cpu().numpy().copy()
         return res
-
-    def peek_stop(self):
-        """(count, stopped) with one small device->host copy."""
-        h = self.state[:2].cpu()
-        return int(h[0]), bool(h[1])
 
 
 def prefix_means(lift_rows: torch.Tensor, carry_sum: torch.Tensor, carry_count: int, out: torch.Tensor) -> None:

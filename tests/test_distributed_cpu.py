@@ -26,10 +26,11 @@ class FakeProblem:
 
 
 class FakeEstimator:
-    def __init__(self, p, max_batches, tol):
-        self.p, self.tol = p, tol
-        self.n, self.mean, self.cov = 0, np.zeros(p), np.zeros((p, p))
-        self.hist, self.stopped = [], False
+    """Same interface as ops.Estimator (partials / snapshot / restore / absorb / read)."""
+
+    def __init__(self, p):
+        self.p = p
+        self.count, self.mean, self.cov = 0, np.zeros(p), np.zeros((p, p))
         self.partial_doubles = 1 + p + p * p
 
     def partials(self, rows, desc):
@@ -43,27 +44,30 @@ class FakeEstimator:
                 out[b, 1 + self.p:] = torch.from_numpy(np.cov(blk, rowvar=False, bias=True).reshape(-1))
         return out
 
-    def update(self, partials, nbatch, nranks=1):
-        for b in range(nbatch):
-            if self.stopped:
-                return
-            blk = partials[b].numpy()
-            n2, m2, c2 = int(blk[0]), blk[1:1 + self.p], blk[1 + self.p:].reshape(self.p, self.p)
-            self.cov = lo.merge_sample_cov(self.mean, m2, self.cov, c2, self.n, n2)
-            self.mean = lo.merge_sample_mean(self.mean, m2, self.n, n2)
-            self.n += n2
-            err = float(np.sqrt(np.trace(self.cov) / max(self.n - 1, 1)))   # deterministic stand-in
-            self.hist.append(err)
-            if err < self.tol:
-                self.stopped = True
+    def snapshot(self):
+        return self.count, self.mean.copy(), self.cov.copy()
 
-    def peek_stop(self):
-        return self.n, self.stopped
+    def restore(self, snap):
+        self.count, self.mean, self.cov = snap[0], snap[1].copy(), snap[2].copy()
+
+    def absorb(self, partials, slots, counts, own=(0, 0), emit=False):
+        flat = partials.reshape(-1, self.partial_doubles).numpy()
+        errs = []
+        for b, slot in enumerate(slots):
+            blk = flat[slot]
+            n2, m2, c2 = int(blk[0]), blk[1:1 + self.p], blk[1 + self.p:].reshape(self.p, self.p)
+            assert n2 == counts[b]
+            self.cov = lo.merge_sample_cov(self.mean, m2, self.cov, c2, self.count, n2)
+            self.mean = lo.merge_sample_mean(self.mean, m2, self.count, n2)
+            self.count += n2
+            if emit and own[0] <= b < own[1]:
+                errs.append(float(np.sqrt(np.trace(self.cov) / max(self.count - 1, 1))))   # deterministic stand-in
+        if emit and own[1] > own[0]:
+            return torch.tensor(errs, dtype=torch.float64), torch.zeros((len(errs), self.p), dtype=torch.float64)
+        return None, None
 
     def read(self):
-        return dict(count=self.n, stopped=self.stopped, n_history=len(self.hist),
-                    overall_error=self.hist[-1] if self.hist else 0.0, mean=self.mean.copy(),
-                    attribution_errors=np.zeros(self.p), error_history=np.array(self.hist))
+        return dict(count=self.count, mean=self.mean.copy())
 
 
 class OracleBackend:
@@ -112,8 +116,8 @@ class OracleBackend:
             out.append(l)
         return torch.from_numpy(np.array(out).reshape(-1, perms.shape[1]))
 
-    def make_estimator(self, cfg, max_batches):
-        return FakeEstimator(cfg.p, max_batches, cfg.tolerance)
+    def make_estimator(self, cfg):
+        return FakeEstimator(cfg.p)
 
     def prefix_means(self, rows, carry_sum, carry_count):
         c = carry_sum.numpy() + np.cumsum(rows.numpy(), 0)

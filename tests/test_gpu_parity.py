@@ -237,16 +237,18 @@ def test_estimator_state_matches_merge_formulas(T):
     p, n = 23, 300
     rows = rng.standard_normal((n, p)) * rng.uniform(0.1, 3.0, p) + rng.standard_normal(p)
     dev = T.device("cuda")
-    est = ops.Estimator(p, 16, 0.0, 99, True, dev)
+    est = ops.Estimator(p, 99, True, dev)
     d = T.from_numpy(rows).to(dev)
     cuts = [(0, 100, 0), (100, 37, 100), (137, 163, 137)]
-    est.update(est.partials(d, cuts), len(cuts))
+    overall, feat = est.absorb(est.partials(d, cuts), [0, 1, 2], [100, 37, 163], own=(0, 3), emit=True)
     out = est.read(want_cov=True)
+    out["attribution_errors"] = feat[-1].cpu().numpy()
+    out["overall_error"] = float(overall[-1].item())
     mean, cov = np.zeros(p), np.zeros((p, p))
     for i, r in enumerate(rows, 1):
         cov = lo.merge_sample_cov(mean, r, cov, np.zeros((p, p)), i - 1, 1)
         mean = lo.merge_sample_mean(mean, r, i - 1, 1)
-    assert out["count"] == n and out["n_history"] == 3
+    assert out["count"] == n and overall.shape == (3,)
     assert scaled_err(out["mean"], mean) < 1e-12
     assert scaled_err(out["cov"], cov) < 1e-11
     # the error draws have covariance unbiased_cov / n: compare with the analytic quantiles
