@@ -53,6 +53,17 @@ def read_peaks():
     return peaks
 
 
+def lifts_dram_bytes_per_perm():
+    """DRAM bytes (read + write) per permutation evaluation of the lift kernel, from the committed
+    `ncu --set full` capture (profiles/r01_lifts_ncu_summary.json); None if absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_lifts_ncu_summary.json")) as f:
+            d = json.load(f)
+        return float(d["dram_bytes_per_launch"]) / float(d["permutation_evaluations_per_launch"])
+    except Exception:
+        return None
+
+
 def fp64_peak_tflops():
     """FP64 pipe peak: live run of tools/bin/fp64_peak (DFMA and DMMA loops), else the
     committed measurement in profiles/."""
@@ -144,7 +155,18 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner to stdout on first use: keep stdout for the one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     import ls_spa_b200 as L
     from ls_spa_b200 import engine, ops
 
@@ -226,6 +248,8 @@ def run_gpu(args):
         peaks = read_peaks()
         fp64_peak, fp64_src = fp64_peak_tflops()
         ach = FLOP_PER_PERM * lift_perms / (lift_ms * 1e-3) / 1e12 if lift_ms > 0 else 0.0
+        bpp = lifts_dram_bytes_per_perm()
+        traffic = bpp * lift_perms / max(len(trace), 1) if bpp is not None else None
         out = {
             "metric": "permutations/sec (LS-SPA, p=100, N=M=1e6 rows, reduction + permutohedron samples + estimator)",
             "value": value, "unit": "permutations/s", "n_gpus": world, "steps": args.steps,
@@ -241,7 +265,9 @@ def run_gpu(args):
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "pipe": "fp64 (DFMA/DMMA share one pipe; tcgen05 has no fp64)",
                          "kernel": "lifts_kernel", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": ach / fp64_peak if fp64_peak else None, "traffic": None,
+                         "frac": ach / fp64_peak if fp64_peak else None, "traffic": traffic,
+                         "traffic_note": "dram read+write bytes per launch from the committed ncu --set full capture, "
+                                         "scaled to this launch size; algorithmic HBM bytes/launch = 1200 B x evaluations / 2",
                          "peak_source": fp64_src, "kernel_ms_per_step": lift_ms / args.steps,
                          "kernel_share_of_step": lift_ms / ms_total,
                          "algorithmic_flop_per_permutation": FLOP_PER_PERM},
