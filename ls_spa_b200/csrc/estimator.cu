@@ -344,93 +344,135 @@ __global__ void __launch_bounds__(512) theta_r2_kernel(int p, const double *Rtr,
   __shared__ int s_rot;
   const int tid = threadIdx.x, nt = blockDim.x;
   const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
-  // Jacobi work matrices: shared memory when 2 p^2 doubles fit (p <= ~118), else the workspace
-  double *A = in_smem ? red + 64 : ws;
-  double *V = A + (size_t)p * p;
-  for (int e = tid; e < p * p; e += nt) {
-    const int j = e / p, i = e - j * p;
-    A[e] = (i <= j) ? Rtr[e] : 0.0;
-    V[e] = (i == j) ? 1.0 : 0.0;
-  }
-  __syncthreads();
-  const int n = p + (p & 1);
-  // stop when every pair is orthogonal to ~sqrt(p) eps (the dgesvj criterion); a tighter bound
-  // sits below the round-off of the dot products and the sweeps never end
-  const double jtol = 4.0 * 2.220446049250313e-16 * sqrt((double)p);
-  for (int sweep = 0; sweep < 40; ++sweep) {
-    if (tid == 0) s_rot = 0;
+  // Fast path: when the diagonal of R_tr shows no sign of rank deficiency (min |R_kk| > 1e-7 max),
+  // lstsq's singular-value cut-off (eps * p * sigma_max) is not active and the minimum-norm
+  // solution is R^-1 c: plain back substitution.  Otherwise the Jacobi SVD below.
+  __shared__ int s_fast;
+  {
+    double dmin = 1e300, dmax = 0.0;
+    for (int i = tid; i < p; i += nt) {
+      const double d = fabs(Rtr[(size_t)i * p + i]);
+      dmin = fmin(dmin, d);
+      dmax = fmax(dmax, d);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      dmin = fmin(dmin, __shfl_xor_sync(kFull, dmin, o));
+      dmax = fmax(dmax, __shfl_xor_sync(kFull, dmax, o));
+    }
+    if (lane == 0) {
+      red[warp] = dmin;
+      red[32 + warp] = dmax;
+    }
     __syncthreads();
-    for (int s = 0; s < n - 1; ++s) {
-      for (int k = warp; k < n / 2; k += nwarps) {
-        int i = (k == 0) ? n - 1 : (s + k) % (n - 1);
-        int j = (k == 0) ? s : (s - k + (n - 1)) % (n - 1);
-        if (i > j) { const int t = i; i = j; j = t; }
-        if (j >= p) continue;  // dummy column of an odd-sized tournament
-        double *ai = A + (size_t)i * p, *aj = A + (size_t)j * p;
-        double al = 0.0, be = 0.0, ga = 0.0;
-        for (int r = lane; r < p; r += kWarp) {
-          const double x = ai[r], y = aj[r];
-          al = fma(x, x, al);
-          be = fma(y, y, be);
-          ga = fma(x, y, ga);
-        }
-        al = warp_sum(al);
-        be = warp_sum(be);
-        ga = warp_sum(ga);
-        if (fabs(ga) > jtol * sqrt(al * be) && ga != 0.0) {
-          const double zeta = (be - al) / (2.0 * ga);
-          const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-          const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
-          double *vi = V + (size_t)i * p, *vj = V + (size_t)j * p;
-          for (int r = lane; r < p; r += kWarp) {
-            const double x = ai[r], y = aj[r];
-            ai[r] = c * x - sn * y;
-            aj[r] = sn * x + c * y;
-            const double u = vi[r], w = vj[r];
-            vi[r] = c * u - sn * w;
-            vj[r] = sn * u + c * w;
-          }
-          if (lane == 0) s_rot = 1;
-        }
+    if (tid == 0) {
+      for (int w = 1; w < nwarps; ++w) {
+        dmin = fmin(dmin, red[w]);
+        dmax = fmax(dmax, red[32 + w]);
       }
+      s_fast = (dmin > 1e-7 * dmax) ? 1 : 0;
+    }
+    __syncthreads();
+  }
+  if (s_fast) {
+    for (int i = tid; i < p; i += nt) coef[i] = ctr[i];
+    __syncthreads();
+    for (int j = p - 1; j >= 0; --j) {
+      if (tid == 0) theta[j] = coef[j] / Rtr[(size_t)j * p + j];
+      __syncthreads();
+      const double tj = theta[j];
+      for (int i = tid; i < j; i += nt) coef[i] = fma(-Rtr[(size_t)j * p + i], tj, coef[i]);
       __syncthreads();
     }
-    const int any = s_rot;
+  } else {
+    // Jacobi work matrices: shared memory when 2 p^2 doubles fit (p <= ~118), else the workspace
+    double *A = in_smem ? red + 64 : ws;
+    double *V = A + (size_t)p * p;
+    for (int e = tid; e < p * p; e += nt) {
+      const int j = e / p, i = e - j * p;
+      A[e] = (i <= j) ? Rtr[e] : 0.0;
+      V[e] = (i == j) ? 1.0 : 0.0;
+    }
     __syncthreads();
-    if (!any) break;
-  }
-  // coef_i = (a_i . c) / sigma_i^2 for the retained singular directions
-  double smax = 0.0;
-  for (int i = warp; i < p; i += nwarps) {
-    const double *ai = A + (size_t)i * p;
-    double nn = 0.0, dc = 0.0;
-    for (int r = lane; r < p; r += kWarp) {
-      nn = fma(ai[r], ai[r], nn);
-      dc = fma(ai[r], ctr[r], dc);
+    const int n = p + (p & 1);
+    // stop when every pair is orthogonal to ~sqrt(p) eps (the dgesvj criterion); a tighter bound
+    // sits below the round-off of the dot products and the sweeps never end
+    const double jtol = 4.0 * 2.220446049250313e-16 * sqrt((double)p);
+    for (int sweep = 0; sweep < 40; ++sweep) {
+      if (tid == 0) s_rot = 0;
+      __syncthreads();
+      for (int s = 0; s < n - 1; ++s) {
+        for (int k = warp; k < n / 2; k += nwarps) {
+          int i = (k == 0) ? n - 1 : (s + k) % (n - 1);
+          int j = (k == 0) ? s : (s - k + (n - 1)) % (n - 1);
+          if (i > j) { const int t = i; i = j; j = t; }
+          if (j >= p) continue;  // dummy column of an odd-sized tournament
+          double *ai = A + (size_t)i * p, *aj = A + (size_t)j * p;
+          double al = 0.0, be = 0.0, ga = 0.0;
+          for (int r = lane; r < p; r += kWarp) {
+            const double x = ai[r], y = aj[r];
+            al = fma(x, x, al);
+            be = fma(y, y, be);
+            ga = fma(x, y, ga);
+          }
+          al = warp_sum(al);
+          be = warp_sum(be);
+          ga = warp_sum(ga);
+          if (fabs(ga) > jtol * sqrt(al * be) && ga != 0.0) {
+            const double zeta = (be - al) / (2.0 * ga);
+            const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+            const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+            double *vi = V + (size_t)i * p, *vj = V + (size_t)j * p;
+            for (int r = lane; r < p; r += kWarp) {
+              const double x = ai[r], y = aj[r];
+              ai[r] = c * x - sn * y;
+              aj[r] = sn * x + c * y;
+              const double u = vi[r], w = vj[r];
+              vi[r] = c * u - sn * w;
+              vj[r] = sn * u + c * w;
+            }
+            if (lane == 0) s_rot = 1;
+          }
+        }
+        __syncthreads();
+      }
+      const int any = s_rot;
+      __syncthreads();
+      if (!any) break;
     }
-    nn = warp_sum(nn);
-    dc = warp_sum(dc);
-    if (lane == 0) {
-      coef[i] = dc;
-      theta[i] = nn;  // sigma_i^2, reused as scratch
+    // coef_i = (a_i . c) / sigma_i^2 for the retained singular directions
+    double smax = 0.0;
+    for (int i = warp; i < p; i += nwarps) {
+      const double *ai = A + (size_t)i * p;
+      double nn = 0.0, dc = 0.0;
+      for (int r = lane; r < p; r += kWarp) {
+        nn = fma(ai[r], ai[r], nn);
+        dc = fma(ai[r], ctr[r], dc);
+      }
+      nn = warp_sum(nn);
+      dc = warp_sum(dc);
+      if (lane == 0) {
+        coef[i] = dc;
+        theta[i] = nn;  // sigma_i^2, reused as scratch
+      }
+      smax = fmax(smax, nn);
     }
-    smax = fmax(smax, nn);
+    if (lane == 0) red[warp] = smax;
+    __syncthreads();
+    smax = 0.0;
+    for (int w = 0; w < nwarps; ++w) smax = fmax(smax, red[w]);
+    const double rcond = 2.220446049250313e-16 * (double)p;
+    const double cut = smax * rcond * rcond;  // compare squared singular values
+    __syncthreads();
+    for (int i = tid; i < p; i += nt) coef[i] = (theta[i] > cut && theta[i] > 0.0) ? coef[i] / theta[i] : 0.0;
+    __syncthreads();
+    for (int r = tid; r < p; r += nt) {
+      double acc = 0.0;
+      for (int i = 0; i < p; ++i) acc = fma(V[(size_t)i * p + r], coef[i], acc);
+      theta[r] = acc;
+    }
+    __syncthreads();
   }
-  if (lane == 0) red[warp] = smax;
-  __syncthreads();
-  smax = 0.0;
-  for (int w = 0; w < nwarps; ++w) smax = fmax(smax, red[w]);
-  const double rcond = 2.220446049250313e-16 * (double)p;
-  const double cut = smax * rcond * rcond;  // compare squared singular values
-  __syncthreads();
-  for (int i = tid; i < p; i += nt) coef[i] = (theta[i] > cut && theta[i] > 0.0) ? coef[i] / theta[i] : 0.0;
-  __syncthreads();
-  for (int r = tid; r < p; r += nt) {
-    double acc = 0.0;
-    for (int i = 0; i < p; ++i) acc = fma(V[(size_t)i * p + r], coef[i], acc);
-    theta[r] = acc;
-  }
-  __syncthreads();
   double s_c = 0.0, s_r = 0.0;
   for (int i = tid; i < p; i += nt) {
     double pred = 0.0;
