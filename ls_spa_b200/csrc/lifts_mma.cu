@@ -297,6 +297,246 @@ __device__ __forceinline__ void trailing_tile(double *A, const double *V, const 
   }
 }
 
+// ---------------------------------------------------------------- cooperative panel (4 warps)
+// The reflector loop of a panel is a serial chain (norm -> sqrt/rcp -> dot -> update, ~1000 cycles
+// per reflector for one warp holding the whole strip).  Four "panel warps" share a strip by rows
+// (warp w holds tiles w, w+4, w+8, ... relative to the top tile): the per-reflector data work
+// shrinks 4x and the two reductions (column norm, dot products) are completed through a small
+// shared-memory exchange and a 128-thread named barrier.  The other four warps of the CTA apply
+// the previous panel to the remaining column tiles meanwhile.
+constexpr int kPW = 4;  // panel warps (warps 0..3)
+
+__device__ __forceinline__ void bar_panel() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+struct PanelXch {      // exchange scratch in shared memory (doubles)
+  double *pn;          // [2][kPW]      partial squared norms (double-buffered by reflector parity)
+  double *x0;          // [2]           pivot value
+  double *pw;          // [kPW][8]      partial dot products
+  double *gp;          // [kPW][64]     partial G / partial W^T (C layout)
+  double *vs;          // [kPW][8*KL]   per-warp u scratch column
+};
+
+// A2[:, tile j] -= U T^T (U^T A2[:, tile j]) for the reflectors of panel s, rows split over the
+// panel warps (cooperative version of trailing_tile)
+template <int KL>
+__device__ __forceinline__ void trailing_coop(double *A, const double *V, const double *Tb, const PanelXch &x,
+                                              int ld, int RT, int s, int j, int lane, int w) {
+  const int c = lane >> 2, q = lane & 3;
+  const int nt = RT - s;
+  double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+  for (int kk = 0; kk < KL; ++kk) {
+    const int k = w + kPW * kk;
+    if (k < nt) {
+      const double2 xx = ld_tile(A, ld, 8 * (s + k), 8 * j, c, q);
+      const double2 v = ld_vfrag(V, 8 * (s + k), c, q);
+      dmma(a0, a1, xx.x, v.x);
+      dmma(a0, a1, xx.y, v.y);
+    }
+  }
+  *reinterpret_cast<double2 *>(x.gp + w * 64 + c * 8 + 2 * q) = make_double2(a0, a1);
+  bar_panel();
+  a0 = 0.0;
+  a1 = 0.0;
+#pragma unroll
+  for (int ww = 0; ww < kPW; ++ww) {
+    const double2 t = *reinterpret_cast<const double2 *>(x.gp + ww * 64 + c * 8 + 2 * q);
+    a0 += t.x;
+    a1 += t.y;
+  }
+  const double2 tt = ld_tile(Tb, 8, 0, 0, c, q);
+  double w0 = 0.0, w1 = 0.0;  // W'^T = Wraw^T T
+  dmma(w0, w1, a0, tt.x);
+  dmma(w0, w1, a1, tt.y);
+  w0 = -w0;
+  w1 = -w1;
+#pragma unroll
+  for (int kk = 0; kk < KL; ++kk) {
+    const int k = w + kPW * kk;
+    if (k < nt) {
+      double2 cf = ld_tile(A, ld, 8 * (s + k), 8 * j, c, q);
+      const double2 vt = *reinterpret_cast<const double2 *>(V + (size_t)(8 * (s + k) + c) * kVS + 2 * q);
+      dmma(cf.x, cf.y, w0, vt.x);
+      dmma(cf.x, cf.y, w1, vt.y);
+      st_tile(A, ld, 8 * (s + k), 8 * j, c, q, cf);
+    }
+  }
+  bar_panel();  // the tile is complete (and gp free) before anyone reloads it with another ownership
+}
+
+// Factor panel s (column tile s, row tiles s..RT-1) with the four panel warps.  Same outputs as the
+// single-warp version: R (top tile) to A, U row-major to V, T (column-major 8x8) to Tb.
+template <int KL>
+__device__ __forceinline__ void panel_coop(double *A, double *V, double *Tb, const PanelXch &x, int ld, int p,
+                                           int RT, int s, int lane, int w) {
+  const int c = lane >> 2, q = lane & 3;
+  const int j0 = 8 * s, r0 = 8 * s;
+  const int nf = (p - j0 < 8) ? p - j0 : 8;
+  const int nt = RT - s;
+  const int l0 = 2 * q, l1 = 2 * q + 1;
+  const bool top = (w == 0);  // this warp's local tile 0 is the top tile of the strip
+  double vr[KL][2];
+  double na = 0.0, nb = 0.0;
+  const double *Acol = A + (size_t)(j0 + c) * ld + r0 + 2 * q;
+#pragma unroll
+  for (int kk = 0; kk < KL; ++kk) {
+    const int k = w + kPW * kk;
+    double2 v = make_double2(0.0, 0.0);
+    if (k < nt) v = *reinterpret_cast<const double2 *>(Acol + 8 * k);
+    vr[kk][0] = v.x;
+    vr[kk][1] = v.y;
+    if (kk == 0 && top) {
+      if (l0 > c) na = v.x * v.x;
+      if (l1 > c) nb = v.y * v.y;
+    } else {
+      na = fma(v.x, v.x, na);
+      nb = fma(v.y, v.y, nb);
+    }
+  }
+  double tau_r[8];
+  double dg = 0.0, du = 0.0;
+  double2 *vs2 = reinterpret_cast<double2 *>(x.vs + w * (8 * KL)) + q;
+#pragma unroll
+  for (int cc = 0; cc < 8; ++cc) {
+    tau_r[cc] = 0.0;
+    if (cc < nf) {
+      double *pn = x.pn + (cc & 1) * kPW;
+      const double part = quad_sum(na + nb);
+      if (lane == 4 * cc) pn[w] = part;
+      if (top && lane == 4 * cc + (cc >> 1)) x.x0[cc & 1] = (cc & 1) ? vr[0][1] : vr[0][0];
+      bar_panel();
+      const double sig = (pn[0] + pn[1]) + (pn[2] + pn[3]);
+      const double x0 = x.x0[cc & 1];
+      if (sig > kTinySig) {  // uniform over the four warps
+        const double nrm = sqrt(fma(x0, x0, sig));
+        const double beta = (x0 >= 0.0) ? -nrm : nrm;
+        const double u1 = x0 - beta;
+        const double tt = -1.0 / (beta * u1);
+        tau_r[cc] = tt;
+        if (c == cc) {
+          if (top) {
+            dg = beta;
+            du = u1;
+            vs2[0] = make_double2((l0 < cc) ? 0.0 : ((l0 == cc) ? u1 : vr[0][0]),
+                                  (l1 < cc) ? 0.0 : ((l1 == cc) ? u1 : vr[0][1]));
+          } else {
+            du = u1;
+            vs2[0] = make_double2(vr[0][0], vr[0][1]);
+          }
+#pragma unroll
+          for (int kk = 1; kk < KL; ++kk) vs2[4 * kk] = make_double2(vr[kk][0], vr[kk][1]);
+        }
+        __syncwarp();
+        double wa = 0.0, wb = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < KL; ++kk) {
+          const double2 u = vs2[4 * kk];
+          wa = fma(u.x, vr[kk][0], wa);
+          wb = fma(u.y, vr[kk][1], wb);
+        }
+        const double wpart = quad_sum(wa + wb);
+        if (q == 0) x.pw[w * 8 + c] = wpart;
+        bar_panel();
+        const double wt = tt * ((x.pw[c] + x.pw[8 + c]) + (x.pw[16 + c] + x.pw[24 + c]));
+        if (c > cc) {
+          na = 0.0;
+          nb = 0.0;
+#pragma unroll
+          for (int kk = 0; kk < KL; ++kk) {
+            const double2 u = vs2[4 * kk];
+            vr[kk][0] = fma(-wt, u.x, vr[kk][0]);
+            vr[kk][1] = fma(-wt, u.y, vr[kk][1]);
+            if (kk == 0 && top) {
+              if (l0 > c) na = vr[0][0] * vr[0][0];
+              if (l1 > c) nb = vr[0][1] * vr[0][1];
+            } else {
+              na = fma(vr[kk][0], vr[kk][0], na);
+              nb = fma(vr[kk][1], vr[kk][1], nb);
+            }
+          }
+        }
+      } else if (c == cc && top) {
+        dg = x0;  // column already zero below the pivot: H = I
+        du = 0.0;
+      }
+    }
+  }
+  // U (row-major) for the trailing updates and R / untouched columns back to A
+  {
+    const bool fact = c < nf;
+    // a column carries a reflector iff its tau is non-zero (known to every warp)
+    double mytau = 0.0;
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc)
+      if (c == cc) mytau = tau_r[cc];
+    const bool refl = fact && (mytau != 0.0);
+    double *Vc = V + (size_t)(r0 + l0) * kVS + c;
+    double *Aw = A + (size_t)(j0 + c) * ld + r0 + 2 * q;
+#pragma unroll
+    for (int kk = 0; kk < KL; ++kk) {
+      const int k = w + kPW * kk;
+      if (k < nt) {
+        if (kk == 0 && top) {
+          Vc[0] = refl ? ((l0 < c) ? 0.0 : ((l0 == c) ? du : vr[0][0])) : 0.0;
+          Vc[kVS] = refl ? ((l1 < c) ? 0.0 : ((l1 == c) ? du : vr[0][1])) : 0.0;
+          double2 v = make_double2(vr[0][0], vr[0][1]);
+          if (fact) {
+            v.x = (l0 < c) ? vr[0][0] : ((l0 == c) ? dg : 0.0);
+            v.y = (l1 < c) ? vr[0][1] : ((l1 == c) ? dg : 0.0);
+          }
+          *reinterpret_cast<double2 *>(Aw) = v;
+        } else {
+          Vc[(size_t)8 * k * kVS] = refl ? vr[kk][0] : 0.0;
+          Vc[(size_t)8 * k * kVS + kVS] = refl ? vr[kk][1] : 0.0;
+          *reinterpret_cast<double2 *>(Aw + 8 * k) =
+              fact ? make_double2(0.0, 0.0) : make_double2(vr[kk][0], vr[kk][1]);
+        }
+      }
+    }
+  }
+  __syncwarp();
+  // partial G = U^T U over this warp's tiles
+  double g0 = 0.0, g1 = 0.0;
+  {
+    const double *Vf = V + (size_t)(r0 + 2 * q) * kVS + c;
+#pragma unroll
+    for (int kk = 0; kk < KL; ++kk) {
+      const int k = w + kPW * kk;
+      if (k < nt) {
+        const double vx = Vf[(size_t)8 * k * kVS];
+        const double vy = Vf[(size_t)8 * k * kVS + kVS];
+        dmma(g0, g1, vx, vx);
+        dmma(g0, g1, vy, vy);
+      }
+    }
+  }
+  *reinterpret_cast<double2 *>(x.gp + w * 64 + c * 8 + 2 * q) = make_double2(g0, g1);  // [m][n] row-major
+  bar_panel();
+  // T (dlarft, forward / columnwise) by warp 0: lane u owns row u; stored column-major for ld_tile
+  if (w == 0 && lane < 8) {
+    const int u = lane;
+    double tr[8];
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) {
+      double val = 0.0;
+      if (cc == u) {
+        val = tau_r[cc];
+      } else if (cc > u) {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (k >= u && k < cc) {
+            const double g = (x.gp[k * 8 + cc] + x.gp[64 + k * 8 + cc]) + (x.gp[128 + k * 8 + cc] + x.gp[192 + k * 8 + cc]);
+            acc = fma(tr[k], g, acc);
+          }
+        val = -tau_r[cc] * acc;
+      }
+      tr[cc] = val;
+      Tb[cc * 8 + u] = val;
+    }
+  }
+}
+
 // ---------------------------------------------------------------- kernel
 template <int MAXT, int MINB>
 __global__ void __launch_bounds__(256, MINB) lifts_mma_kernel(LiftParams2 a) {
@@ -311,8 +551,16 @@ __global__ void __launch_bounds__(256, MINB) lifts_mma_kernel(LiftParams2 a) {
   double *V1 = V0 + (size_t)NR * kVS;      //                             (phase 2: cost partials, 8 x NR)
   double *Tb = V1 + (size_t)NR * kVS;      // 2 x 64
   double *Gs = Tb + 128;                   // 64
-  double *vs = Gs + 64;                    // NR  (scratch column of the panel warp)
-  double *cost = vs + 128;                 // p + 1
+  double *vs = Gs + 64;                    // 128: per-warp u scratch columns of the panel warps
+  double *xch = vs + 128;                  // 8 (pn) + 2 (x0) + 6 pad + 32 (pw) + 256 (gp) = 304
+  double *cost = xch + 304;                // p + 1
+  PanelXch px;
+  px.pn = xch;
+  px.x0 = xch + 8;
+  px.pw = xch + 16;
+  px.gp = xch + 48;
+  px.vs = vs;
+  constexpr int KL = (MAXT + kPW - 1) / kPW;
   double *acc = cost + (p + 2);            // p
   int *perm_s = reinterpret_cast<int *>(acc + p + (p & 1));
   double *Dbuf = V0;
@@ -352,21 +600,18 @@ __global__ void __launch_bounds__(256, MINB) lifts_mma_kernel(LiftParams2 a) {
       // ---- phase 1: blocked Householder with one panel of look-ahead.  In step s warp 0 first
       // brings column tile s+1 up to date and factors it (into the other V/T buffer) while
       // warps 1..7 apply panel s to the remaining tiles: one barrier per panel.
-      if (warp == 0) panel_dispatch<MAXT>(A, V0, Tb, Gs, vs, ld, p, RT, 0, lane);
+      if (warp < kPW) panel_coop<KL>(A, V0, Tb, px, ld, p, RT, 0, lane, warp);
       __syncthreads();
       for (int s = 0; s < RT; ++s) {
         const double *Vc = (s & 1) ? V1 : V0;
         double *Vn = (s & 1) ? V0 : V1;
         const double *Tc = Tb + 64 * (s & 1);
         double *Tn = Tb + 64 * ((s + 1) & 1);
-        if (warp == 0) {
-          if (s + 1 < PT) trailing_tile(A, Vc, Tc, ld, RT, s, s + 1, lane);
-          if (s + 1 < RT) {
-            __syncwarp();
-            panel_dispatch<MAXT>(A, Vn, Tn, Gs, vs, ld, p, RT, s + 1, lane);
-          }
+        if (warp < kPW) {
+          if (s + 1 < PT) trailing_coop<KL>(A, Vc, Tc, px, ld, RT, s, s + 1, lane, warp);
+          if (s + 1 < RT) panel_coop<KL>(A, Vn, Tn, px, ld, p, RT, s + 1, lane, warp);
         } else {
-          for (int j = s + 2 + (warp - 1); j < PT; j += 7) trailing_tile(A, Vc, Tc, ld, RT, s, j, lane);
+          for (int j = s + 2 + (warp - kPW); j < PT; j += 8 - kPW) trailing_tile(A, Vc, Tc, ld, RT, s, j, lane);
         }
         __syncthreads();
       }
@@ -491,7 +736,7 @@ static int mma_ld(int rt) {
 static size_t mma_smem_bytes(int p) {
   const int rt = (p + 7) / 8, pt = (p + 8) / 8;
   const int ld = mma_ld(rt);
-  size_t d = (size_t)8 * pt * ld + 2 * (size_t)8 * rt * 10 + 192 + 128 + (size_t)(p + 2) + (size_t)(p + 1);
+  size_t d = (size_t)8 * pt * ld + 2 * (size_t)8 * rt * 10 + 192 + 128 + 304 + (size_t)(p + 2) + (size_t)(p + 1);
   return d * sizeof(double) + (size_t)p * sizeof(int) + 32;
 }
 

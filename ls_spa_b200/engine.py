@@ -230,7 +230,9 @@ def run_samples(backend, coll: Collective, prob, source: PermutationSource, cfg:
     if source.total is not None:
         limit = source.total if limit is None else min(limit, source.total)
     tgt = target_samples(p)
-    bs_eff = cfg.batch_size if cfg.estimate_errors else tgt   # no estimates -> boundaries are irrelevant
+    # without error estimates batch boundaries are irrelevant: cut the super-batch into 1024-sample
+    # batches so that the per-batch moment kernels run in parallel
+    bs_eff = cfg.batch_size if cfg.estimate_errors else min(tgt, 1024)
     g_local = max(1, -(-tgt // bs_eff))
     sb_samples = g_local * W * bs_eff
     est = backend.make_estimator(cfg)
