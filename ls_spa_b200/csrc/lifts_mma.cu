@@ -40,6 +40,7 @@ struct LiftParams2 {
   int64_t count;
   int anti;
   double *out;
+  long long *dbg;  // optional: cycle counters of block 0 (development aid), else nullptr
 };
 
 __device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b) {
@@ -396,48 +397,61 @@ __device__ __forceinline__ void panel_coop(double *A, double *V, double *Tb, con
   double tau_r[8];
   double dg = 0.0, du = 0.0;
   double2 *vs2 = reinterpret_cast<double2 *>(x.vs + w * (8 * KL)) + q;
+  // ONE exchange per reflector.  u = x - beta e1 is unnormalised, so everything a warp needs for its
+  // partial dot products (the raw sub-pivot entries of column cc) is known before beta is: each
+  // warp publishes {partial |x|^2, partial u^T a_c without the pivot row}, warp 0 adds the pivot
+  // row a_piv,c, and after the barrier every warp derives beta, u1, tt and w_c = tt (sum + u1 a_piv,c).
 #pragma unroll
   for (int cc = 0; cc < 8; ++cc) {
     tau_r[cc] = 0.0;
     if (cc < nf) {
-      double *pn = x.pn + (cc & 1) * kPW;
-      const double part = quad_sum(na + nb);
-      if (lane == 4 * cc) pn[w] = part;
-      if (top && lane == 4 * cc + (cc >> 1)) x.x0[cc & 1] = (cc & 1) ? vr[0][1] : vr[0][0];
+      double *ex = x.pw + (cc & 1) * 48;   // [kPW][8] partial dots, [kPW] partial norms, [8] pivot row
+      __syncwarp();                        // every lane is done reading the previous reflector's column
+      if (c == cc) {
+        // publish the raw column (top tile: zeros on and above the pivot row)
+        if (top)
+          vs2[0] = make_double2((l0 <= cc) ? 0.0 : vr[0][0], (l1 <= cc) ? 0.0 : vr[0][1]);
+        else
+          vs2[0] = make_double2(vr[0][0], vr[0][1]);
+#pragma unroll
+        for (int kk = 1; kk < KL; ++kk) vs2[4 * kk] = make_double2(vr[kk][0], vr[kk][1]);
+      }
+      __syncwarp();
+      double wa = 0.0, wb = 0.0;
+#pragma unroll
+      for (int kk = 0; kk < KL; ++kk) {
+        const double2 u = vs2[4 * kk];
+        wa = fma(u.x, vr[kk][0], wa);
+        wb = fma(u.y, vr[kk][1], wb);
+      }
+      // both reductions over the quad at once: lanes of column cc carry the norm, all carry the dot
+      double wpart = wa + wb, npart = na + nb;
+      wpart += __shfl_xor_sync(kFull, wpart, 1);
+      npart += __shfl_xor_sync(kFull, npart, 1);
+      wpart += __shfl_xor_sync(kFull, wpart, 2);
+      npart += __shfl_xor_sync(kFull, npart, 2);
+      if (q == 0) ex[w * 8 + c] = wpart;
+      if (lane == 4 * cc) ex[32 + w] = npart;
+      if (top && q == (cc >> 1)) ex[36 + c] = (cc & 1) ? vr[0][1] : vr[0][0];   // pivot-row entries a_piv,c
       bar_panel();
-      const double sig = (pn[0] + pn[1]) + (pn[2] + pn[3]);
-      const double x0 = x.x0[cc & 1];
+      const double sig = (ex[32] + ex[33]) + (ex[34] + ex[35]);
+      const double x0 = ex[36 + cc];
       if (sig > kTinySig) {  // uniform over the four warps
-        const double nrm = sqrt(fma(x0, x0, sig));
+        // beta = -sign(x0) |x|, u1 = x0 - beta (|u1| = |x0| + |x|), tt = 1 / (|x| |u1|)
+        // (dependent fp64 operations cost ~20 cycles each here, so the chain is kept short:
+        //  one rsqrt and one reciprocal, 1/(|x| |u1|) = 1/(|x|^2 + |x0| |x|))
+        const double s2 = fma(x0, x0, sig);
+        const double nrm = s2 * rsqrt(s2);
+        const double tt = 1.0 / fma(fabs(x0), nrm, s2);
         const double beta = (x0 >= 0.0) ? -nrm : nrm;
         const double u1 = x0 - beta;
-        const double tt = -1.0 / (beta * u1);
         tau_r[cc] = tt;
-        if (c == cc) {
-          if (top) {
-            dg = beta;
-            du = u1;
-            vs2[0] = make_double2((l0 < cc) ? 0.0 : ((l0 == cc) ? u1 : vr[0][0]),
-                                  (l1 < cc) ? 0.0 : ((l1 == cc) ? u1 : vr[0][1]));
-          } else {
-            du = u1;
-            vs2[0] = make_double2(vr[0][0], vr[0][1]);
-          }
-#pragma unroll
-          for (int kk = 1; kk < KL; ++kk) vs2[4 * kk] = make_double2(vr[kk][0], vr[kk][1]);
+        if (c == cc && top) {
+          dg = beta;
+          du = u1;
         }
-        __syncwarp();
-        double wa = 0.0, wb = 0.0;
-#pragma unroll
-        for (int kk = 0; kk < KL; ++kk) {
-          const double2 u = vs2[4 * kk];
-          wa = fma(u.x, vr[kk][0], wa);
-          wb = fma(u.y, vr[kk][1], wb);
-        }
-        const double wpart = quad_sum(wa + wb);
-        if (q == 0) x.pw[w * 8 + c] = wpart;
-        bar_panel();
-        const double wt = tt * ((x.pw[c] + x.pw[8 + c]) + (x.pw[16 + c] + x.pw[24 + c]));
+        const double apiv = ex[36 + c];
+        const double wt = tt * (((ex[c] + ex[8 + c]) + (ex[16 + c] + ex[24 + c])) + u1 * apiv);
         if (c > cc) {
           na = 0.0;
           nb = 0.0;
@@ -447,6 +461,9 @@ __device__ __forceinline__ void panel_coop(double *A, double *V, double *Tb, con
             vr[kk][0] = fma(-wt, u.x, vr[kk][0]);
             vr[kk][1] = fma(-wt, u.y, vr[kk][1]);
             if (kk == 0 && top) {
+              // the pivot row is not part of the published column: a_piv,c -= wt * u1
+              if (l0 == cc) vr[0][0] = fma(-wt, u1, vr[0][0]);
+              if (l1 == cc) vr[0][1] = fma(-wt, u1, vr[0][1]);
               if (l0 > c) na = vr[0][0] * vr[0][0];
               if (l1 > c) nb = vr[0][1] * vr[0][1];
             } else {
@@ -552,13 +569,13 @@ __global__ void __launch_bounds__(256, MINB) lifts_mma_kernel(LiftParams2 a) {
   double *Tb = V1 + (size_t)NR * kVS;      // 2 x 64
   double *Gs = Tb + 128;                   // 64
   double *vs = Gs + 64;                    // 128: per-warp u scratch columns of the panel warps
-  double *xch = vs + 128;                  // 8 (pn) + 2 (x0) + 6 pad + 32 (pw) + 256 (gp) = 304
-  double *cost = xch + 304;                // p + 1
+  double *xch = vs + 128;                  // 16 (unused) + 96 (2 x {32 dots, 4 norms, 8 pivot row, pad}) + 256 (gp)
+  double *cost = xch + 368;                // p + 1
   PanelXch px;
   px.pn = xch;
   px.x0 = xch + 8;
   px.pw = xch + 16;
-  px.gp = xch + 48;
+  px.gp = xch + 112;
   px.vs = vs;
   constexpr int KL = (MAXT + kPW - 1) / kPW;
   double *acc = cost + (p + 2);            // p
@@ -574,6 +591,7 @@ __global__ void __launch_bounds__(256, MINB) lifts_mma_kernel(LiftParams2 a) {
       __syncthreads();
       for (int k = tid; k < p; k += 256) perm_s[k] = a.perms[sidx * p + (h == 0 ? k : p - 1 - k)];
       __syncthreads();
+      long long t_a = clock64();
       // ---- phase 0: gather A = [R_tr[:, perm] | c_tr], zero padding
       for (int e = tid; e < NC * (NR / 2); e += 256) {
         const int k = e / (NR / 2), i = 2 * (e - k * (NR / 2));
@@ -600,21 +618,31 @@ __global__ void __launch_bounds__(256, MINB) lifts_mma_kernel(LiftParams2 a) {
       // ---- phase 1: blocked Householder with one panel of look-ahead.  In step s warp 0 first
       // brings column tile s+1 up to date and factors it (into the other V/T buffer) while
       // warps 1..7 apply panel s to the remaining tiles: one barrier per panel.
+      long long t_b = clock64(), t_pan = 0, t_trc = 0, t_wait = 0;
       if (warp < kPW) panel_coop<KL>(A, V0, Tb, px, ld, p, RT, 0, lane, warp);
+      t_pan += clock64() - t_b;
       __syncthreads();
       for (int s = 0; s < RT; ++s) {
         const double *Vc = (s & 1) ? V1 : V0;
         double *Vn = (s & 1) ? V0 : V1;
         const double *Tc = Tb + 64 * (s & 1);
         double *Tn = Tb + 64 * ((s + 1) & 1);
+        long long t0 = clock64();
         if (warp < kPW) {
           if (s + 1 < PT) trailing_coop<KL>(A, Vc, Tc, px, ld, RT, s, s + 1, lane, warp);
+          long long t1 = clock64();
+          t_trc += t1 - t0;
           if (s + 1 < RT) panel_coop<KL>(A, Vn, Tn, px, ld, p, RT, s + 1, lane, warp);
+          t_pan += clock64() - t1;
         } else {
           for (int j = s + 2 + (warp - kPW); j < PT; j += 8 - kPW) trailing_tile(A, Vc, Tc, ld, RT, s, j, lane);
+          t_trc += clock64() - t0;
         }
+        long long t2 = clock64();
         __syncthreads();
+        t_wait += clock64() - t2;
       }
+      long long t_c = clock64();
 
       // ---- phase 1.5: inverses of the 8x8 diagonal blocks of R (column-major 8x8 each), zero the
       //      per-warp cost partials (both overlay the V buffers)
@@ -709,7 +737,17 @@ __global__ void __launch_bounds__(256, MINB) lifts_mma_kernel(LiftParams2 a) {
           }
         }
       }
+      long long t_d = clock64();
       __syncthreads();
+      if (a.dbg != nullptr && blockIdx.x == 0 && lane == 0 && sidx == blockIdx.x && h == 0) {
+        long long *d = a.dbg + warp * 8;
+        d[0] = t_b - t_a;      // gather
+        d[1] = t_pan;          // panel (warps 0-3)
+        d[2] = t_trc;          // trailing work
+        d[3] = t_wait;         // waiting at the step barrier
+        d[4] = t_c - t_b;      // whole phase 1
+        d[5] = t_d - t_c;      // phase 1.5 + phase 2 (this warp)
+      }
       for (int k = tid; k < p; k += 256) {
         double sacc = 0.0;
 #pragma unroll
@@ -736,7 +774,7 @@ static int mma_ld(int rt) {
 static size_t mma_smem_bytes(int p) {
   const int rt = (p + 7) / 8, pt = (p + 8) / 8;
   const int ld = mma_ld(rt);
-  size_t d = (size_t)8 * pt * ld + 2 * (size_t)8 * rt * 10 + 192 + 128 + 304 + (size_t)(p + 2) + (size_t)(p + 1);
+  size_t d = (size_t)8 * pt * ld + 2 * (size_t)8 * rt * 10 + 192 + 128 + 368 + (size_t)(p + 2) + (size_t)(p + 1);
   return d * sizeof(double) + (size_t)p * sizeof(int) + 32;
 }
 
@@ -752,6 +790,8 @@ static int launch_mma(const LiftParams2 &a, int grid, size_t smem, cudaStream_t 
 }
 
 // below ~48 features the scalar kernel (many small CTAs per SM) is faster (profiles/r01_quick_bench_v2.log)
+long long *g_lifts_dbg = nullptr;  // set through lsspa_debug_set_lifts_counters (development aid)
+
 bool lifts_mma_supported(int p) { return p >= 49 && p <= 128; }
 
 int lifts_mma_launch(int p, const double *R_tr_cm, const double *c_tr, const double *R_te_cm, const double *c_te,
@@ -771,6 +811,7 @@ int lifts_mma_launch(int p, const double *R_tr_cm, const double *c_tr, const dou
   a.count = count;
   a.anti = antithetical ? 1 : 0;
   a.out = lifts_out;
+  a.dbg = g_lifts_dbg;
   const size_t smem = mma_smem_bytes(p);
   const DeviceInfo &d = device_info();
   const int sms = d.sm_count > 0 ? d.sm_count : 148;
@@ -786,3 +827,8 @@ int lifts_mma_launch(int p, const double *R_tr_cm, const double *c_tr, const dou
 }
 
 }  // namespace lsspa
+
+// development aid, not part of include/lsspa.h: 64 device long longs receiving block 0's cycle counters
+extern "C" __attribute__((visibility("default"))) void lsspa_debug_set_lifts_counters(long long *dev_ptr) {
+  lsspa::g_lifts_dbg = dev_ptr;
+}

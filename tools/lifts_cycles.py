@@ -1,0 +1,21 @@
+"""Cycle counters of one CTA of the DMMA lift kernel (development aid)."""
+import ctypes, sys, torch
+sys.path.insert(0, "."); sys.path.insert(0, "tools")
+from quick_bench import synth_problem
+from ls_spa_b200 import ops, samplers, _cabi
+dev = torch.device("cuda")
+p = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+prob = synth_problem(p, dev)
+perms = samplers.PermutohedronSource(p, 42, None, dev).take(4096)
+buf = torch.zeros(64, dtype=torch.int64, device=dev)
+lib = _cabi.load()
+lib.lsspa_debug_set_lifts_counters.argtypes = [ctypes.c_void_p]
+ops.lifts(prob, perms, True)
+lib.lsspa_debug_set_lifts_counters(buf.data_ptr())
+ops.lifts(prob, perms, True)
+torch.cuda.synchronize()
+lib.lsspa_debug_set_lifts_counters(None)
+d = buf.cpu().numpy().reshape(8, 8).copy()
+print("warp  gather   panel  trailing  barrier-wait  phase1  phase1.5+2")
+for w in range(8):
+    print(w, d[w, :6])
