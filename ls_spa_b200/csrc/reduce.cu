@@ -225,23 +225,29 @@ __device__ __forceinline__ void absorb_regs(double *T, double (&b)[32], double *
   for (int k = kstart; k < kend; ++k) {
     double *ub = us + (k & 1) * 72;
     if (active && j == k) {
-      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0, s5 = 0.0, s6 = 0.0, s7 = 0.0;
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
+      for (int i = 0; i < 32; i += 8) {
         s0 = fma(b[i], b[i], s0);
         s1 = fma(b[i + 1], b[i + 1], s1);
         s2 = fma(b[i + 2], b[i + 2], s2);
         s3 = fma(b[i + 3], b[i + 3], s3);
+        s4 = fma(b[i + 4], b[i + 4], s4);
+        s5 = fma(b[i + 5], b[i + 5], s5);
+        s6 = fma(b[i + 6], b[i + 6], s6);
+        s7 = fma(b[i + 7], b[i + 7], s7);
       }
-      double sig = (s0 + s1) + (s2 + s3);
+      double sig = ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
       if (HALVES == 2) sig += __shfl_xor_sync(__activemask(), sig, 1);
       const double x0 = T[(size_t)k * q + k];
       double u1 = 0.0, tt = 0.0, beta = x0;
       if (sig > kTinySig) {
-        const double nrm = sqrt(fma(x0, x0, sig));
+        // dependent fp64 operations cost ~20 cycles each: one rsqrt, one reciprocal
+        const double ss = fma(x0, x0, sig);
+        const double nrm = ss * rsqrt(ss);
+        tt = 1.0 / fma(fabs(x0), nrm, ss);      // = 1 / (|x| |u1|) = -1 / (beta u1)
         beta = (x0 >= 0.0) ? -nrm : nrm;
         u1 = x0 - beta;
-        tt = -1.0 / (beta * u1);
       }
       double2 *dst = reinterpret_cast<double2 *>(ub + 32 * h);
 #pragma unroll
@@ -256,16 +262,20 @@ __device__ __forceinline__ void absorb_regs(double *T, double (&b)[32], double *
     const double tt = ub[65];
     if (active && j > k && tt != 0.0) {
       const double2 *src = reinterpret_cast<const double2 *>(ub + 32 * h);
-      double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+      double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0, d4 = 0.0, d5 = 0.0, d6 = 0.0, d7 = 0.0;
 #pragma unroll
-      for (int i = 0; i < 16; i += 2) {
-        const double2 a = src[i], c = src[i + 1];
+      for (int i = 0; i < 16; i += 4) {
+        const double2 a = src[i], c = src[i + 1], e = src[i + 2], g = src[i + 3];
         d0 = fma(a.x, b[2 * i], d0);
         d1 = fma(a.y, b[2 * i + 1], d1);
         d2 = fma(c.x, b[2 * i + 2], d2);
         d3 = fma(c.y, b[2 * i + 3], d3);
+        d4 = fma(e.x, b[2 * i + 4], d4);
+        d5 = fma(e.y, b[2 * i + 5], d5);
+        d6 = fma(g.x, b[2 * i + 6], d6);
+        d7 = fma(g.y, b[2 * i + 7], d7);
       }
-      double d = (d0 + d1) + (d2 + d3);
+      double d = ((d0 + d1) + (d2 + d3)) + ((d4 + d5) + (d6 + d7));
       if (HALVES == 2) d += __shfl_xor_sync(__activemask(), d, 1);
       const double u1 = ub[64];
       const double tkj = T[(size_t)k * q + j];
