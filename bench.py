@@ -83,16 +83,20 @@ def fp64_peak_tflops():
 
 
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """nvidia-smi polled every 100 ms from before the warm-up; only the samples whose timestamp falls
+    inside the timed region (mark_start .. mark_end) are reported (all samples if none does)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
         self.rows, self.proc, self.index = [], None, index
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -100,25 +104,42 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
         self.proc.terminate()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-                for n, v in zip(names, r[2:6]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-            except Exception:
-                continue
+
+        def summarise(rows):
+            sm, mx, reasons = [], [], set()
+            for _, r in rows:
+                try:
+                    sm.append(float(r[1]))
+                    mx.append(float(r[2]))
+                    for n, v in zip(names, r[3:7]):
+                        if v.lower().startswith("active"):
+                            reasons.add(n)
+                except Exception:
+                    continue
+            return sm, mx, reasons
+
+        inside = [x for x in self.rows if self.t0 is not None and self.t0 - 0.05 <= x[0] <= self.t1 + 0.15]
+        sm, mx, reasons = summarise(inside)
+        scope = "timed region"
+        if not sm:
+            sm, mx, reasons = summarise(self.rows)
+            scope = "whole run (no sample fell inside the timed region)"
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "scope": scope}
 
 
 # --------------------------------------------------------------------------- GPU arm
@@ -201,14 +222,16 @@ def run_gpu(args):
     def step_device():
         last["res"] = L.ls_spa(Xtr, Xte, ytr, yte, **kw)
 
-    for _ in range(max(args.warmup, 3)):
-        step_device()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step_device()
     ops.LIFT_TRACE = []
     launches0 = ops.LAUNCHES
+    sampler.mark_start()
     ms_total = timed(step_device, args.steps)
+    sampler.mark_end()
     launches = ops.LAUNCHES - launches0
     trace, ops.LIFT_TRACE = ops.LIFT_TRACE, None
     clocks = sampler.stop() if rank == 0 else None

@@ -529,27 +529,41 @@ __device__ __forceinline__ void panel_coop(double *A, double *V, double *Tb, con
   }
   *reinterpret_cast<double2 *>(x.gp + w * 64 + c * 8 + 2 * q) = make_double2(g0, g1);  // [m][n] row-major
   bar_panel();
-  // T (dlarft, forward / columnwise) by warp 0: lane u owns row u; stored column-major for ld_tile
-  if (w == 0 && lane < 8) {
-    const int u = lane;
-    double tr[8];
+  // T (dlarft, forward / columnwise) by warp 0: the 32 lanes first add the four partial G's, then
+  // lane u < 8 runs the recurrence of row u with two accumulators (dependent fp64 ops are ~20
+  // cycles each and this sits on the critical path of the panel chain)
+  if (w == 0) {
+    {
+      const int o = c * 8 + 2 * q;
+      const double2 p0 = *reinterpret_cast<const double2 *>(x.gp + o);
+      const double2 p1 = *reinterpret_cast<const double2 *>(x.gp + 64 + o);
+      const double2 p2 = *reinterpret_cast<const double2 *>(x.gp + 128 + o);
+      const double2 p3 = *reinterpret_cast<const double2 *>(x.gp + 192 + o);
+      __syncwarp();
+      *reinterpret_cast<double2 *>(x.gp + o) = make_double2((p0.x + p1.x) + (p2.x + p3.x), (p0.y + p1.y) + (p2.y + p3.y));
+      __syncwarp();
+    }
+    if (lane < 8) {
+      const int u = lane;
+      double tr[8];
 #pragma unroll
-    for (int cc = 0; cc < 8; ++cc) {
-      double val = 0.0;
-      if (cc == u) {
-        val = tau_r[cc];
-      } else if (cc > u) {
-        double acc = 0.0;
+      for (int cc = 0; cc < 8; ++cc) {
+        double val = 0.0;
+        if (cc == u) {
+          val = tau_r[cc];
+        } else if (cc > u) {
+          double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          if (k >= u && k < cc) {
-            const double g = (x.gp[k * 8 + cc] + x.gp[64 + k * 8 + cc]) + (x.gp[128 + k * 8 + cc] + x.gp[192 + k * 8 + cc]);
-            acc = fma(tr[k], g, acc);
-          }
-        val = -tau_r[cc] * acc;
+          for (int k = 0; k < 8; ++k)
+            if (k >= u && k < cc) {
+              if (k & 1) acc1 = fma(tr[k], x.gp[k * 8 + cc], acc1);
+              else acc0 = fma(tr[k], x.gp[k * 8 + cc], acc0);
+            }
+          val = -tau_r[cc] * (acc0 + acc1);
+        }
+        tr[cc] = val;
+        Tb[cc * 8 + u] = val;
       }
-      tr[cc] = val;
-      Tb[cc * 8 + u] = val;
     }
   }
 }
@@ -593,19 +607,23 @@ __global__ void __launch_bounds__(256, MINB) lifts_mma_kernel(LiftParams2 a) {
       __syncthreads();
       long long t_a = clock64();
       // ---- phase 0: gather A = [R_tr[:, perm] | c_tr], zero padding
-      for (int e = tid; e < NC * (NR / 2); e += 256) {
-        const int k = e / (NR / 2), i = 2 * (e - k * (NR / 2));
-        double2 v = make_double2(0.0, 0.0);
-        if (k < p) {
-          const int col = perm_s[k];
-          const double *src = a.Rtr + (size_t)col * p;
-          if (i <= col) v.x = src[i];
-          if (i + 1 <= col) v.y = src[i + 1];
-        } else if (k == p) {
-          if (i < p) v.x = a.ctr[i];
-          if (i + 1 < p) v.y = a.ctr[i + 1];
+      {
+        const int half = NR / 2, tot = NC * half;
+#pragma unroll 4
+        for (int e = tid; e < tot; e += 256) {
+          const int k = e / half, i = 2 * (e - k * half);
+          double2 v = make_double2(0.0, 0.0);
+          if (k < p) {
+            const int col = perm_s[k];
+            const double *src = a.Rtr + (size_t)col * p;
+            if (i <= col) v.x = __ldg(src + i);
+            if (i + 1 <= col) v.y = __ldg(src + i + 1);
+          } else if (k == p) {
+            if (i < p) v.x = __ldg(a.ctr + i);
+            if (i + 1 < p) v.y = __ldg(a.ctr + i + 1);
+          }
+          *reinterpret_cast<double2 *>(A + (size_t)k * ld + i) = v;
         }
-        *reinterpret_cast<double2 *>(A + (size_t)k * ld + i) = v;
       }
       if (warp == 7) {
         double s0 = 0.0;

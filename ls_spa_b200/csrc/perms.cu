@@ -97,9 +97,20 @@ __global__ void pcg64_scan_kernel(int p, int64_t count, const uint32_t *raw, int
   const int64_t total = count * (int64_t)steps;
   int64_t t = 0, pos = 0, consumed = 0;
   int tmod = 0;
+  // the walk is serial, so the loads are not: keep the next kAhead windows of draws in registers
+  constexpr int kAhead = 8;
+  uint32_t win[kAhead];
+#pragma unroll
+  for (int a = 0; a < kAhead; ++a) win[a] = (32 * a + lane < ndraws) ? raw[32 * a + lane] : 0u;
   while (t < total && pos < ndraws) {
     const bool in_range = pos + lane < ndraws;
-    const uint32_t d = in_range ? raw[pos + lane] : 0u;
+    const uint32_t d = win[0];
+#pragma unroll
+    for (int a = 0; a + 1 < kAhead; ++a) win[a] = win[a + 1];
+    {
+      const int64_t nxt = pos + 32 * kAhead + lane;
+      win[kAhead - 1] = (nxt < ndraws) ? raw[nxt] : 0u;
+    }
     unsigned accmask = kFull;
     uint32_t val = 0;
     int64_t tl = 0;
@@ -107,7 +118,12 @@ __global__ void pcg64_scan_kernel(int p, int64_t count, const uint32_t *raw, int
     for (int it = 0; it < 33; ++it) {
       const int prior = __popc(accmask & lt_mask);
       tl = t + prior;
-      const int m = (tmod + prior) % steps;
+      int m = tmod + prior;  // < steps + 32
+      if (steps >= 32) {
+        if (m >= steps) m -= steps;
+      } else {
+        m %= steps;
+      }
       const uint32_t i = (uint32_t)(steps - m);  // Fisher-Yates index p-1 .. 1
       const uint32_t msk = 0xffffffffu >> __clz(i);
       val = d & msk;
