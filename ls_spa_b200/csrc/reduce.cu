@@ -16,6 +16,8 @@
 
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace lsspa {
 
 constexpr int kRBMax = 32;   // rows per block (one warp computes the reflector)
@@ -394,6 +396,7 @@ static RegsGeom regs_geom(int p) {
   const int q = p + 1;
   if (q > 512) return g;
   g.halves = (q <= 256) ? 2 : 1;
+  if (const char *e = getenv("LSSPA_TSQR_HALVES")) g.halves = (e[0] == '1') ? 1 : g.halves;
   g.threads = ((q * g.halves + 31) / 32) * 32;
   const DeviceInfo &d = device_info();
   const size_t limit = (size_t)(d.smem_optin > 0 ? d.smem_optin : 227 * 1024);
@@ -425,6 +428,7 @@ extern "C" int lsspa_tsqr_num_parts(int p, int64_t nrows) {
   const DeviceInfo &d = device_info();
   const int sms = d.sm_count > 0 ? d.sm_count : 148;
   int64_t cap = g.t_in_smem ? (int64_t)sms * ((g.smem * 2 + 2048 <= 227 * 1024) ? 2 : 1) : sms;
+  if (const char *e = getenv("LSSPA_TSQR_CTAS_PER_SM")) cap = (int64_t)sms * atoi(e);
   int64_t want = ceil_div(nrows, (int64_t)g.rb * 4);  // at least ~4 blocks per CTA
   if (want < 1) want = 1;
   return (int)(want < cap ? want : cap);

@@ -117,6 +117,26 @@ def test_lifts_match_reference(T, name):
         assert scaled_err(anti, 0.5 * (got + rev)) < 1e-13
 
 
+def test_lifts_bitwise_reproducible(T):
+    """compute-sanitizer is closed on this pool, so races are hunted the cheap way: the same launch
+    repeated, and the same permutations in differently sized launches (different CTA <-> sample
+    mapping, different co-residency), must give bit-identical rows."""
+    from ls_spa_b200 import ops, samplers
+    dev = T.device("cuda")
+    for name in ("syn_p100", "syn_p33", "syn_p160"):
+        g = load_golden(name)
+        p = int(g["p"])
+        prob = device_problem(T, g)
+        perms = samplers.PermutohedronSource(p, 3, None, dev).take(1500)
+        base = ops.lifts(prob, perms, True).cpu().numpy()
+        for _ in range(3):
+            assert np.array_equal(ops.lifts(prob, perms, True).cpu().numpy(), base), name
+        parts = [ops.lifts(prob, perms[a:b].contiguous(), True).cpu().numpy()
+                 for a, b in ((0, 7), (7, 300), (300, 1500))]
+        assert np.array_equal(np.vstack(parts), base), name
+        np.testing.assert_allclose(base.sum(axis=1), float(g["argsort_anti0_r_squared"]), atol=1e-10)
+
+
 def test_square_shapley_export(T, L):
     g = load_golden("syn_p33")
     perm = g["perms_random"][3].astype(np.int64)
