@@ -294,7 +294,7 @@ def run_gpu(args):
                          "peak_source": fp64_src, "kernel_ms_per_step": lift_ms / args.steps,
                          "kernel_share_of_step": lift_ms / ms_total,
                          "algorithmic_flop_per_permutation": FLOP_PER_PERM},
-            "roofline_reduce": {"bound": "hbm", "kernel": "tsqr_rows_kernel + tsqr_merge_kernel",
+            "roofline_reduce": {"bound": "hbm", "kernel": "gram_rows_kernel x2 (CholeskyQR2) + chol_factor_kernel",
                                 "achieved": red_bytes / (red_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
                                 "unit": "GB/s", "frac": red_bytes / (red_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                                 "peak_source": peaks["which"], "ms": red_ms, "algorithmic_bytes": red_bytes},

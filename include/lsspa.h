@@ -72,6 +72,28 @@ LSSPA_API int lsspa_tsqr_rows(const double *X, int64_t ldx, const double *y, int
 LSSPA_API int lsspa_tsqr_merge(const double *parts, int count, int group, int p, double *out,
                      void *stream);
 
+/* CholeskyQR2 variant of the same reduction for p <= 119 (gram.cu): Gram matrices with fp64 tensor
+ * tiles instead of one Householder reflector per column per row block.
+ *   pass 1: lsspa_gram_rows(Rinv = NULL) -> partial Grams; lsspa_gram_finish sums them (fixed
+ *           order) and scales by 1/divisor^2 -> G1 ((8*ceil((p+1)/8))^2 doubles, row-major);
+ *           lsspa_chol_factor -> R1 (q x q row-major), R1^-1 (padded, the layout pass 2 wants),
+ *           info[2] = {0 ok / 1 bad pivot, |R|_F |R^-1|_F >= cond_2};
+ *   pass 2: lsspa_gram_rows(Rinv = R1^-1) accumulates (Z R1^-1)^T (Z R1^-1) -> G2 -> R2;
+ *   lsspa_tri_product: factor = R2 R1 in the slot layout of lsspa_tsqr_merge.
+ * The caller falls back to lsspa_tsqr_rows when info reports a bad pivot or cond > ~1e6. */
+LSSPA_API int lsspa_gram_supported(int p);
+LSSPA_API int64_t lsspa_gram_slot_doubles(int p);
+LSSPA_API int64_t lsspa_gram_rinv_doubles(int p);
+LSSPA_API int lsspa_gram_num_parts(int p, int64_t nrows, int pass2);
+LSSPA_API int lsspa_gram_rows(const double *X, int64_t ldx, const double *y, int64_t nrows, int p,
+                              const double *Rinv_or_null, double *parts, int nparts, void *stream);
+LSSPA_API int lsspa_gram_finish(const double *parts, int count, int p, double scale, double *G_out,
+                                void *stream);
+LSSPA_API int lsspa_chol_factor(const double *G, int p, double *R_out, double *Rinv_out, double *info,
+                                void *stream);
+LSSPA_API int lsspa_tri_product(const double *R2, const double *R1, int p, const double *G1, double *out_slot,
+                                void *stream);
+
 /* ------------------------------------------------------------------------
  * 2. Permutation sources (int32 indices, perms_out[count][p])
  *    exact          itertools.permutations(range(p)), ls_spa/ls_spa.py:171

@@ -26,6 +26,14 @@ SIGNATURES = {
     "lsspa_tsqr_num_parts": (c_i32, [c_i32, c_i64]),
     "lsspa_tsqr_rows": (c_i32, [vp, c_i64, vp, c_i64, c_i32, c_f64, vp, c_i32, vp]),
     "lsspa_tsqr_merge": (c_i32, [vp, c_i32, c_i32, c_i32, vp, vp]),
+    "lsspa_gram_supported": (c_i32, [c_i32]),
+    "lsspa_gram_slot_doubles": (c_i64, [c_i32]),
+    "lsspa_gram_rinv_doubles": (c_i64, [c_i32]),
+    "lsspa_gram_num_parts": (c_i32, [c_i32, c_i64, c_i32]),
+    "lsspa_gram_rows": (c_i32, [vp, c_i64, vp, c_i64, c_i32, vp, vp, c_i32, vp]),
+    "lsspa_gram_finish": (c_i32, [vp, c_i32, c_i32, c_f64, vp, vp]),
+    "lsspa_chol_factor": (c_i32, [vp, c_i32, vp, vp, vp, vp]),
+    "lsspa_tri_product": (c_i32, [vp, vp, c_i32, vp, vp, vp]),
     "lsspa_perms_exact": (c_i32, [c_i32, c_u64, c_i64, vp, vp]),
     "lsspa_perms_pcg64_workspace_bytes": (sz, [c_i32, c_i64]),
     "lsspa_perms_pcg64": (c_i32, [c_i32, vp, c_i64, vp, vp, sz, vp, vp]),

@@ -1,0 +1,377 @@
+// CholeskyQR2 reduction of [X | y] to its (p+1) x (p+1) triangular factor, p <= 119.
+//
+// Second implementation of reduce_data (reference ls_spa/ls_spa.py:290-318) next to the Householder
+// TSQR of reduce.cu.  The Householder kernel is bound by the latency of one reflector per column
+// per 64-row block (~2000 cycles each); here almost all work is dense 8x8x4 fp64 tensor products:
+//
+//   pass 1   G1 = Z^T Z           (Z = [X | y], streamed once)      R1 = chol(G1)
+//   pass 2   G2 = Q1^T Q1, Q1 = Z R1^-1 formed on the fly per 32-row chunk      R2 = chol(G2)
+//   result   R = R2 R1
+//
+// One Cholesky-QR pass loses cond(Z)^2 eps; repeating it on Q1 = Z R1^-1 (whose condition number is
+// ~1) restores Householder-level accuracy as long as cond(Z) <~ 1e7 (Yamamoto et al. 2015).  The
+// caller checks the condition estimate / pivot status written by lsspa_chol_factor and falls back to
+// the Householder TSQR otherwise (rank-deficient inputs such as the reference's own "hard" test data).
+//
+// Fragments: chunk rows live in shared memory row-major with row stride ldr (ldr % 16 == 4), so
+// the access "rows 4s+q, columns 8t+c" (lane = 4c + q) is bank-conflict free; the same fragment
+// f_t is the A operand of tile row t and the B operand of tile column t of the Gram product.
+
+#include "common.cuh"
+
+namespace lsspa {
+
+constexpr int kGR = 32;          // rows per chunk
+constexpr int kGramThreads = 256;
+
+__device__ __forceinline__ void dmma_g(double &d0, double &d1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(d0), "+d"(d1)
+      : "d"(a), "d"(b));
+}
+
+static int gram_nt(int p) { return (p + 1 + 7) / 8; }
+static int gram_ldr(int nt) {
+  int n = 8 * nt;
+  return n + ((4 - (n % 16)) + 16) % 16;   // smallest >= n with % 16 == 4
+}
+
+struct GramParams {
+  const double *X;
+  int64_t ldx;
+  const double *y;
+  int64_t nrows;
+  int p;
+  const double *Rinv;  // pass 2: [8nt][ldr] row-major upper triangular, else nullptr
+  double *parts;       // [nparts][(8nt)^2] row-major partial Gram matrices (upper tiles valid)
+  int nparts;
+  int nt;
+  int ldr;
+};
+
+// accumulate the Gram of the kGR x 8nt chunk C (row-major, stride ldr) into the warp's tiles:
+// warp g owns tile rows g and nt-1-g (their union has nt+1 tiles for every g: balanced)
+template <int MAXNT>
+__device__ __forceinline__ void gram_chunk(const double *C, int ldr, int nt, int g, int lane,
+                                           double (&accA)[MAXNT][2], double (&accB)[MAXNT][2]) {
+  const int c = lane >> 2, q = lane & 3;
+  const int i2 = nt - 1 - g;
+#pragma unroll
+  for (int ks = 0; ks < kGR / 4; ++ks) {
+    const double *row = C + (size_t)(4 * ks + q) * ldr + c;
+    double f[MAXNT];
+#pragma unroll
+    for (int t = 0; t < MAXNT; ++t) f[t] = (t >= g && t < nt) ? row[8 * t] : 0.0;
+    double fa = 0.0, fb = 0.0;
+#pragma unroll
+    for (int t = 0; t < MAXNT; ++t) {
+      if (t == g) fa = f[t];
+      if (t == i2) fb = f[t];
+    }
+#pragma unroll
+    for (int t = 0; t < MAXNT; ++t) {
+      if (t >= g && t < nt) dmma_g(accA[t][0], accA[t][1], fa, f[t]);
+      if (i2 > g && t >= i2 && t < nt) dmma_g(accB[t][0], accB[t][1], fb, f[t]);
+    }
+  }
+}
+
+template <int MAXNT>
+__global__ void __launch_bounds__(kGramThreads) gram_rows_kernel(GramParams a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int p = a.p, nt = a.nt, ldr = a.ldr, nc = 8 * nt;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c = lane >> 2, q = lane & 3;
+  const bool pass2 = a.Rinv != nullptr;
+  double *sm = reinterpret_cast<double *>(smem_raw);
+  double *Zc0 = sm;                               // kGR x ldr
+  double *Zc1 = Zc0 + (size_t)kGR * ldr;
+  double *Qc = Zc1 + (size_t)kGR * ldr;           // pass 2 only
+  double *Ri = Qc + (size_t)kGR * ldr;            // pass 2 only: nc x ldr
+  if (pass2)
+    for (int e = tid; e < nc * ldr; e += kGramThreads) Ri[e] = a.Rinv[e];
+
+  double accA[MAXNT][2], accB[MAXNT][2];
+#pragma unroll
+  for (int t = 0; t < MAXNT; ++t) accA[t][0] = accA[t][1] = accB[t][0] = accB[t][1] = 0.0;
+  const int ngroups = (nt + 1) / 2;
+  const bool has_group = warp < ngroups;
+
+  const int64_t per = ceil_div(ceil_div(a.nrows, (int64_t)a.nparts), (int64_t)kGR) * kGR;
+  const int64_t r_begin = (int64_t)blockIdx.x * per;
+  const int64_t r_end = (r_begin + per < a.nrows) ? r_begin + per : a.nrows;
+
+  constexpr int NPT = (kGR * 8 * MAXNT + kGramThreads - 1) / kGramThreads;
+  double stage[NPT];
+  auto fetch = [&](int64_t r0) {
+#pragma unroll
+    for (int u = 0; u < NPT; ++u) {
+      const int e = tid + u * kGramThreads;
+      const int row = e / nc, col = e - row * nc;
+      double v = 0.0;
+      if (e < kGR * nc && r0 + row < r_end) {
+        if (col < p) v = a.X[(r0 + row) * a.ldx + col];
+        else if (col == p) v = a.y[r0 + row];
+      }
+      stage[u] = v;
+    }
+  };
+  auto commit = [&](double *Z) {
+#pragma unroll
+    for (int u = 0; u < NPT; ++u) {
+      const int e = tid + u * kGramThreads;
+      const int row = e / nc, col = e - row * nc;
+      if (e < kGR * nc) Z[(size_t)row * ldr + col] = stage[u];
+    }
+  };
+  if (r_begin < r_end) {
+    fetch(r_begin);
+    commit(Zc0);
+  }
+  __syncthreads();
+  int buf = 0;
+  for (int64_t r0 = r_begin; r0 < r_end; r0 += kGR) {
+    double *Z = buf ? Zc1 : Zc0;
+    double *Zn = buf ? Zc0 : Zc1;
+    const bool more = r0 + kGR < r_end;
+    if (more) fetch(r0 + kGR);
+    const double *G_in = Z;
+    if (pass2) {
+      // Q = Z Rinv for this chunk: warp w owns output column tiles j = w, w+8, all 4 row tiles
+      for (int j = warp; j < nt; j += kGramThreads / 32) {
+        double o[kGR / 8][2];
+#pragma unroll
+        for (int rt = 0; rt < kGR / 8; ++rt) o[rt][0] = o[rt][1] = 0.0;
+        for (int kt = 0; kt <= j; ++kt) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const double b = Ri[(size_t)(8 * kt + 4 * e + q) * ldr + 8 * j + c];
+#pragma unroll
+            for (int rt = 0; rt < kGR / 8; ++rt) {
+              const double av = Z[(size_t)(8 * rt + c) * ldr + 8 * kt + 4 * e + q];
+              dmma_g(o[rt][0], o[rt][1], av, b);
+            }
+          }
+        }
+#pragma unroll
+        for (int rt = 0; rt < kGR / 8; ++rt)
+          *reinterpret_cast<double2 *>(Qc + (size_t)(8 * rt + c) * ldr + 8 * j + 2 * q) = make_double2(o[rt][0], o[rt][1]);
+      }
+      __syncthreads();
+      G_in = Qc;
+    }
+    if (has_group) gram_chunk<MAXNT>(G_in, ldr, nt, warp, lane, accA, accB);
+    if (more) commit(Zn);
+    __syncthreads();
+    buf ^= 1;
+  }
+  // write this CTA's partial Gram (upper tiles): C layout lane (m = c, n = 2q+e)
+  double *out = a.parts + (size_t)blockIdx.x * nc * nc;
+  for (int e = tid; e < nc * nc; e += kGramThreads) out[e] = 0.0;
+  __syncthreads();
+  if (has_group) {
+    const int g = warp, i2 = nt - 1 - g;
+#pragma unroll
+    for (int t = 0; t < MAXNT; ++t) {
+      if (t >= g && t < nt)
+        *reinterpret_cast<double2 *>(out + (size_t)(8 * g + c) * nc + 8 * t + 2 * q) = make_double2(accA[t][0], accA[t][1]);
+      if (i2 > g && t >= i2 && t < nt)
+        *reinterpret_cast<double2 *>(out + (size_t)(8 * i2 + c) * nc + 8 * t + 2 * q) = make_double2(accB[t][0], accB[t][1]);
+    }
+  }
+}
+
+// G[e] = scale * sum_cta parts[cta][e], fixed order (deterministic)
+__global__ void gram_sum_kernel(const double *parts, int count, int n2, double scale, double *G) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n2) return;
+  double s = 0.0;
+  for (int k = 0; k < count; ++k) s += parts[(size_t)k * n2 + e];
+  G[e] = s * scale;
+}
+
+// Cholesky G = R^T R (upper, G row-major nc x nc, leading q x q block used), then R^-1.
+// info[0] = 0 ok / 1 non-positive or tiny pivot, info[1] = |R|_F |R^-1|_F (>= cond_2(R)).
+// R is written row-major q x q (slot layout of reduce.cu); Rinv row-major [nc][ldr], zero padded.
+__global__ void __launch_bounds__(256) chol_factor_kernel(const double *G, int q, int nc, int ldr, double *R_out,
+                                                          double *Rinv_out, double *info) {
+  extern __shared__ double sm[];
+  double *A = sm;                        // nc x nc working copy (upper part)
+  double *Vi = A + (size_t)nc * nc;      // nc x nc inverse
+  __shared__ double s_piv, s_fail, red[16];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int e = tid; e < nc * nc; e += nt) {
+    const int i = e / nc, j = e - i * nc;
+    A[e] = (i < q && j < q && j >= i) ? G[e] : 0.0;
+    Vi[e] = 0.0;
+  }
+  if (tid == 0) s_fail = 0.0;
+  __syncthreads();
+  double dmax = 0.0;
+  for (int i = 0; i < q; ++i) dmax = fmax(dmax, A[(size_t)i * nc + i]);
+  for (int k = 0; k < q; ++k) {
+    if (tid == 0) {
+      const double d = A[(size_t)k * nc + k];
+      if (!(d > 1e-14 * dmax)) s_fail = 1.0;
+      const double r = sqrt(d > 0.0 ? d : 1.0);
+      A[(size_t)k * nc + k] = r;
+      s_piv = 1.0 / r;
+    }
+    __syncthreads();
+    const double ri = s_piv;
+    for (int j = k + 1 + tid; j < q; j += nt) A[(size_t)k * nc + j] *= ri;
+    __syncthreads();
+    const int m = q - k - 1;
+    for (int e = tid; e < m * m; e += nt) {
+      const int i = k + 1 + e / m, j = k + 1 + e % m;
+      if (j >= i) A[(size_t)i * nc + j] = fma(-A[(size_t)k * nc + i], A[(size_t)k * nc + j], A[(size_t)i * nc + j]);
+    }
+    __syncthreads();
+  }
+  // inverse: thread j solves R x = e_j by back substitution (column j of R^-1)
+  for (int j = tid; j < q; j += nt) {
+    Vi[(size_t)j * nc + j] = 1.0 / A[(size_t)j * nc + j];
+    for (int i = j - 1; i >= 0; --i) {
+      double s0 = 0.0, s1 = 0.0;
+      int k = i + 1;
+      for (; k + 1 <= j; k += 2) {
+        s0 = fma(A[(size_t)i * nc + k], Vi[(size_t)k * nc + j], s0);
+        s1 = fma(A[(size_t)i * nc + k + 1], Vi[(size_t)(k + 1) * nc + j], s1);
+      }
+      if (k <= j) s0 = fma(A[(size_t)i * nc + k], Vi[(size_t)k * nc + j], s0);
+      Vi[(size_t)i * nc + j] = -(s0 + s1) / A[(size_t)i * nc + i];
+    }
+  }
+  __syncthreads();
+  double fr = 0.0, fi = 0.0;
+  for (int e = tid; e < nc * nc; e += nt) {
+    fr = fma(A[e], A[e], fr);
+    fi = fma(Vi[e], Vi[e], fi);
+  }
+  fr = warp_sum(fr);
+  fi = warp_sum(fi);
+  if ((tid & 31) == 0) {
+    red[tid >> 5] = fr;
+    red[8 + (tid >> 5)] = fi;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < nt / 32; ++w) {
+      a += red[w];
+      b += red[8 + w];
+    }
+    info[0] = s_fail;
+    info[1] = sqrt(a) * sqrt(b);
+  }
+  for (int e = tid; e < q * q; e += nt) {
+    const int i = e / q, j = e - i * q;
+    R_out[e] = A[(size_t)i * nc + j];
+  }
+  for (int e = tid; e < nc * ldr; e += nt) {
+    const int i = e / ldr, j = e - i * ldr;
+    Rinv_out[e] = (j < nc) ? Vi[(size_t)i * nc + j] : 0.0;
+  }
+}
+
+// out (slot layout: q x q row-major, then [q*q] = sum of squares of the y column) = R2 R1
+__global__ void tri_product_kernel(const double *R2, const double *R1, int q, const double *G1, int nc,
+                                   double *out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < q * q) {
+    const int i = e / q, j = e - i * q;
+    double s = 0.0;
+    for (int k = i; k <= j; ++k) s = fma(R2[(size_t)i * q + k], R1[(size_t)k * q + j], s);
+    out[e] = (j >= i) ? s : 0.0;
+  }
+  if (e < 8) out[(size_t)q * q + e] = (e == 0) ? G1[(size_t)(q - 1) * nc + (q - 1)] : 0.0;
+}
+
+template <int MAXNT>
+static int launch_gram(const GramParams &a, size_t smem, cudaStream_t st) {
+  LSSPA_CUDA_TRY(cudaFuncSetAttribute(gram_rows_kernel<MAXNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gram_rows_kernel<MAXNT><<<a.nparts, kGramThreads, smem, st>>>(a);
+  LSSPA_LAUNCH_CHECK();
+  return LSSPA_OK;
+}
+
+}  // namespace lsspa
+
+using namespace lsspa;
+
+// (p + 1 <= 120: the Cholesky kernel keeps the factor and its inverse, 2 x (8 nt)^2 doubles, in shared memory)
+extern "C" int lsspa_gram_supported(int p) { return (p >= 1 && p + 1 <= 120) ? 1 : 0; }
+
+extern "C" int64_t lsspa_gram_slot_doubles(int p) {
+  if (!lsspa_gram_supported(p)) return 0;
+  const int nc = 8 * gram_nt(p);
+  return (int64_t)nc * nc;
+}
+
+extern "C" int64_t lsspa_gram_rinv_doubles(int p) {
+  if (!lsspa_gram_supported(p)) return 0;
+  const int nt = gram_nt(p);
+  return (int64_t)8 * nt * gram_ldr(nt);
+}
+
+extern "C" int lsspa_gram_num_parts(int p, int64_t nrows, int pass2) {
+  if (!lsspa_gram_supported(p) || nrows < 1) return 0;
+  const DeviceInfo &d = device_info();
+  const int sms = d.sm_count > 0 ? d.sm_count : 148;
+  (void)pass2;
+  int64_t cap = (int64_t)sms;  // 255 registers x 256 threads: one CTA per SM in both passes
+  int64_t want = ceil_div(nrows, (int64_t)kGR * 4);
+  return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+}
+
+extern "C" int lsspa_gram_rows(const double *X, int64_t ldx, const double *y, int64_t nrows, int p,
+                               const double *Rinv_or_null, double *parts, int nparts, void *stream) {
+  if (!X || !y || !parts || !lsspa_gram_supported(p) || nrows < 1 || ldx < p || nparts < 1) return LSSPA_E_BADARG;
+  GramParams a;
+  a.X = X;
+  a.ldx = ldx;
+  a.y = y;
+  a.nrows = nrows;
+  a.p = p;
+  a.Rinv = Rinv_or_null;
+  a.parts = parts;
+  a.nparts = nparts;
+  a.nt = gram_nt(p);
+  a.ldr = gram_ldr(a.nt);
+  size_t smem = (size_t)2 * kGR * a.ldr * sizeof(double);
+  if (Rinv_or_null) smem += ((size_t)kGR * a.ldr + (size_t)8 * a.nt * a.ldr) * sizeof(double);
+  cudaStream_t st = as_stream(stream);
+  if (a.nt <= 4) return launch_gram<4>(a, smem, st);
+  if (a.nt <= 8) return launch_gram<8>(a, smem, st);
+  if (a.nt <= 13) return launch_gram<13>(a, smem, st);
+  return launch_gram<16>(a, smem, st);
+}
+
+extern "C" int lsspa_gram_finish(const double *parts, int count, int p, double scale, double *G_out,
+                                 void *stream) {
+  if (!parts || !G_out || !lsspa_gram_supported(p) || count < 1) return LSSPA_E_BADARG;
+  const int n2 = (int)lsspa_gram_slot_doubles(p);
+  gram_sum_kernel<<<(n2 + 255) / 256, 256, 0, as_stream(stream)>>>(parts, count, n2, scale, G_out);
+  LSSPA_LAUNCH_CHECK();
+  return LSSPA_OK;
+}
+
+extern "C" int lsspa_chol_factor(const double *G, int p, double *R_out, double *Rinv_out, double *info,
+                                 void *stream) {
+  if (!G || !R_out || !Rinv_out || !info || !lsspa_gram_supported(p)) return LSSPA_E_BADARG;
+  const int nt = gram_nt(p), nc = 8 * nt, ldr = gram_ldr(nt);
+  const size_t smem = (size_t)2 * nc * nc * sizeof(double);
+  LSSPA_CUDA_TRY(cudaFuncSetAttribute(chol_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  chol_factor_kernel<<<1, 256, smem, as_stream(stream)>>>(G, p + 1, nc, ldr, R_out, Rinv_out, info);
+  LSSPA_LAUNCH_CHECK();
+  return LSSPA_OK;
+}
+
+extern "C" int lsspa_tri_product(const double *R2, const double *R1, int p, const double *G1, double *out_slot,
+                                 void *stream) {
+  if (!R2 || !R1 || !G1 || !out_slot || !lsspa_gram_supported(p)) return LSSPA_E_BADARG;
+  const int q = p + 1, nc = 8 * gram_nt(p);
+  tri_product_kernel<<<(q * q + 255) / 256, 256, 0, as_stream(stream)>>>(R2, R1, q, G1, nc, out_slot);
+  LSSPA_LAUNCH_CHECK();
+  return LSSPA_OK;
+}

@@ -18,6 +18,7 @@ Multi-GPU (one process per GPU, ``torch.distributed``):
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -103,14 +104,17 @@ class CudaBackend:
     def __init__(self, device=None):
         self.device = device if device is not None else ops.require_cuda()
         self.copy_stream = None
+        self.use_cholqr2 = os.environ.get("LSSPA_REDUCE", "cholqr2") != "householder"
 
     # -- reduction ----------------------------------------------------------
-    def _row_chunks(self, X, y, lo, hi, p):
-        """Yield device (X_chunk, y_chunk) covering rows [lo, hi); host inputs are streamed
-        through two device buffers so the copy of chunk i+1 overlaps the TSQR of chunk i."""
+    def _row_chunks(self, X, y, lo, hi, p, keep=False):
+        """Yield device (X_chunk, y_chunk) covering rows [lo, hi); host inputs are streamed on a copy
+        stream so that the copy of chunk i+1 overlaps the work on chunk i.  keep=False recycles two
+        staging buffers (single-pass consumers); keep=True lands the chunks in one resident device
+        array (the CholeskyQR2 reduction reads the rows twice)."""
         if isinstance(X, torch.Tensor) and X.is_cuda:
             yv = y if (isinstance(y, torch.Tensor) and y.is_cuda) else torch.as_tensor(y).to(self.device)
-            yield X[lo:hi], yv[lo:hi], None
+            yield X[lo:hi], yv[lo:hi].contiguous(), None
             return
         Xh = X if isinstance(X, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(X))
         yh = y if isinstance(y, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(y))
@@ -123,36 +127,59 @@ class CudaBackend:
         if self.copy_stream is None:
             self.copy_stream = torch.cuda.Stream(device=self.device)
         main = torch.cuda.current_stream()
-        bufs = [(torch.empty((chunk, p), dtype=torch.float64, device=self.device),
-                 torch.empty(chunk, dtype=torch.float64, device=self.device)) for _ in range(2)]
-        # the staging buffers come from the main stream's allocator pool: whatever used that
-        # memory before (e.g. the previous reduction's kernels) must finish before we copy
+        if keep:
+            bigX = torch.empty((rows, p), dtype=torch.float64, device=self.device)
+            bigy = torch.empty(rows, dtype=torch.float64, device=self.device)
+            bufs = None
+        else:
+            bufs = [(torch.empty((chunk, p), dtype=torch.float64, device=self.device),
+                     torch.empty(chunk, dtype=torch.float64, device=self.device)) for _ in range(2)]
+        # the buffers come from the main stream's allocator pool: whatever used that memory before
+        # (e.g. the previous reduction's kernels) must finish before we copy into it
         self.copy_stream.wait_stream(main)
         free_ev = [None, None]
         for i, r0 in enumerate(range(lo, hi, chunk)):
             r1 = min(r0 + chunk, hi)
-            bx, by = bufs[i % 2]
+            if keep:
+                bx, by = bigX[r0 - lo: r1 - lo], bigy[r0 - lo: r1 - lo]
+            else:
+                bx, by = bufs[i % 2][0][: r1 - r0], bufs[i % 2][1][: r1 - r0]
             with torch.cuda.stream(self.copy_stream):
-                if free_ev[i % 2] is not None:
+                if not keep and free_ev[i % 2] is not None:
                     self.copy_stream.wait_event(free_ev[i % 2])
-                bx[: r1 - r0].copy_(Xh[r0:r1], non_blocking=True)
-                by[: r1 - r0].copy_(yh[r0:r1], non_blocking=True)
+                bx.copy_(Xh[r0:r1], non_blocking=True)
+                by.copy_(yh[r0:r1], non_blocking=True)
                 ready = torch.cuda.Event()
                 ready.record(self.copy_stream)
             main.wait_event(ready)
             done = torch.cuda.Event()
-            yield bx[: r1 - r0], by[: r1 - r0], done
+            yield bx, by, done
             done.record(main)
             free_ev[i % 2] = done
 
+    # condition-number bound up to which the CholeskyQR2 reduction is used (it is as accurate as
+    # Householder up to ~1e7); beyond it, or on a failed pivot, the Householder TSQR takes over
+    CHOLQR2_MAX_COND = 1e6
+
     def reduce_rows(self, X, y, lo, hi, p, divisor):
         """Rows [lo, hi) of [X|y]/divisor -> one triangular factor in slot layout (device)."""
-        parts = []
-        for Xc, yc, _ in self._row_chunks(X, y, lo, hi, p):
-            if Xc.shape[0] > 0:
-                parts.append(ops.tsqr_rows(Xc, yc, divisor))
-        if not parts:
+        if hi - lo <= 0:
             return torch.zeros(ops.tsqr_slot(p), dtype=torch.float64, device=self.device)
+        if self.use_cholqr2 and ops.gram_supported(p) and hi - lo >= 4 * (p + 1):
+            fac = ops.CholQR2(p, divisor)
+            for Xc, yc, _ in self._row_chunks(X, y, lo, hi, p, keep=True):
+                fac.add_chunk(Xc, yc)          # pass 1 on this chunk overlaps the next copy
+            chunks = fac.chunks
+            slot, info = fac.finish()          # pass 2 re-reads the resident rows
+            bad1, cond1, bad2, cond2 = info.cpu().numpy().ravel()
+            if bad1 == 0 and bad2 == 0 and cond1 <= self.CHOLQR2_MAX_COND and cond2 <= 10.0 * (p + 1):
+                return slot
+            parts = [ops.tsqr_rows(Xc, yc, divisor) for Xc, yc in chunks if Xc.shape[0] > 0]
+        else:
+            parts = []
+            for Xc, yc, _ in self._row_chunks(X, y, lo, hi, p):
+                if Xc.shape[0] > 0:
+                    parts.append(ops.tsqr_rows(Xc, yc, divisor))
         stacked = parts[0] if len(parts) == 1 else torch.cat(parts, 0)
         return ops.tsqr_merge(stacked, p)
 

@@ -95,6 +95,79 @@ def tsqr_merge(parts: torch.Tensor, p: int, group: int = 8) -> torch.Tensor:
             return parts[0]
 
 
+def gram_supported(p: int) -> bool:
+    return bool(_lib().lsspa_gram_supported(p))
+
+
+class CholQR2:
+    """CholeskyQR2 of [X | y] / divisor over device row chunks (csrc/gram.cu).
+
+    add_chunk() launches pass 1 on a chunk as soon as it is resident (so it overlaps the copy of the
+    next one); finish() sums the partial Gram matrices, factors, runs pass 2 over the kept chunks
+    and returns (slot, info): slot has the layout of tsqr_merge's result, info (device) =
+    [[bad pivot 1, cond bound 1], [bad pivot 2, cond bound 2]]."""
+
+    def __init__(self, p: int, divisor: float):
+        self.p, self.scale = p, 1.0 / (float(divisor) ** 2)
+        self.chunks, self.parts1 = [], []
+        self.n2 = int(_lib().lsspa_gram_slot_doubles(p))
+
+    def _rows(self, Xc, yc, rinv):
+        lib = _lib()
+        n = Xc.shape[0]
+        nparts = lib.lsspa_gram_num_parts(self.p, n, 1 if rinv is not None else 0)
+        buf = torch.empty((nparts, self.n2), dtype=torch.float64, device=Xc.device)
+        check(lib.lsspa_gram_rows(Xc.data_ptr(), Xc.stride(0), yc.data_ptr(), n, self.p, _ptr(rinv),
+                                  buf.data_ptr(), nparts, _stream()), "lsspa_gram_rows")
+        _count(1)
+        return buf
+
+    def _sum(self, parts):
+        allp = parts[0] if len(parts) == 1 else torch.cat(parts, 0)
+        G = torch.empty(self.n2, dtype=torch.float64, device=allp.device)
+        check(_lib().lsspa_gram_finish(allp.data_ptr(), allp.shape[0], self.p, self.scale, G.data_ptr(),
+                                       _stream()), "lsspa_gram_finish")
+        _count(1)
+        return G
+
+    def add_chunk(self, Xc: torch.Tensor, yc: torch.Tensor) -> None:
+        if Xc.shape[0] == 0:
+            return
+        if Xc.stride(1) != 1:
+            Xc = Xc.contiguous()
+        self.chunks.append((Xc, yc))
+        self.parts1.append(self._rows(Xc, yc, None))
+
+    def finish(self):
+        lib = _lib()
+        p, q = self.p, self.p + 1
+        dev = self.chunks[0][0].device
+        G1 = self._sum(self.parts1)
+        R1 = torch.empty(q * q, dtype=torch.float64, device=dev)
+        Rinv = torch.empty(int(lib.lsspa_gram_rinv_doubles(p)), dtype=torch.float64, device=dev)
+        info = torch.zeros((2, 2), dtype=torch.float64, device=dev)
+        check(lib.lsspa_chol_factor(G1.data_ptr(), p, R1.data_ptr(), Rinv.data_ptr(), info[0].data_ptr(),
+                                    _stream()), "lsspa_chol_factor")
+        G2 = self._sum([self._rows(Xc, yc, Rinv) for Xc, yc in self.chunks])
+        R2 = torch.empty_like(R1)
+        Rinv2 = torch.empty_like(Rinv)
+        check(lib.lsspa_chol_factor(G2.data_ptr(), p, R2.data_ptr(), Rinv2.data_ptr(), info[1].data_ptr(),
+                                    _stream()), "lsspa_chol_factor")
+        slot = torch.empty(tsqr_slot(p), dtype=torch.float64, device=dev)
+        check(lib.lsspa_tri_product(R2.data_ptr(), R1.data_ptr(), p, G1.data_ptr(), slot.data_ptr(), _stream()),
+              "lsspa_tri_product")
+        _count(3)
+        return slot, info
+
+
+def cholqr2_factor(chunks, p: int, divisor: float):
+    """One-shot helper: CholeskyQR2 over a list of device chunks [(X, y), ...]."""
+    f = CholQR2(p, divisor)
+    for Xc, yc in chunks:
+        f.add_chunk(Xc, yc)
+    return f.finish()
+
+
 def split_factor(slot: torch.Tensor, p: int):
     """(slot,) -> R (p,p) row-major upper triangular, c (p,), sum of squares of the y column."""
     q = p + 1
