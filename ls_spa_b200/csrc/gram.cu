@@ -50,34 +50,32 @@ struct GramParams {
 };
 
 // accumulate the Gram of the kGR x 8nt chunk C (row-major, stride ldr) into the warp's tiles:
-// warp g owns tile rows g and nt-1-g (their union has nt+1 tiles for every g: balanced)
+// warp g owns tile rows g and i2 = nt-1-g, i.e. the nt+1 tiles (g, g..nt-1) and (i2, i2..nt-1)
+// (every group has the same count: balanced).  acc[idx]: idx < nt-g -> tile (g, g+idx), else
+// tile (i2, i2 + idx - (nt-g)).
 template <int MAXNT>
 __device__ __forceinline__ void gram_chunk(const double *C, int ldr, int nt, int g, int lane,
-                                           double (&accA)[MAXNT][2], double (&accB)[MAXNT][2]) {
+                                           double (&acc)[MAXNT + 1][2]) {
   const int c = lane >> 2, q = lane & 3;
-  const int i2 = nt - 1 - g;
-#pragma unroll
+  const int i2 = nt - 1 - g, nA = nt - g;
+  const bool two = i2 > g;
+#pragma unroll 2
   for (int ks = 0; ks < kGR / 4; ++ks) {
     const double *row = C + (size_t)(4 * ks + q) * ldr + c;
-    double f[MAXNT];
+    const double fa = row[8 * g], fb = row[8 * i2];
 #pragma unroll
-    for (int t = 0; t < MAXNT; ++t) f[t] = (t >= g && t < nt) ? row[8 * t] : 0.0;
-    double fa = 0.0, fb = 0.0;
-#pragma unroll
-    for (int t = 0; t < MAXNT; ++t) {
-      if (t == g) fa = f[t];
-      if (t == i2) fb = f[t];
-    }
-#pragma unroll
-    for (int t = 0; t < MAXNT; ++t) {
-      if (t >= g && t < nt) dmma_g(accA[t][0], accA[t][1], fa, f[t]);
-      if (i2 > g && t >= i2 && t < nt) dmma_g(accB[t][0], accB[t][1], fb, f[t]);
+    for (int idx = 0; idx <= MAXNT; ++idx) {
+      if (idx < nA) {
+        dmma_g(acc[idx][0], acc[idx][1], fa, row[8 * (g + idx)]);
+      } else if (two && idx <= nt) {
+        dmma_g(acc[idx][0], acc[idx][1], fb, row[8 * (i2 + idx - nA)]);
+      }
     }
   }
 }
 
-template <int MAXNT>
-__global__ void __launch_bounds__(kGramThreads) gram_rows_kernel(GramParams a) {
+template <int MAXNT, int MINB>
+__global__ void __launch_bounds__(kGramThreads, MINB) gram_rows_kernel(GramParams a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int p = a.p, nt = a.nt, ldr = a.ldr, nc = 8 * nt;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -91,9 +89,9 @@ __global__ void __launch_bounds__(kGramThreads) gram_rows_kernel(GramParams a) {
   if (pass2)
     for (int e = tid; e < nc * ldr; e += kGramThreads) Ri[e] = a.Rinv[e];
 
-  double accA[MAXNT][2], accB[MAXNT][2];
+  double acc[MAXNT + 1][2];
 #pragma unroll
-  for (int t = 0; t < MAXNT; ++t) accA[t][0] = accA[t][1] = accB[t][0] = accB[t][1] = 0.0;
+  for (int t = 0; t <= MAXNT; ++t) acc[t][0] = acc[t][1] = 0.0;
   const int ngroups = (nt + 1) / 2;
   const bool has_group = warp < ngroups;
 
@@ -101,27 +99,27 @@ __global__ void __launch_bounds__(kGramThreads) gram_rows_kernel(GramParams a) {
   const int64_t r_begin = (int64_t)blockIdx.x * per;
   const int64_t r_end = (r_begin + per < a.nrows) ? r_begin + per : a.nrows;
 
-  constexpr int NPT = (kGR * 8 * MAXNT + kGramThreads - 1) / kGramThreads;
+  // staging: thread (rr = tid / 128, col = tid % 128) moves rows 2u + rr, u = 0..15, of column col
+  constexpr int NPT = kGR / 2;
+  const int rr = tid >> 7, col = tid & 127;
+  const bool live = col < nc;
   double stage[NPT];
   auto fetch = [&](int64_t r0) {
 #pragma unroll
     for (int u = 0; u < NPT; ++u) {
-      const int e = tid + u * kGramThreads;
-      const int row = e / nc, col = e - row * nc;
+      const int64_t r = r0 + 2 * u + rr;
       double v = 0.0;
-      if (e < kGR * nc && r0 + row < r_end) {
-        if (col < p) v = a.X[(r0 + row) * a.ldx + col];
-        else if (col == p) v = a.y[r0 + row];
+      if (live && r < r_end) {
+        if (col < p) v = a.X[r * a.ldx + col];
+        else if (col == p) v = a.y[r];
       }
       stage[u] = v;
     }
   };
   auto commit = [&](double *Z) {
+    if (live) {
 #pragma unroll
-    for (int u = 0; u < NPT; ++u) {
-      const int e = tid + u * kGramThreads;
-      const int row = e / nc, col = e - row * nc;
-      if (e < kGR * nc) Z[(size_t)row * ldr + col] = stage[u];
+      for (int u = 0; u < NPT; ++u) Z[(size_t)(2 * u + rr) * ldr + col] = stage[u];
     }
   };
   if (r_begin < r_end) {
@@ -160,7 +158,7 @@ __global__ void __launch_bounds__(kGramThreads) gram_rows_kernel(GramParams a) {
       __syncthreads();
       G_in = Qc;
     }
-    if (has_group) gram_chunk<MAXNT>(G_in, ldr, nt, warp, lane, accA, accB);
+    if (has_group) gram_chunk<MAXNT>(G_in, ldr, nt, warp, lane, acc);
     if (more) commit(Zn);
     __syncthreads();
     buf ^= 1;
@@ -170,13 +168,13 @@ __global__ void __launch_bounds__(kGramThreads) gram_rows_kernel(GramParams a) {
   for (int e = tid; e < nc * nc; e += kGramThreads) out[e] = 0.0;
   __syncthreads();
   if (has_group) {
-    const int g = warp, i2 = nt - 1 - g;
+    const int g = warp, i2 = nt - 1 - g, nA = nt - g;
 #pragma unroll
-    for (int t = 0; t < MAXNT; ++t) {
-      if (t >= g && t < nt)
-        *reinterpret_cast<double2 *>(out + (size_t)(8 * g + c) * nc + 8 * t + 2 * q) = make_double2(accA[t][0], accA[t][1]);
-      if (i2 > g && t >= i2 && t < nt)
-        *reinterpret_cast<double2 *>(out + (size_t)(8 * i2 + c) * nc + 8 * t + 2 * q) = make_double2(accB[t][0], accB[t][1]);
+    for (int idx = 0; idx <= MAXNT; ++idx) {
+      if (idx < nA)
+        *reinterpret_cast<double2 *>(out + (size_t)(8 * g + c) * nc + 8 * (g + idx) + 2 * q) = make_double2(acc[idx][0], acc[idx][1]);
+      else if (i2 > g && idx <= nt)
+        *reinterpret_cast<double2 *>(out + (size_t)(8 * i2 + c) * nc + 8 * (i2 + idx - nA) + 2 * q) = make_double2(acc[idx][0], acc[idx][1]);
     }
   }
 }
@@ -289,8 +287,14 @@ __global__ void tri_product_kernel(const double *R2, const double *R1, int q, co
 
 template <int MAXNT>
 static int launch_gram(const GramParams &a, size_t smem, cudaStream_t st) {
-  LSSPA_CUDA_TRY(cudaFuncSetAttribute(gram_rows_kernel<MAXNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  gram_rows_kernel<MAXNT><<<a.nparts, kGramThreads, smem, st>>>(a);
+  if (a.Rinv == nullptr) {   // pass 1: small shared-memory footprint, two CTAs per SM
+    LSSPA_CUDA_TRY(cudaFuncSetAttribute(gram_rows_kernel<MAXNT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gram_rows_kernel<MAXNT, 2><<<a.nparts, kGramThreads, smem, st>>>(a);
+    LSSPA_LAUNCH_CHECK();
+    return LSSPA_OK;
+  }
+  LSSPA_CUDA_TRY(cudaFuncSetAttribute(gram_rows_kernel<MAXNT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gram_rows_kernel<MAXNT, 1><<<a.nparts, kGramThreads, smem, st>>>(a);
   LSSPA_LAUNCH_CHECK();
   return LSSPA_OK;
 }
@@ -318,8 +322,7 @@ extern "C" int lsspa_gram_num_parts(int p, int64_t nrows, int pass2) {
   if (!lsspa_gram_supported(p) || nrows < 1) return 0;
   const DeviceInfo &d = device_info();
   const int sms = d.sm_count > 0 ? d.sm_count : 148;
-  (void)pass2;
-  int64_t cap = (int64_t)sms;  // 255 registers x 256 threads: one CTA per SM in both passes
+  int64_t cap = (int64_t)sms * (pass2 ? 1 : 2);  // pass 2 keeps R1^-1 in shared memory: one CTA per SM
   int64_t want = ceil_div(nrows, (int64_t)kGR * 4);
   return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
 }
