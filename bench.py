@@ -271,6 +271,10 @@ def run_gpu(args):
         peaks = read_peaks()
         fp64_peak, fp64_src = fp64_peak_tflops()
         ach = FLOP_PER_PERM * lift_perms / (lift_ms * 1e-3) / 1e12 if lift_ms > 0 else 0.0
+        # `achieved` counts SURVEY 8(d)'s algorithmic figure (7/3 p^3: Householder R + triangular
+        # solve).  The Cholesky route executes 1/3 p^3 + p^3; frac_executed rates the pipe on that.
+        chol = ops.LIFT_ROUTE == "cholesky"
+        exec_flop = (4.0 / 3.0 if chol else 7.0 / 3.0) * P ** 3
         bpp = lifts_dram_bytes_per_perm()
         traffic = bpp * lift_perms / max(len(trace), 1) if bpp is not None else None
         out = {
@@ -287,8 +291,12 @@ def run_gpu(args):
                     "d2h_bytes_per_step": d2h, "timer": "wall clock around ls_spa() incl. H2D/D2H, max over ranks"},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "pipe": "fp64 (DFMA/DMMA share one pipe; tcgen05 has no fp64)",
-                         "kernel": "lifts_kernel", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": ach / fp64_peak if fp64_peak else None, "traffic": traffic,
+                         "kernel": "lifts_chol_kernel" if chol else "lifts_mma_kernel",
+                         "route": ops.LIFT_ROUTE, "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": ach / fp64_peak if fp64_peak else None,
+                         "executed_flop_per_permutation": exec_flop,
+                         "frac_executed": (ach * exec_flop / FLOP_PER_PERM) / fp64_peak if fp64_peak else None,
+                         "traffic": traffic,
                          "traffic_note": "dram read+write bytes per launch from the committed ncu --set full capture, "
                                          "scaled to this launch size; algorithmic HBM bytes/launch = 1200 B x evaluations / 2",
                          "peak_source": fp64_src, "kernel_ms_per_step": lift_ms / args.steps,

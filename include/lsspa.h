@@ -135,6 +135,24 @@ LSSPA_API int lsspa_lifts(int p, const double *R_tr_cm, const double *c_tr, cons
                 int antithetical, double *lifts_out, void *workspace, size_t workspace_bytes,
                 void *stream);
 
+/* Fast route of the same function for well-conditioned reduced problems (49 <= p <= 128):
+ * the triangular factor of R_tr[:, perm] (np.linalg.qr, ls_spa/ls_spa.py:268) is computed as
+ * the Cholesky factor of the permuted Gram matrix of [R_tr | c_tr], so the forward error grows
+ * like eps * cond(R_tr)^2 instead of eps * cond(R_tr).
+ *   lsspa_lifts_gram   once per reduced problem: gram_out[0 .. (p+1)^2) = [R_tr|c_tr]^T [R_tr|c_tr],
+ *                      gram_out[(p+1)^2 + 0] = |R_tr|_F |R_tr^-1|_F  (>= cond_2, inf if singular),
+ *                      gram_out[(p+1)^2 + 1] = min|R_kk| / max|R_kk|; the rest is scratch.
+ *   lsspa_lifts_chol   same outputs as lsspa_lifts, reading gram_out instead of R_tr / c_tr.
+ * The caller decides from the condition estimate which route to take (ls_spa_b200/ops.py uses
+ * the Cholesky route when the estimate is <= 1e3, i.e. an expected error <= 1e-10). */
+LSSPA_API int lsspa_lifts_chol_supported(int p);
+LSSPA_API int64_t lsspa_lifts_gram_doubles(int p);
+LSSPA_API int lsspa_lifts_gram(int p, const double *R_tr_cm, const double *c_tr, double *gram_out,
+                     void *stream);
+LSSPA_API int lsspa_lifts_chol(int p, const double *gram, const double *R_te_cm, const double *c_te,
+                     double y_norm_sq, const int32_t *perms, int64_t count, int antithetical,
+                     double *lifts_out, void *stream);
+
 /* ------------------------------------------------------------------------
  * 4. Estimator                        replaces ls_spa/ls_spa.py:186-236
  *    (merge_sample_mean/cov :103-119, error_estimates :321-341, stop test :229).

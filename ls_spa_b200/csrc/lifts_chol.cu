@@ -1,0 +1,485 @@
+// Per-permutation core of LS-SPA for WELL-CONDITIONED reduced problems: the triangular factor of
+// R_tr[:, perm] (reference ls_spa/ls_spa.py:268, np.linalg.qr) is obtained as the Cholesky factor
+// of the permuted Gram matrix instead of by Householder reflections.
+//
+//   Gh = [R_tr | c_tr]^T [R_tr | c_tr]           (p+1) x (p+1), once per reduced problem
+//   Gh[pi^, pi^] = [R c]^T [R c]                  with pi^ = (perm, p):  R = chol, c = R^-T b
+//
+// R agrees with the QR factor up to row signs, which the lifts do not see.  The factorisation
+// is a left-looking blocked Cholesky on 8x8 tiles: every product is a DMMA, the only serial
+// part is the 8x8 diagonal block (8 pivots instead of the 8 full-height reflectors a Householder
+// panel needs), and the inverse of the diagonal block -- which the elimination phase needs
+// anyway -- falls out of the same pivots.  Forward error ~ eps * cond(R_tr)^2, so the host only
+// takes this route when lsspa_lifts_gram reports a small condition estimate; otherwise the
+// Householder kernel (lifts_mma.cu) runs.  Phase 2 (elimination of X = R_te[:, perm], reference
+// :279-283) is the same as in lifts_mma.cu.
+//
+// Fragment conventions as in lifts_mma.cu (lane = 4c + q): A[m=c][k=q], B[k=q][n=c],
+// C[m=c][n=2q+e]; "tile access" = lane touches M[i0+2q..+1][j0+c] of the column-major matrix.
+
+#include "common.cuh"
+
+namespace lsspa {
+namespace {
+
+struct CholParams {
+  int p;
+  int ld;
+  int rt;   // row tiles      ceil(p / 8)
+  int pt;   // column tiles   ceil((p + 1) / 8)
+  const double *Gh;   // (p+1) x (p+1) symmetric, leading dimension p+1
+  const double *Rte;  // column-major p x p
+  const double *cte;
+  double inv_ynsq;
+  const int32_t *perms;
+  int64_t count;
+  int anti;
+  double *out;
+  long long *dbg;  // optional cycle counters of block 0 (development aid), else nullptr
+};
+
+__device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(d0), "+d"(d1)
+      : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double2 ld_tile(const double *M, int ld, int i0, int j0, int c, int q) {
+  return *reinterpret_cast<const double2 *>(M + (size_t)(j0 + c) * ld + i0 + 2 * q);
+}
+__device__ __forceinline__ void st_tile(double *M, int ld, int i0, int j0, int c, int q, double2 v) {
+  *reinterpret_cast<double2 *>(M + (size_t)(j0 + c) * ld + i0 + 2 * q) = v;
+}
+
+// 1/d and 1/sqrt(d) from the 20-bit MUFU seeds and one cubic correction step each (relative
+// error ~ seed^3 ~ 1e-18 before the final rounding): 3 dependent fp64 operations after the seed
+// instead of the ~7 of the IEEE-exact library sequences.  These sit on the pivot chain.
+__device__ __forceinline__ double rcp_fast(double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  const double e = fma(-d, r, 1.0);
+  return fma(r, fma(e, e, e), r);
+}
+__device__ __forceinline__ double rsqrt_fast(double d) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  const double e = fma(-d * r, r, 1.0);
+  return fma(r * e, fma(0.375, e, 0.5), r);
+}
+
+// Pivots outside this range (or NaN) are not factored: the host never sends such a problem here,
+// the guard only keeps the arithmetic finite.
+constexpr double kPivMin = 1e-200, kPivMax = 1e200;
+
+// In-register factorisation of the diagonal tile.  (t0, t1) = T[m=c][n=2q+e], symmetric, only the
+// part m >= n is used.  nf pivots.  On return (t0, t1) = Lo = U^T (lower triangular Cholesky
+// factor; rows m >= nf carry the finished entries of the non-pivot rows, i.e. the c row), and
+// (y0, y1) = U^-1 in the layout Dbuf wants: lane (c, q) holds Uinv[2q+e][c].
+__device__ __forceinline__ void diag_factor(double &t0, double &t1, double &y0, double &y1, int nf, int lane) {
+  const int c = lane >> 2, q = lane & 3;
+  y0 = (c == 2 * q) ? 1.0 : 0.0;
+  y1 = (c == 2 * q + 1) ? 1.0 : 0.0;
+  double rs0 = 0.0, rs1 = 0.0, rsc = 0.0;  // rsqrt of the pivots of columns 2q, 2q+1 and c
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (j < nf) {
+      const double sel = (j & 1) ? t1 : t0;         // this lane's entry of column (2q' + (j&1)); column j on lanes q == j/2
+      const int jq = j >> 1;
+      const double d = __shfl_sync(kFull, sel, 4 * j + jq);
+      const double colm = __shfl_sync(kFull, sel, (lane & ~3) | jq);      // T[c][j]
+      const double cn0 = __shfl_sync(kFull, sel, (2 * q) * 4 + jq);       // T[2q][j]
+      const double cn1 = __shfl_sync(kFull, sel, (2 * q + 1) * 4 + jq);   // T[2q+1][j]
+      const double yj0 = __shfl_sync(kFull, y0, 4 * j + q);               // Y[j][2q]
+      const double yj1 = __shfl_sync(kFull, y1, 4 * j + q);               // Y[j][2q+1]
+      const bool ok = (d > kPivMin) && (d < kPivMax);
+      const double ri = ok ? rcp_fast(d) : 0.0;
+      const double rs = ok ? rsqrt_fast(d) : 0.0;
+      if (2 * q == j) rs0 = rs;
+      if (2 * q + 1 == j) rs1 = rs;
+      if (c == j) rsc = rs;
+      if (c > j) {
+        const double f = colm * ri;
+        if (2 * q > j) t0 = fma(-f, cn0, t0);
+        if (2 * q + 1 > j) t1 = fma(-f, cn1, t1);
+        y0 = fma(-f, yj0, y0);
+        y1 = fma(-f, yj1, y1);
+      }
+    }
+  }
+  // Lo[m][n] = T_n[m][n] * rsqrt(d_n) for m >= n, n < nf
+  t0 = (c >= 2 * q && 2 * q < nf) ? t0 * rs0 : 0.0;
+  t1 = (c >= 2 * q + 1 && 2 * q + 1 < nf) ? t1 * rs1 : 0.0;
+  // Uinv[u][jj] = Y[jj][u] * rsqrt(d_jj); columns jj >= nf are zero
+  y0 = (c < nf) ? y0 * rsc : 0.0;
+  y1 = (c < nf) ? y1 * rsc : 0.0;
+}
+
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(256, MINB) lifts_chol_kernel(CholParams a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int p = a.p, ld = a.ld, RT = a.rt, PT = a.pt;
+  const int NR = 8 * RT, NC = 8 * PT;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c = lane >> 2, q = lane & 3;
+  constexpr int NTL = (MAXT + 1 + 7) / 8;  // column tiles of one row block per warp
+
+  double *A = reinterpret_cast<double *>(smem_raw);  // upper tiles of the permuted Gram matrix -> R, c
+  double *Dbuf = A + (size_t)NC * ld;                 // RT x 64: inverses of the diagonal blocks of R
+  double *wcost = Dbuf + (size_t)RT * 64;             // 8 x NR per-warp cost partials
+  double *cost = wcost + (size_t)8 * NR;              // p + 2
+  double *acc = cost + (p + 2);                       // p
+  int *perm_s = reinterpret_cast<int *>(acc + p + (p & 1));  // p + 1
+
+  const int halves = a.anti ? 2 : 1;
+  const double weight = a.anti ? 0.5 : 1.0;
+  const int ldg = p + 1;
+
+  for (int64_t sidx = blockIdx.x; sidx < a.count; sidx += gridDim.x) {
+    for (int h = 0; h < halves; ++h) {
+      __syncthreads();
+      for (int k = tid; k <= p; k += 256)
+        perm_s[k] = (k == p) ? p : a.perms[sidx * p + (h == 0 ? k : p - 1 - k)];
+      __syncthreads();
+      const long long t_a = clock64();
+      // ---- phase 0: gather the upper tiles of Gh[pi^, pi^] (rows < p, columns <= p), zero padding
+      {
+        const int half = NR / 2, tot = NC * half;
+#pragma unroll 8
+        for (int e = tid; e < tot; e += 256) {
+          const int l = e / half, i = 2 * (e - l * half);
+          if ((i >> 3) <= (l >> 3)) {
+            double2 v = make_double2(0.0, 0.0);
+            if (l <= p) {
+              const double *src = a.Gh + (size_t)perm_s[l] * ldg;
+              if (i < p) v.x = __ldg(src + perm_s[i]);
+              if (i + 1 < p) v.y = __ldg(src + perm_s[i + 1]);
+            }
+            *reinterpret_cast<double2 *>(A + (size_t)l * ld + i) = v;
+          }
+        }
+      }
+      if (warp == 7) {
+        double s0 = 0.0;
+        for (int i = lane; i < p; i += 32) s0 = fma(a.cte[i], a.cte[i], s0);
+        s0 = warp_sum(s0);
+        if (lane == 0) cost[0] = s0;
+      }
+      for (int e = tid; e < 8 * NR; e += 256) wcost[e] = 0.0;
+      __syncthreads();
+
+      const long long t_b = clock64();
+      long long t_acc = 0, t_diag = 0, t_wait = 0;
+      // ---- phase 1: left-looking blocked Cholesky, row block s per step.  Warp w owns the tiles
+      // (s, s + w) and (s, s + w + 8): tile - sum_{k<s} R_kL^T R_ks accumulates in registers, warp 0
+      // factors the diagonal tile and publishes its inverse, the others scale with it.
+      for (int s = 0; s < RT; ++s) {
+        const int nf = (p - 8 * s < 8) ? p - 8 * s : 8;
+        const long long u0 = clock64();
+        double2 tv[NTL];
+#pragma unroll
+        for (int t = 0; t < NTL; ++t) {
+          const int L = s + warp + 8 * t;
+          tv[t] = make_double2(0.0, 0.0);
+          if (L < PT) {
+            double p0 = 0.0, p1 = 0.0, r0 = 0.0, r1 = 0.0;
+            int k = 0;
+            for (; k + 1 < s; k += 2) {
+              const double2 xa = ld_tile(A, ld, 8 * k, 8 * L, c, q);
+              const double2 xb = ld_tile(A, ld, 8 * k, 8 * s, c, q);
+              const double2 ya = ld_tile(A, ld, 8 * k + 8, 8 * L, c, q);
+              const double2 yb = ld_tile(A, ld, 8 * k + 8, 8 * s, c, q);
+              dmma(p0, p1, xa.x, xb.x);
+              dmma(r0, r1, ya.x, yb.x);
+              dmma(p0, p1, xa.y, xb.y);
+              dmma(r0, r1, ya.y, yb.y);
+            }
+            if (k < s) {
+              const double2 xa = ld_tile(A, ld, 8 * k, 8 * L, c, q);
+              const double2 xb = ld_tile(A, ld, 8 * k, 8 * s, c, q);
+              dmma(p0, p1, xa.x, xb.x);
+              dmma(p0, p1, xa.y, xb.y);
+            }
+            const double2 g = ld_tile(A, ld, 8 * s, 8 * L, c, q);
+            tv[t].x = g.x - (p0 + r0);
+            tv[t].y = g.y - (p1 + r1);
+          }
+        }
+        const long long u1 = clock64();
+        t_acc += u1 - u0;
+        if (warp == 0) {
+          double y0, y1;
+          diag_factor(tv[0].x, tv[0].y, y0, y1, nf, lane);
+          st_tile(A, ld, 8 * s, 8 * s, c, q, tv[0]);
+          *reinterpret_cast<double2 *>(Dbuf + s * 64 + c * 8 + 2 * q) = make_double2(y0, y1);
+        }
+        const long long u2 = clock64();
+        t_diag += u2 - u1;
+        __syncthreads();
+        t_wait += clock64() - u2;
+        {
+          const double2 dv = ld_tile(Dbuf + s * 64, 8, 0, 0, c, q);
+#pragma unroll
+          for (int t = 0; t < NTL; ++t) {
+            const int L = s + warp + 8 * t;
+            if (L < PT && L > s) {
+              double r0 = 0.0, r1 = 0.0;
+              dmma(r0, r1, tv[t].x, dv.x);
+              dmma(r0, r1, tv[t].y, dv.y);
+              st_tile(A, ld, 8 * s, 8 * L, c, q, make_double2(r0, r1));
+            }
+          }
+        }
+        __syncthreads();
+      }
+
+      const long long t_c = clock64();
+      // ---- phase 2: X = R_te[:, perm] eliminated against R, one warp per 8-row tile, registers only
+      double *wc = wcost + (size_t)warp * NR;
+      const double *cvec = A + (size_t)p * ld;
+      for (int it = warp; it < RT; it += 8) {
+        const int row = 8 * it + c;  // C layout: lane (m = row, n = columns 2q+e)
+        double xr[MAXT][2];
+#pragma unroll
+        for (int L = 0; L < MAXT; ++L) {
+          xr[L][0] = 0.0;
+          xr[L][1] = 0.0;
+          if (L < RT) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int l = 8 * L + 2 * q + e;
+              if (l < p) {
+                const int col = perm_s[l];
+                if (row <= col) xr[L][e] = a.Rte[(size_t)col * p + row];
+              }
+            }
+          }
+        }
+        double r_in = (row < p) ? a.cte[row] : 0.0;
+#pragma unroll
+        for (int J = 0; J < MAXT; ++J) {
+          if (J < RT) {
+            const double2 dv = ld_tile(Dbuf + J * 64, 8, 0, 0, c, q);
+            double m0 = 0.0, m1 = 0.0;  // M_J = X_J R_JJ^-1, C layout (row, column 2q+e of the panel)
+            dmma(m0, m1, xr[J][0], dv.x);
+            dmma(m0, m1, xr[J][1], dv.y);
+            // running test residual of this row after each of the 8 columns of the panel
+            const double2 cv = *reinterpret_cast<const double2 *>(cvec + 8 * J + 2 * q);
+            const double t0 = m0 * cv.x, t1 = m1 * cv.y;
+            const double sl = t0 + t1;
+            double P = sl;
+            double up = __shfl_up_sync(kFull, P, 1, 4);
+            if (q >= 1) P += up;
+            up = __shfl_up_sync(kFull, P, 2, 4);
+            if (q >= 2) P += up;
+            const double ra = r_in - (P - sl) - t0;
+            const double rb = r_in - P;
+            double d0 = ra * ra, d1 = rb * rb;
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+              d0 += __shfl_xor_sync(kFull, d0, o);
+              d1 += __shfl_xor_sync(kFull, d1, o);
+            }
+            if (c == 0) {
+              const int k0 = 8 * J + 2 * q;
+              if (k0 < p) wc[k0] += d0;          // wc[k] collects cost_{k+1}
+              if (k0 + 1 < p) wc[k0 + 1] += d1;
+            }
+            r_in -= __shfl_sync(kFull, P, 3, 4);
+            m0 = -m0;
+            m1 = -m1;
+#pragma unroll
+            for (int L = 0; L < MAXT; ++L) {
+              if (L > J && L < RT) {
+                const double2 rt = ld_tile(A, ld, 8 * J, 8 * L, c, q);
+                dmma(xr[L][0], xr[L][1], m0, rt.x);
+                dmma(xr[L][0], xr[L][1], m1, rt.y);
+              }
+            }
+          }
+        }
+      }
+      const long long t_d = clock64();
+      __syncthreads();
+      if (a.dbg != nullptr && blockIdx.x == 0 && lane == 0 && sidx == blockIdx.x && h == 0) {
+        long long *d = a.dbg + warp * 8;
+        d[0] = t_b - t_a;   // gather
+        d[1] = t_diag;      // diagonal blocks (warp 0)
+        d[2] = t_acc;       // accumulation of the row block
+        d[3] = t_wait;      // waiting for the diagonal block
+        d[4] = t_c - t_b;   // whole phase 1
+        d[5] = t_d - t_c;   // phase 2 (this warp)
+      }
+      for (int k = tid; k < p; k += 256) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sacc += wcost[(size_t)w * NR + k];
+        cost[k + 1] = sacc;
+      }
+      __syncthreads();
+      for (int k = tid; k < p; k += 256) {
+        const double lift = (cost[k] - cost[k + 1]) * a.inv_ynsq;
+        const int f = perm_s[k];
+        acc[f] = (h == 0 ? 0.0 : acc[f]) + weight * lift;
+      }
+    }
+    __syncthreads();
+    for (int f = tid; f < p; f += 256) a.out[sidx * p + f] = acc[f];
+  }
+}
+
+int chol_ld(int rt) {
+  const int n = 8 * rt;
+  return (n % 16 == 8) ? n : n + 8;
+}
+
+size_t chol_smem_bytes(int p) {
+  const int rt = (p + 7) / 8, pt = (p + 8) / 8;
+  const int ld = chol_ld(rt);
+  const size_t d = (size_t)8 * pt * ld + (size_t)rt * 64 + (size_t)64 * rt + (size_t)(p + 2) + (size_t)(p + 1);
+  return d * sizeof(double) + (size_t)(p + 1) * sizeof(int) + 32;
+}
+
+template <int MAXT, int MINB>
+int launch_chol(const CholParams &a, int grid, size_t smem, cudaStream_t st) {
+  LSSPA_CUDA_TRY(cudaFuncSetAttribute(lifts_chol_kernel<MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+  LSSPA_CUDA_TRY(cudaFuncSetAttribute(lifts_chol_kernel<MAXT, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared));
+  lifts_chol_kernel<MAXT, MINB><<<grid, 256, smem, st>>>(a);
+  LSSPA_LAUNCH_CHECK();
+  return LSSPA_OK;
+}
+
+// Gh = [R | c]^T [R | c] for upper-triangular R (column-major, ld p): block (i), thread (j)
+__global__ void lift_gram_kernel(int p, const double *__restrict__ R, const double *__restrict__ cvec,
+                                 double *__restrict__ Gh) {
+  const int i = blockIdx.x;  // 0..p
+  const double *ci = (i < p) ? R + (size_t)i * p : cvec;
+  const int ni = (i < p) ? i + 1 : p;
+  for (int j = threadIdx.x; j <= p; j += blockDim.x) {
+    const double *cj = (j < p) ? R + (size_t)j * p : cvec;
+    const int nj = (j < p) ? j + 1 : p;
+    const int n = ni < nj ? ni : nj;
+    double s0 = 0.0, s1 = 0.0;
+    int k = 0;
+    for (; k + 1 < n; k += 2) {
+      s0 = fma(ci[k], cj[k], s0);
+      s1 = fma(ci[k + 1], cj[k + 1], s1);
+    }
+    if (k < n) s0 = fma(ci[k], cj[k], s0);
+    Gh[(size_t)i * (p + 1) + j] = s0 + s1;
+  }
+}
+
+// info[0] = |R|_F |R^-1|_F (>= cond_2(R)), info[1] = min |R_kk| / max |R_kk|.  One CTA; thread j
+// solves R x = e_j by back substitution (x has j + 1 non-zeros).  inf when R is singular.
+__global__ void lift_cond_kernel(int p, const double *__restrict__ R, double *__restrict__ info,
+                                 double *__restrict__ scratch /* p * p */) {
+  __shared__ double red[3][32];
+  double fr = 0.0, fi = 0.0, dmin = 1e300, dmax = 0.0;
+  for (int j = threadIdx.x; j < p; j += blockDim.x) {
+    double *x = scratch + (size_t)j * p;
+    for (int i = j; i >= 0; --i) {
+      double sacc = (i == j) ? 1.0 : 0.0;
+      for (int k = i + 1; k <= j; ++k) sacc = fma(-R[(size_t)k * p + i], x[k], sacc);
+      const double v = sacc / R[(size_t)i * p + i];
+      x[i] = v;
+      fi = fma(v, v, fi);
+      const double r = R[(size_t)j * p + i];
+      fr = fma(r, r, fr);
+    }
+    const double d = fabs(R[(size_t)j * p + j]);
+    dmin = fmin(dmin, d);
+    dmax = fmax(dmax, d);
+  }
+  fr = warp_sum(fr);
+  fi = warp_sum(fi);
+  for (int o = 16; o > 0; o >>= 1) {
+    dmin = fmin(dmin, __shfl_xor_sync(kFull, dmin, o));
+    dmax = fmax(dmax, __shfl_xor_sync(kFull, dmax, o));
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __shared__ double rmin[32], rmax[32];
+  if (l == 0) {
+    red[0][w] = fr;
+    red[1][w] = fi;
+    rmin[w] = dmin;
+    rmax[w] = dmax;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int nw = (blockDim.x + 31) / 32;
+    double a = 0.0, b = 0.0, mn = 1e300, mx = 0.0;
+    for (int k = 0; k < nw; ++k) {
+      a += red[0][k];
+      b += red[1][k];
+      mn = fmin(mn, rmin[k]);
+      mx = fmax(mx, rmax[k]);
+    }
+    const double cnd = sqrt(a) * sqrt(b);
+    info[0] = (cnd == cnd) ? cnd : INFINITY;
+    info[1] = (mx > 0.0) ? mn / mx : 0.0;
+  }
+}
+
+}  // namespace
+
+extern long long *g_lifts_dbg;  // lifts_mma.cu
+
+bool lifts_chol_supported(int p) { return p >= 49 && p <= 128; }
+
+}  // namespace lsspa
+
+using namespace lsspa;
+
+extern "C" int lsspa_lifts_chol_supported(int p) { return lifts_chol_supported(p) ? 1 : 0; }
+
+extern "C" int64_t lsspa_lifts_gram_doubles(int p) {
+  if (p < 1) return 0;
+  return (int64_t)(p + 1) * (p + 1) + 8 + (int64_t)p * p;  // Gh, info[8], scratch of the estimate
+}
+
+extern "C" int lsspa_lifts_gram(int p, const double *R_tr_cm, const double *c_tr, double *gram_out, void *stream) {
+  if (p < 1 || !R_tr_cm || !c_tr || !gram_out) return LSSPA_E_BADARG;
+  cudaStream_t st = as_stream(stream);
+  lift_gram_kernel<<<p + 1, 128, 0, st>>>(p, R_tr_cm, c_tr, gram_out);
+  LSSPA_LAUNCH_CHECK();
+  double *info = gram_out + (size_t)(p + 1) * (p + 1);
+  lift_cond_kernel<<<1, 128, 0, st>>>(p, R_tr_cm, info, info + 8);
+  LSSPA_LAUNCH_CHECK();
+  return LSSPA_OK;
+}
+
+extern "C" int lsspa_lifts_chol(int p, const double *gram, const double *R_te_cm, const double *c_te,
+                                double y_norm_sq, const int32_t *perms, int64_t count, int antithetical,
+                                double *lifts_out, void *stream) {
+  if (!lifts_chol_supported(p)) return LSSPA_E_UNSUPPORTED;
+  if (!gram || !R_te_cm || !c_te || !lifts_out || (count > 0 && !perms) || !(y_norm_sq > 0.0)) return LSSPA_E_BADARG;
+  if (count == 0) return LSSPA_OK;
+  if (count < 0) return LSSPA_E_BADARG;
+  CholParams a;
+  a.p = p;
+  a.rt = (p + 7) / 8;
+  a.pt = (p + 8) / 8;
+  a.ld = chol_ld(a.rt);
+  a.Gh = gram;
+  a.Rte = R_te_cm;
+  a.cte = c_te;
+  a.inv_ynsq = 1.0 / y_norm_sq;
+  a.perms = perms;
+  a.count = count;
+  a.anti = antithetical ? 1 : 0;
+  a.out = lifts_out;
+  a.dbg = g_lifts_dbg;
+  const size_t smem = chol_smem_bytes(p);
+  const DeviceInfo &d = device_info();
+  const int sms = d.sm_count > 0 ? d.sm_count : 148;
+  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 2) per_sm = 2;
+  int64_t grid = (int64_t)per_sm * sms;
+  if (grid > count) grid = count;
+  cudaStream_t st = as_stream(stream);
+  if (a.rt <= 8) return launch_chol<8, 2>(a, (int)grid, smem, st);
+  if (a.rt <= 13) return launch_chol<13, 2>(a, (int)grid, smem, st);
+  return launch_chol<16, 1>(a, (int)grid, smem, st);
+}

@@ -9,6 +9,7 @@ raise ``LsSpaCudaError`` otherwise -- there is no CPU path.
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 
@@ -21,6 +22,11 @@ ERR_DRAWS = 1024
 LAUNCHES = 0
 # when set to a list, every lifts() call appends (start_event, end_event, permutations)
 LIFT_TRACE = None
+# |R_tr|_F |R_tr^-1|_F above which the per-permutation core keeps to Householder reflections:
+# the Cholesky route loses eps * cond^2, 1e3 keeps that at ~1e-10 of the lift scale.
+CHOL_COND_LIMIT = 1e3
+# route taken by the most recent lifts() call: 'cholesky' or 'householder' (bench.py reports it)
+LIFT_ROUTE = None
 
 
 def _count(n: int) -> None:
@@ -247,6 +253,21 @@ class ReducedProblem:
         self.c_te = _dev_f64(c_te, "c_te").contiguous()
         self.y_norm_sq = float(y_norm_sq)
         self._ws = None
+        # Route of the per-permutation core: Cholesky of the permuted Gram matrix when the
+        # train factor is well conditioned (error ~ eps * cond^2), Householder otherwise.
+        self.gram = None
+        self.cond_estimate = float("inf")
+        self.use_chol = False
+        forced = os.environ.get("LSSPA_LIFTS_IMPL", "")
+        if forced not in ("v1", "householder") and _lib().lsspa_lifts_chol_supported(p):
+            n = _lib().lsspa_lifts_gram_doubles(p)
+            self.gram = torch.empty(n, dtype=torch.float64, device=dev)
+            check(_lib().lsspa_lifts_gram(p, self.R_tr_cm.data_ptr(), self.c_tr.data_ptr(),
+                                          self.gram.data_ptr(), _stream()), "lsspa_lifts_gram")
+            _count(2)
+            info = self.gram[(p + 1) * (p + 1):(p + 1) * (p + 1) + 2].cpu()
+            self.cond_estimate = float(info[0])
+            self.use_chol = forced == "chol" or self.cond_estimate <= CHOL_COND_LIMIT
 
     def workspace(self, count: int):
         nbytes = _lib().lsspa_lifts_workspace_bytes(self.p, count)
@@ -272,10 +293,17 @@ def lifts(prob: ReducedProblem, perms: torch.Tensor, antithetical: bool, out: to
     if trace is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    check(_lib().lsspa_lifts(p, prob.R_tr_cm.data_ptr(), prob.c_tr.data_ptr(), prob.R_te_cm.data_ptr(),
-                             prob.c_te.data_ptr(), prob.y_norm_sq, perms.data_ptr(), count,
-                             1 if antithetical else 0, out.data_ptr(), _ptr(ws), nbytes, _stream()),
-          "lsspa_lifts")
+    global LIFT_ROUTE
+    LIFT_ROUTE = "cholesky" if prob.use_chol else "householder"
+    if prob.use_chol:
+        check(_lib().lsspa_lifts_chol(p, prob.gram.data_ptr(), prob.R_te_cm.data_ptr(), prob.c_te.data_ptr(),
+                                      prob.y_norm_sq, perms.data_ptr(), count, 1 if antithetical else 0,
+                                      out.data_ptr(), _stream()), "lsspa_lifts_chol")
+    else:
+        check(_lib().lsspa_lifts(p, prob.R_tr_cm.data_ptr(), prob.c_tr.data_ptr(), prob.R_te_cm.data_ptr(),
+                                 prob.c_te.data_ptr(), prob.y_norm_sq, perms.data_ptr(), count,
+                                 1 if antithetical else 0, out.data_ptr(), _ptr(ws), nbytes, _stream()),
+              "lsspa_lifts")
     _count(1)
     if trace is not None:
         e1.record()

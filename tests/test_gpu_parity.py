@@ -104,7 +104,12 @@ def test_lifts_match_reference(T, name):
     g = load_golden(name)
     prob = device_problem(T, g)
     methods = ["random", "argsort", "permutohedron"] + (["exact"] if f"perms_exact" in g.files else [])
-    for method in methods:
+    # both routes of the per-permutation core: Householder always, Cholesky where it is offered
+    routes = [False] + ([True] if prob.gram is not None else [])
+    if name.startswith("syn_p100"):
+        assert prob.use_chol and prob.cond_estimate < 1e3, prob.cond_estimate   # the golden data are benign
+    for method, route in itertools.product(methods, routes):
+        prob.use_chol = route
         perms = g[f"perms_{method}"].astype(np.int32)
         got = ops.lifts(prob, T.from_numpy(perms).cuda(), False).cpu().numpy()
         want = g[f"lifts_{method}"]
@@ -128,13 +133,48 @@ def test_lifts_bitwise_reproducible(T):
         p = int(g["p"])
         prob = device_problem(T, g)
         perms = samplers.PermutohedronSource(p, 3, None, dev).take(1500)
-        base = ops.lifts(prob, perms, True).cpu().numpy()
-        for _ in range(3):
-            assert np.array_equal(ops.lifts(prob, perms, True).cpu().numpy(), base), name
-        parts = [ops.lifts(prob, perms[a:b].contiguous(), True).cpu().numpy()
-                 for a, b in ((0, 7), (7, 300), (300, 1500))]
-        assert np.array_equal(np.vstack(parts), base), name
-        np.testing.assert_allclose(base.sum(axis=1), float(g["argsort_anti0_r_squared"]), atol=1e-10)
+        for route in [False] + ([True] if prob.gram is not None else []):
+            prob.use_chol = route
+            base = ops.lifts(prob, perms, True).cpu().numpy()
+            for _ in range(3):
+                assert np.array_equal(ops.lifts(prob, perms, True).cpu().numpy(), base), (name, route)
+            parts = [ops.lifts(prob, perms[a:b].contiguous(), True).cpu().numpy()
+                     for a, b in ((0, 7), (7, 300), (300, 1500))]
+            assert np.array_equal(np.vstack(parts), base), (name, route)
+            np.testing.assert_allclose(base.sum(axis=1), float(g["argsort_anti0_r_squared"]), atol=1e-10)
+
+
+def test_lift_route_selection(T):
+    """The Cholesky route (error ~ eps cond^2) is only taken for well-conditioned train factors;
+    both routes agree there for every tile count, and ill-conditioned or singular factors keep
+    to Householder."""
+    from ls_spa_b200 import ops, samplers
+    dev = T.device("cuda")
+    rng = np.random.default_rng(5)
+    f = lambda a: T.from_numpy(np.ascontiguousarray(a)).to(dev)
+    for p in (49, 56, 64, 71, 100, 104, 120, 128):
+        R1 = np.linalg.qr(rng.standard_normal((3 * p, p)) / np.sqrt(3 * p), mode="r")
+        R2 = np.linalg.qr(rng.standard_normal((3 * p, p)), mode="r")
+        c1, c2 = rng.standard_normal(p), rng.standard_normal(p)
+        prob = ops.ReducedProblem(f(R1), f(c1), f(R2), f(c2), float(c2 @ c2) * 1.5)
+        assert prob.use_chol and prob.cond_estimate >= np.linalg.cond(R1) * (1 - 1e-12)
+        perms = samplers.ArgsortSource(p, 11, None, dev).take(600)
+        for anti in (False, True):
+            prob.use_chol = True
+            a = ops.lifts(prob, perms, anti).cpu().numpy()
+            prob.use_chol = False
+            b = ops.lifts(prob, perms, anti).cpu().numpy()
+            assert scaled_err(a, b) < 1e-11, (p, anti, scaled_err(a, b))
+    p = 100
+    R2 = np.linalg.qr(rng.standard_normal((3 * p, p)), mode="r")
+    c1, c2 = rng.standard_normal(p), rng.standard_normal(p)
+    U, _, Vt = np.linalg.svd(rng.standard_normal((p, p)))
+    for smin in (1e-6, 0.0):
+        ill = np.linalg.qr((U * np.geomspace(1.0, max(smin, 1e-300), p)) @ Vt, mode="r")
+        if smin == 0.0:
+            ill[-1, -1] = 0.0
+        prob = ops.ReducedProblem(f(ill), f(c1), f(R2), f(c2), float(c2 @ c2) * 1.5)
+        assert not prob.use_chol and prob.cond_estimate > 1e5, (smin, prob.cond_estimate)
 
 
 def test_square_shapley_export(T, L):

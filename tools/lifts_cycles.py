@@ -6,6 +6,9 @@ from ls_spa_b200 import ops, samplers, _cabi
 dev = torch.device("cuda")
 p = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 prob = synth_problem(p, dev)
+if len(sys.argv) > 2:
+    prob.use_chol = sys.argv[2] == "chol"
+print("route:", "chol" if prob.use_chol else "householder")
 perms = samplers.PermutohedronSource(p, 42, None, dev).take(4096)
 buf = torch.zeros(64, dtype=torch.int64, device=dev)
 lib = _cabi.load()
@@ -16,6 +19,6 @@ ops.lifts(prob, perms, True)
 torch.cuda.synchronize()
 lib.lsspa_debug_set_lifts_counters(None)
 d = buf.cpu().numpy().reshape(8, 8).copy()
-print("warp  gather   panel  trailing  barrier-wait  phase1  phase1.5+2")
+print("warp  gather   panel|diag  trailing|accumulate  barrier-wait  phase1  phase1.5+2")
 for w in range(8):
     print(w, d[w, :6])
