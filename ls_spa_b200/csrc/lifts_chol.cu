@@ -113,14 +113,20 @@ __device__ __forceinline__ void diag_factor(double &t0, double &t1, double &y0, 
   y1 = (c < nf) ? y1 * rsc : 0.0;
 }
 
-template <int MAXT, int MINB>
+// leading dimension of the tile array (column-major, ld % 16 == 8: conflict-free tile accesses)
+__host__ __device__ constexpr int chol_ld(int rt) { return ((8 * rt) % 16 == 8) ? 8 * rt : 8 * rt + 8; }
+
+// The tile geometry (RT row tiles, PT = RT or RT + 1 column tiles) is a template parameter: every
+// tile address is then base + immediate and no tile loop carries a run-time guard.
+template <int RT, int PT, int MINB>
 __global__ void __launch_bounds__(256, MINB) lifts_chol_kernel(CholParams a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int p = a.p, ld = a.ld, RT = a.rt, PT = a.pt;
-  const int NR = 8 * RT, NC = 8 * PT;
+  const int p = a.p;
+  constexpr int ld = chol_ld(RT);
+  constexpr int NR = 8 * RT, NC = 8 * PT;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int c = lane >> 2, q = lane & 3;
-  constexpr int NTL = (MAXT + 1 + 7) / 8;  // column tiles of one row block per warp
+  constexpr int NTL = (PT + 7) / 8;  // column tiles of one row block per warp
 
   double *A = reinterpret_cast<double *>(smem_raw);  // upper tiles of the permuted Gram matrix -> R, c
   double *Dbuf = A + (size_t)NC * ld;                 // RT x 64: inverses of the diagonal blocks of R
@@ -237,12 +243,12 @@ __global__ void __launch_bounds__(256, MINB) lifts_chol_kernel(CholParams a) {
       const double *cvec = A + (size_t)p * ld;
       for (int it = warp; it < RT; it += 8) {
         const int row = 8 * it + c;  // C layout: lane (m = row, n = columns 2q+e)
-        double xr[MAXT][2];
+        double xr[RT][2];
 #pragma unroll
-        for (int L = 0; L < MAXT; ++L) {
+        for (int L = 0; L < RT; ++L) {
           xr[L][0] = 0.0;
           xr[L][1] = 0.0;
-          if (L < RT) {
+          {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
               const int l = 8 * L + 2 * q + e;
@@ -255,8 +261,8 @@ __global__ void __launch_bounds__(256, MINB) lifts_chol_kernel(CholParams a) {
         }
         double r_in = (row < p) ? a.cte[row] : 0.0;
 #pragma unroll
-        for (int J = 0; J < MAXT; ++J) {
-          if (J < RT) {
+        for (int J = 0; J < RT; ++J) {
+          {
             const double2 dv = ld_tile(Dbuf + J * 64, 8, 0, 0, c, q);
             double m0 = 0.0, m1 = 0.0;  // M_J = X_J R_JJ^-1, C layout (row, column 2q+e of the panel)
             dmma(m0, m1, xr[J][0], dv.x);
@@ -287,8 +293,8 @@ __global__ void __launch_bounds__(256, MINB) lifts_chol_kernel(CholParams a) {
             m0 = -m0;
             m1 = -m1;
 #pragma unroll
-            for (int L = 0; L < MAXT; ++L) {
-              if (L > J && L < RT) {
+            for (int L = 0; L < RT; ++L) {
+              if (L > J) {
                 const double2 rt = ld_tile(A, ld, 8 * J, 8 * L, c, q);
                 dmma(xr[L][0], xr[L][1], m0, rt.x);
                 dmma(xr[L][0], xr[L][1], m1, rt.y);
@@ -326,11 +332,6 @@ __global__ void __launch_bounds__(256, MINB) lifts_chol_kernel(CholParams a) {
   }
 }
 
-int chol_ld(int rt) {
-  const int n = 8 * rt;
-  return (n % 16 == 8) ? n : n + 8;
-}
-
 size_t chol_smem_bytes(int p) {
   const int rt = (p + 7) / 8, pt = (p + 8) / 8;
   const int ld = chol_ld(rt);
@@ -338,15 +339,21 @@ size_t chol_smem_bytes(int p) {
   return d * sizeof(double) + (size_t)(p + 1) * sizeof(int) + 32;
 }
 
-template <int MAXT, int MINB>
+template <int RT, int PT, int MINB>
 int launch_chol(const CholParams &a, int grid, size_t smem, cudaStream_t st) {
-  LSSPA_CUDA_TRY(cudaFuncSetAttribute(lifts_chol_kernel<MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  LSSPA_CUDA_TRY(cudaFuncSetAttribute(lifts_chol_kernel<RT, PT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
-  LSSPA_CUDA_TRY(cudaFuncSetAttribute(lifts_chol_kernel<MAXT, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+  LSSPA_CUDA_TRY(cudaFuncSetAttribute(lifts_chol_kernel<RT, PT, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                       cudaSharedmemCarveoutMaxShared));
-  lifts_chol_kernel<MAXT, MINB><<<grid, 256, smem, st>>>(a);
+  lifts_chol_kernel<RT, PT, MINB><<<grid, 256, smem, st>>>(a);
   LSSPA_LAUNCH_CHECK();
   return LSSPA_OK;
+}
+
+template <int RT>
+int launch_chol_rt(const CholParams &a, int grid, size_t smem, cudaStream_t st) {
+  constexpr int MINB = RT <= 13 ? 2 : 1;
+  return (a.pt == RT) ? launch_chol<RT, RT, MINB>(a, grid, smem, st) : launch_chol<RT, RT + 1, MINB>(a, grid, smem, st);
 }
 
 // Gh = [R | c]^T [R | c] for upper-triangular R (column-major, ld p): block (i), thread (j)
@@ -479,7 +486,17 @@ extern "C" int lsspa_lifts_chol(int p, const double *gram, const double *R_te_cm
   int64_t grid = (int64_t)per_sm * sms;
   if (grid > count) grid = count;
   cudaStream_t st = as_stream(stream);
-  if (a.rt <= 8) return launch_chol<8, 2>(a, (int)grid, smem, st);
-  if (a.rt <= 13) return launch_chol<13, 2>(a, (int)grid, smem, st);
-  return launch_chol<16, 1>(a, (int)grid, smem, st);
+  switch (a.rt) {
+    case 7: return launch_chol_rt<7>(a, (int)grid, smem, st);
+    case 8: return launch_chol_rt<8>(a, (int)grid, smem, st);
+    case 9: return launch_chol_rt<9>(a, (int)grid, smem, st);
+    case 10: return launch_chol_rt<10>(a, (int)grid, smem, st);
+    case 11: return launch_chol_rt<11>(a, (int)grid, smem, st);
+    case 12: return launch_chol_rt<12>(a, (int)grid, smem, st);
+    case 13: return launch_chol_rt<13>(a, (int)grid, smem, st);
+    case 14: return launch_chol_rt<14>(a, (int)grid, smem, st);
+    case 15: return launch_chol_rt<15>(a, (int)grid, smem, st);
+    case 16: return launch_chol_rt<16>(a, (int)grid, smem, st);
+  }
+  return LSSPA_E_UNSUPPORTED;
 }

@@ -21,4 +21,4 @@ lib.lsspa_debug_set_lifts_counters(None)
 d = buf.cpu().numpy().reshape(8, 8).copy()
 print("warp  gather   panel|diag  trailing|accumulate  barrier-wait  phase1  phase1.5+2")
 for w in range(8):
-    print(w, d[w, :6])
+    print(w, d[w, :8])
