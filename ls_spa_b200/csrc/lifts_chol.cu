@@ -78,7 +78,7 @@ __device__ __forceinline__ void diag_factor(double &t0, double &t1, double &y0, 
   const int c = lane >> 2, q = lane & 3;
   y0 = (c == 2 * q) ? 1.0 : 0.0;
   y1 = (c == 2 * q + 1) ? 1.0 : 0.0;
-  double rs0 = 0.0, rs1 = 0.0, rsc = 0.0;  // rsqrt of the pivots of columns 2q, 2q+1 and c
+  double ds0 = 0.0, ds1 = 0.0, dsc = 0.0;  // pivots of columns 2q, 2q+1 and c (their rsqrt is needed at the end)
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     if (j < nf) {
@@ -92,10 +92,9 @@ __device__ __forceinline__ void diag_factor(double &t0, double &t1, double &y0, 
       const double yj1 = __shfl_sync(kFull, y1, 4 * j + q);               // Y[j][2q+1]
       const bool ok = (d > kPivMin) && (d < kPivMax);
       const double ri = ok ? rcp_fast(d) : 0.0;
-      const double rs = ok ? rsqrt_fast(d) : 0.0;
-      if (2 * q == j) rs0 = rs;
-      if (2 * q + 1 == j) rs1 = rs;
-      if (c == j) rsc = rs;
+      if (2 * q == j) ds0 = d;
+      if (2 * q + 1 == j) ds1 = d;
+      if (c == j) dsc = d;
       if (c > j) {
         const double f = colm * ri;
         if (2 * q > j) t0 = fma(-f, cn0, t0);
@@ -105,12 +104,40 @@ __device__ __forceinline__ void diag_factor(double &t0, double &t1, double &y0, 
       }
     }
   }
+  const double rs0 = (ds0 > kPivMin && ds0 < kPivMax) ? rsqrt_fast(ds0) : 0.0;
+  const double rs1 = (ds1 > kPivMin && ds1 < kPivMax) ? rsqrt_fast(ds1) : 0.0;
+  const double rsc = (dsc > kPivMin && dsc < kPivMax) ? rsqrt_fast(dsc) : 0.0;
   // Lo[m][n] = T_n[m][n] * rsqrt(d_n) for m >= n, n < nf
   t0 = (c >= 2 * q && 2 * q < nf) ? t0 * rs0 : 0.0;
   t1 = (c >= 2 * q + 1 && 2 * q + 1 < nf) ? t1 * rs1 : 0.0;
   // Uinv[u][jj] = Y[jj][u] * rsqrt(d_jj); columns jj >= nf are zero
   y0 = (c < nf) ? y0 * rsc : 0.0;
   y1 = (c < nf) ? y1 * rsc : 0.0;
+}
+
+// sum_{k < kend} R(k, L)^T R(k, S) in C layout (the transpose of what tile (S, L) loses): four
+// independent accumulation chains, a dependent DMMA costs more than an issue slot
+template <int LD>
+__device__ __forceinline__ double2 acc_tile(const double *A, int kend, int L, int S, int c, int q) {
+  double p0 = 0.0, p1 = 0.0, r0 = 0.0, r1 = 0.0, e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0;
+  int k = 0;
+  for (; k + 1 < kend; k += 2) {
+    const double2 xa = ld_tile(A, LD, 8 * k, 8 * L, c, q);
+    const double2 xb = ld_tile(A, LD, 8 * k, 8 * S, c, q);
+    const double2 ya = ld_tile(A, LD, 8 * k + 8, 8 * L, c, q);
+    const double2 yb = ld_tile(A, LD, 8 * k + 8, 8 * S, c, q);
+    dmma(p0, p1, xa.x, xb.x);
+    dmma(r0, r1, ya.x, yb.x);
+    dmma(e0, e1, xa.y, xb.y);
+    dmma(f0, f1, ya.y, yb.y);
+  }
+  if (k < kend) {
+    const double2 xa = ld_tile(A, LD, 8 * k, 8 * L, c, q);
+    const double2 xb = ld_tile(A, LD, 8 * k, 8 * S, c, q);
+    dmma(p0, p1, xa.x, xb.x);
+    dmma(e0, e1, xa.y, xb.y);
+  }
+  return make_double2((p0 + r0) + (e0 + f0), (p1 + r1) + (e1 + f1));
 }
 
 // leading dimension of the tile array (column-major, ld % 16 == 8: conflict-free tile accesses)
@@ -126,7 +153,6 @@ __global__ void __launch_bounds__(256, MINB) lifts_chol_kernel(CholParams a) {
   constexpr int NR = 8 * RT, NC = 8 * PT;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int c = lane >> 2, q = lane & 3;
-  constexpr int NTL = (PT + 7) / 8;  // column tiles of one row block per warp
 
   double *A = reinterpret_cast<double *>(smem_raw);  // upper tiles of the permuted Gram matrix -> R, c
   double *Dbuf = A + (size_t)NC * ld;                 // RT x 64: inverses of the diagonal blocks of R
@@ -146,20 +172,56 @@ __global__ void __launch_bounds__(256, MINB) lifts_chol_kernel(CholParams a) {
         perm_s[k] = (k == p) ? p : a.perms[sidx * p + (h == 0 ? k : p - 1 - k)];
       __syncthreads();
       const long long t_a = clock64();
-      // ---- phase 0: gather the upper tiles of Gh[pi^, pi^] (rows < p, columns <= p), zero padding
+      // ---- phase 0: gather the upper tiles of Gh[pi^, pi^] (rows < p, columns <= p), zero padding.
+      // Warp w takes the columns l = w + 8 g (column tile g); lane -> rows 2 lane, 2 lane + 1 (+ 64).
+      // All loads of a batch of column tiles are issued from valid addresses before the first store
+      // and masked afterwards, so they are in flight together.
       {
-        const int half = NR / 2, tot = NC * half;
-#pragma unroll 8
-        for (int e = tid; e < tot; e += 256) {
-          const int l = e / half, i = 2 * (e - l * half);
-          if ((i >> 3) <= (l >> 3)) {
-            double2 v = make_double2(0.0, 0.0);
-            if (l <= p) {
-              const double *src = a.Gh + (size_t)perm_s[l] * ldg;
-              if (i < p) v.x = __ldg(src + perm_s[i]);
-              if (i + 1 < p) v.y = __ldg(src + perm_s[i + 1]);
+        int pr[2][2];
+        bool pv[2][2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int i0 = 2 * lane + 64 * r;
+          pv[r][0] = i0 < p;
+          pv[r][1] = i0 + 1 < p;
+          pr[r][0] = pv[r][0] ? perm_s[i0] : 0;
+          pr[r][1] = pv[r][1] ? perm_s[i0 + 1] : 0;
+        }
+        constexpr int GB = (PT + 1) / 2;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          double vv[GB][2][2];
+#pragma unroll
+          for (int gg = 0; gg < GB; ++gg) {
+            const int g = b * GB + gg;
+            if (g < PT) {
+              const int l = warp + 8 * g;
+              const double *src = a.Gh + (size_t)perm_s[(l <= p) ? l : p] * ldg;
+              vv[gg][0][0] = __ldg(src + pr[0][0]);
+              vv[gg][0][1] = __ldg(src + pr[0][1]);
+              if (8 * g + 8 > 64) {  // compile-time: the column tile reaches below row 64
+                vv[gg][1][0] = __ldg(src + pr[1][0]);
+                vv[gg][1][1] = __ldg(src + pr[1][1]);
+              }
             }
-            *reinterpret_cast<double2 *>(A + (size_t)l * ld + i) = v;
+          }
+#pragma unroll
+          for (int gg = 0; gg < GB; ++gg) {
+            const int g = b * GB + gg;
+            if (g < PT) {
+              const int l = warp + 8 * g;
+              const bool colv = l <= p;
+#pragma unroll
+              for (int r = 0; r < 2; ++r) {
+                const int i0 = 2 * lane + 64 * r;
+                if (64 * r < 8 * g + 8 && i0 < 8 * g + 8 && i0 < NR) {
+                  double2 v;
+                  v.x = (colv && pv[r][0]) ? vv[gg][r][0] : 0.0;
+                  v.y = (colv && pv[r][1]) ? vv[gg][r][1] : 0.0;
+                  *reinterpret_cast<double2 *>(A + (size_t)l * ld + i0) = v;
+                }
+              }
+            }
           }
         }
       }
@@ -174,67 +236,92 @@ __global__ void __launch_bounds__(256, MINB) lifts_chol_kernel(CholParams a) {
 
       const long long t_b = clock64();
       long long t_acc = 0, t_diag = 0, t_wait = 0;
-      // ---- phase 1: left-looking blocked Cholesky, row block s per step.  Warp w owns the tiles
-      // (s, s + w) and (s, s + w + 8): tile - sum_{k<s} R_kL^T R_ks accumulates in registers, warp 0
-      // factors the diagonal tile and publishes its inverse, the others scale with it.
+      // ---- phase 1: left-looking blocked Cholesky, software-pipelined around the serial part.
+      // The 8x8 diagonal blocks form a chain (factor s needs row block s - 1), so warp 0 does
+      // nothing else: D(s) = last update of the diagonal tile + factorisation + inverse.  Meanwhile
+      // warps 1..7 pre-accumulate row block s + 1 over the finished rows k < s (P), after barrier 1
+      // scale their tiles of row block s with Dinv_s (S), and after barrier 2 add the missing k = s
+      // term (F).  Tile (r, L), L > r, belongs to warp 1 + (L - r - 1) % 7; the diagonal tile of row
+      // r is pre-accumulated in place by warp 1 + r % 7.
+      constexpr int NSL = (PT - 1 + 6) / 7;
+      double2 tv[NSL];
+#pragma unroll
+      for (int sl = 0; sl < NSL; ++sl) {
+        const int L = warp + 7 * sl;  // row block 0
+        tv[sl] = make_double2(0.0, 0.0);
+        if (warp != 0 && L < PT) tv[sl] = ld_tile(A, ld, 0, 8 * L, c, q);
+      }
       for (int s = 0; s < RT; ++s) {
         const int nf = (p - 8 * s < 8) ? p - 8 * s : 8;
         const long long u0 = clock64();
-        double2 tv[NTL];
+        double2 tvn[NSL];
+        if (warp == 0) {
+          double2 t = ld_tile(A, ld, 8 * s, 8 * s, c, q);
+          if (s > 0) {
+            const double2 xa = ld_tile(A, ld, 8 * (s - 1), 8 * s, c, q);
+            double p0 = 0.0, p1 = 0.0, e0 = 0.0, e1 = 0.0;
+            dmma(p0, p1, xa.x, xa.x);
+            dmma(e0, e1, xa.y, xa.y);
+            t.x -= p0 + e0;
+            t.y -= p1 + e1;
+          }
+          double y0, y1;
+          diag_factor(t.x, t.y, y0, y1, nf, lane);
+          st_tile(A, ld, 8 * s, 8 * s, c, q, t);
+          *reinterpret_cast<double2 *>(Dbuf + s * 64 + c * 8 + 2 * q) = make_double2(y0, y1);
+        } else if (s + 1 < RT) {
 #pragma unroll
-        for (int t = 0; t < NTL; ++t) {
-          const int L = s + warp + 8 * t;
-          tv[t] = make_double2(0.0, 0.0);
-          if (L < PT) {
-            double p0 = 0.0, p1 = 0.0, r0 = 0.0, r1 = 0.0;
-            int k = 0;
-            for (; k + 1 < s; k += 2) {
-              const double2 xa = ld_tile(A, ld, 8 * k, 8 * L, c, q);
-              const double2 xb = ld_tile(A, ld, 8 * k, 8 * s, c, q);
-              const double2 ya = ld_tile(A, ld, 8 * k + 8, 8 * L, c, q);
-              const double2 yb = ld_tile(A, ld, 8 * k + 8, 8 * s, c, q);
-              dmma(p0, p1, xa.x, xb.x);
-              dmma(r0, r1, ya.x, yb.x);
-              dmma(p0, p1, xa.y, xb.y);
-              dmma(r0, r1, ya.y, yb.y);
+          for (int sl = 0; sl < NSL; ++sl) {
+            const int L = s + 1 + warp + 7 * sl;
+            tvn[sl] = make_double2(0.0, 0.0);
+            if (L < PT) {
+              const double2 g = ld_tile(A, ld, 8 * (s + 1), 8 * L, c, q);
+              const double2 z = acc_tile<ld>(A, s, L, s + 1, c, q);
+              tvn[sl] = make_double2(g.x - z.x, g.y - z.y);
             }
-            if (k < s) {
-              const double2 xa = ld_tile(A, ld, 8 * k, 8 * L, c, q);
-              const double2 xb = ld_tile(A, ld, 8 * k, 8 * s, c, q);
-              dmma(p0, p1, xa.x, xb.x);
-              dmma(p0, p1, xa.y, xb.y);
-            }
-            const double2 g = ld_tile(A, ld, 8 * s, 8 * L, c, q);
-            tv[t].x = g.x - (p0 + r0);
-            tv[t].y = g.y - (p1 + r1);
+          }
+          if (warp == 1 + (s + 1) % 7 && s > 0) {
+            const double2 g = ld_tile(A, ld, 8 * (s + 1), 8 * (s + 1), c, q);
+            const double2 z = acc_tile<ld>(A, s, s + 1, s + 1, c, q);
+            st_tile(A, ld, 8 * (s + 1), 8 * (s + 1), c, q, make_double2(g.x - z.x, g.y - z.y));
           }
         }
         const long long u1 = clock64();
         t_acc += u1 - u0;
-        if (warp == 0) {
-          double y0, y1;
-          diag_factor(tv[0].x, tv[0].y, y0, y1, nf, lane);
-          st_tile(A, ld, 8 * s, 8 * s, c, q, tv[0]);
-          *reinterpret_cast<double2 *>(Dbuf + s * 64 + c * 8 + 2 * q) = make_double2(y0, y1);
-        }
-        const long long u2 = clock64();
-        t_diag += u2 - u1;
         __syncthreads();
-        t_wait += clock64() - u2;
-        {
+        const long long u2 = clock64();
+        t_wait += u2 - u1;
+        if (warp != 0) {
           const double2 dv = ld_tile(Dbuf + s * 64, 8, 0, 0, c, q);
 #pragma unroll
-          for (int t = 0; t < NTL; ++t) {
-            const int L = s + warp + 8 * t;
-            if (L < PT && L > s) {
+          for (int sl = 0; sl < NSL; ++sl) {
+            const int L = s + warp + 7 * sl;
+            if (L < PT) {
               double r0 = 0.0, r1 = 0.0;
-              dmma(r0, r1, tv[t].x, dv.x);
-              dmma(r0, r1, tv[t].y, dv.y);
+              dmma(r0, r1, tv[sl].x, dv.x);
+              dmma(r0, r1, tv[sl].y, dv.y);
               st_tile(A, ld, 8 * s, 8 * L, c, q, make_double2(r0, r1));
             }
           }
         }
         __syncthreads();
+        if (warp != 0 && s + 1 < RT) {
+#pragma unroll
+          for (int sl = 0; sl < NSL; ++sl) {
+            const int L = s + 1 + warp + 7 * sl;
+            tv[sl] = tvn[sl];
+            if (L < PT) {
+              const double2 xa = ld_tile(A, ld, 8 * s, 8 * L, c, q);
+              const double2 xb = ld_tile(A, ld, 8 * s, 8 * (s + 1), c, q);
+              double p0 = 0.0, p1 = 0.0, e0 = 0.0, e1 = 0.0;
+              dmma(p0, p1, xa.x, xb.x);
+              dmma(e0, e1, xa.y, xb.y);
+              tv[sl].x -= p0 + e0;
+              tv[sl].y -= p1 + e1;
+            }
+          }
+        }
+        t_diag += clock64() - u2;
       }
 
       const long long t_c = clock64();
