@@ -27,6 +27,16 @@ from . import engine, ops
 from ._cabi import LsSpaCudaError
 from .samplers import make_source
 
+_SOURCE_POOL = None
+
+
+def _source_pool():
+    global _SOURCE_POOL
+    if _SOURCE_POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _SOURCE_POOL = ThreadPoolExecutor(max_workers=1, thread_name_prefix="lsspa-source")
+    return _SOURCE_POOL
+
 METHODS = ("random", "permutohedron", "argsort", "exact")
 
 
@@ -180,13 +190,31 @@ def ls_spa(X_train, X_test, y_train, y_test, reg: float = 0.0, method: str | Non
     if bs < 1:
         raise ValueError("batch_size must be positive")
 
-    source = make_source(meth, p, seed, total, device, perms=perms)
+    # The Sobol-based generators spend a few ms of host time in scipy building their scrambled
+    # direction numbers: do that on a helper thread while the reduction runs on the device.
+    if perms is None and meth in ("argsort", "permutohedron"):
+        def _build_source():
+            torch.cuda.set_device(device)
+            src = make_source(meth, p, seed, total, device, perms=None)
+            done = torch.cuda.Event()
+            done.record()                      # the helper thread uploads on its own current stream
+            return src, done
+        pending = _source_pool().submit(_build_source)
+
+        def get_source():
+            src, done = pending.result()
+            torch.cuda.current_stream().wait_event(done)
+            return src
+    else:
+        ready = make_source(meth, p, seed, total, device, perms=perms)
+        get_source = lambda: ready
     cfg = engine.JobConfig(p=p, batch_size=bs, max_samples=total, tolerance=float(tolerance),
                            seed=int(seed), antithetical=anti, estimate_errors=estimate,
                            return_history=want_history, penultimate_check=penultimate)
 
     prob = engine.reduce_problem(backend, coll, X_train, X_test, y_train, y_test, float(reg), p,
                                  row_sharded=row_sharded)
+    source = get_source()
     res, history, done = engine.run_samples(backend, coll, prob, source, cfg)
     if done == 0 and p >= 9:
         raise ValueError("no permutations were supplied")

@@ -213,6 +213,19 @@ class CudaBackend:
     def zeros(self, *shape):
         return torch.zeros(shape, dtype=torch.float64, device=self.device)
 
+    def to_host_async(self, t):
+        """Start the device-to-host copy of `t` now (pinned buffer, current stream); the returned
+        callable waits for it and hands back the numpy array."""
+        buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        buf.copy_(t, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record()
+
+        def wait():
+            done.synchronize()
+            return buf.numpy()
+        return wait
+
 
 # ---------------------------------------------------------------------------
 # the job
@@ -270,8 +283,9 @@ def run_samples(backend, coll: Collective, prob, source: PermutationSource, cfg:
     carry_sum = backend.zeros(p) if cfg.return_history else None
     err_parts, feat_last = [], None        # device tensors of per-batch errors (read at the end)
     err_hist = []                          # host copy, filled eagerly only when a stop is possible
-    pos, stopped = 0, False
-    while (limit is None or pos < limit) and not stopped:
+    def launch_lifts(pos):
+        """Stage A of a super-batch: permutations and lift rows of this rank's run of batches.
+        Touches neither the estimator nor the host, so it can be issued one super-batch ahead."""
         want = sb_samples if limit is None else min(sb_samples, limit - pos)
         perms_all = None
         if not source.random_access:
@@ -280,10 +294,9 @@ def run_samples(backend, coll: Collective, prob, source: PermutationSource, cfg:
         else:
             n_sb = want
         if n_sb == 0:
-            break
+            return None
         batches = split_batches(pos, n_sb, bs_eff, quirk)
-        nb = len(batches)
-        runs, per = contiguous_runs(nb, W)
+        runs, per = contiguous_runs(len(batches), W)
         b0, b1 = runs[rank]
         mine = batches[b0:b1]
         my_start = mine[0][0] if mine else pos
@@ -295,6 +308,17 @@ def run_samples(backend, coll: Collective, prob, source: PermutationSource, cfg:
             perms = source.take(my_count)
             source.position = pos + n_sb
         rows = backend.lifts(prob, perms, cfg.antithetical) if my_count > 0 else backend.zeros(0, p)
+        return dict(pos=pos, n_sb=n_sb, dry=perms_all is not None and n_sb < want, batches=batches, runs=runs,
+                    per=per, mine=mine, my_count=my_count, rows=rows)
+
+    pos, stopped = 0, False
+    nxt = launch_lifts(0) if (limit is None or limit > 0) else None
+    while nxt is not None:
+        cur, nxt = nxt, None
+        pos, n_sb, batches, runs, per = cur["pos"], cur["n_sb"], cur["batches"], cur["runs"], cur["per"]
+        mine, my_count, rows = cur["mine"], cur["my_count"], cur["rows"]
+        nb = len(batches)
+        b0, b1 = runs[rank]
         desc, off = [], 0
         for first, n in mine:
             desc.append((off, n, first))
@@ -323,6 +347,7 @@ def run_samples(backend, coll: Collective, prob, source: PermutationSource, cfg:
             else:
                 rows_in_order = rows
         keep = nb
+        more = (not cur["dry"]) and (limit is None or pos + n_sb < limit)
         if cfg.estimate_errors:
             if W > 1:
                 ov = backend.zeros(per)
@@ -334,11 +359,20 @@ def run_samples(backend, coll: Collective, prob, source: PermutationSource, cfg:
                 overall = torch.cat([ov_all[r, : b - a] for r, (a, b) in enumerate(runs)], 0)
                 feat = torch.cat([ft_all[r, : b - a] for r, (a, b) in enumerate(runs)], 0)
             if can_stop:
-                errs = overall.cpu().numpy()                      # the only host sync of the super-batch
+                # The per-batch errors start their way to the host, the lifts of the NEXT super-batch
+                # are issued behind them, and only then does the host wait: the stop test (the only
+                # host sync of a super-batch) is hidden behind device work.  If the test stops the
+                # job, the speculative rows are dropped; they never touched the estimator.
+                errs_t = (backend.to_host_async(overall) if hasattr(backend, "to_host_async")
+                          else (lambda t=overall: t.cpu().numpy()))
+                if more:
+                    nxt = launch_lifts(pos + n_sb)
+                errs = errs_t()
                 hit = np.nonzero(errs < cfg.tolerance)[0]         # strict <, reference :229
                 if hit.size:
                     keep = int(hit[0]) + 1
                     stopped = True
+                    nxt = None
                     if keep < nb:                                 # stop inside the super-batch: replay
                         est.restore(snap)
                         est.absorb(gathered, slots[:keep], counts[:keep], emit=False)
@@ -351,8 +385,8 @@ def run_samples(backend, coll: Collective, prob, source: PermutationSource, cfg:
             kept_rows = sum(counts[:keep])
             hist_chunks.append(backend.prefix_means(rows_in_order[:kept_rows].contiguous(), carry_sum, pos))
         pos += n_sb
-        if perms_all is not None and n_sb < want:
-            break                                  # explicit stream ran dry
+        if more and not stopped and nxt is None:
+            nxt = launch_lifts(pos)
     if hasattr(source, "check"):
         source.check()
     res = est.read()
