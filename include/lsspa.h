@@ -183,12 +183,12 @@ LSSPA_API int lsspa_estimator_max_batches(int p);
  * first sample}; partials[nbatch][partial_doubles] */
 LSSPA_API int lsspa_estimator_partials(int p, const double *lifts, const int64_t *batch_desc, int nbatch,
                              uint64_t seed, int estimate_errors, double *partials, void *stream);
-/* zsq: device [own1-own0][p][1024] doubles, or NULL when no error draws are wanted; with_draws = 0
+/* zsq: device [own1-own0][p+1][1024] doubles (row p of every batch is scratch of lsspa_estimator_quantiles), or NULL when no error draws are wanted; with_draws = 0
  * skips the draw sums altogether (partials made with estimate_errors = 0 carry none) */
 LSSPA_API int lsspa_estimator_absorb(void *state, int p, int cur, double n_before, const double *partials,
                            const int32_t *slot_map, int nb, int own0, int own1, double *zsq, int with_draws,
                            void *stream);
-LSSPA_API int lsspa_estimator_quantiles(int p, const double *zsq, int nown, double *overall_out,
+LSSPA_API int lsspa_estimator_quantiles(int p, double *zsq, int nown, double *overall_out,
                               double *feat_out, void *stream);
 /* running means after each sample (attribution_history, :217-219): hist[k] =
  * (carry_sum + sum_{r<=k} lifts[r]) / (carry_count + k + 1); carry is updated */

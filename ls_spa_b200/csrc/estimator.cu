@@ -176,24 +176,197 @@ __global__ void __launch_bounds__(1024) part_s_kernel(int p, const double *lifts
   if (tid < kDrawTile) Gout[tile * kDrawTile + tid] = gsum;
 }
 
-// ---------------------------------------------------------------- batch step
-__device__ __forceinline__ void bitonic_sort_1024(double *buf, int tid) {
-  // blockDim.x == 1024, ascending
-  for (int k = 2; k <= kDraws; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      __syncthreads();
-      const int ixj = tid ^ j;
-      if (ixj > tid) {
-        const double a = buf[tid], b = buf[ixj];
-        const bool up = (tid & k) == 0;
-        if ((a > b) == up) {
-          buf[tid] = b;
-          buf[ixj] = a;
+// ---------------------------------------------------------------- per-batch partial moments on DMMA (p <= 128)
+// Both second-order partials are products over the rows of the batch:
+//   M2 = Xc^T Xc   (p x p)      and      S = Xc^T g   (p x 1024 draws),     Xc = lifts - mean.
+// A CTA stages up to 128 centered rows in shared memory (row-major, stride % 16 == 8, so that the
+// 8 bytes a lane needs, Xc[4 ks + q][8 t + c], are conflict-free) -- that value is at once the A
+// fragment of feature tile t (A[m=c][k=q]) and the B fragment of the same tile (B[k=q][n=c]).
+constexpr int kMmaRows = 128;
+
+__device__ __forceinline__ void dmma_e(double &d0, double &d1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(d0), "+d"(d1)
+      : "d"(a), "d"(b));
+}
+
+__host__ __device__ inline int mma_ldx(int ft) { return ((8 * ft) % 16 == 8) ? 8 * ft : 8 * ft + 8; }
+
+// rows [k0, k0 + rows) of the batch, centered, zero padded to kMmaRows x ldx
+__device__ __forceinline__ void stage_rows(double *Xs, int ldx, const double *lifts, const double *mean, int p,
+                                           int64_t row0, int rows, int tid, int nt) {
+  for (int e = tid; e < kMmaRows * ldx; e += nt) {
+    const int r = e / ldx, f = e - r * ldx;
+    double v = 0.0;
+    if (r < rows && f < p) v = lifts[(row0 + r) * p + f] - mean[f];
+    Xs[e] = v;
+  }
+}
+
+// M2: warp g owns tile rows g and FT-1-g of the upper triangle (FT + 1 tiles, balanced)
+template <int MAXFT>
+__global__ void __launch_bounds__(256) part_m2_mma_kernel(int p, const double *lifts, const int64_t *desc,
+                                                          double *partials, size_t pstride) {
+  extern __shared__ __align__(16) double Xs[];
+  const int b = blockIdx.x;
+  const int64_t r0 = desc[3 * b], cnt = desc[3 * b + 1];
+  double *base = partials + (size_t)b * pstride;
+  const double *mean = base + kPartHdr;
+  double *m2 = base + kPartHdr + p;
+  const int FT = (p + 7) / 8, ldx = mma_ldx(FT);
+  const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5;
+  const int c = lane >> 2, q = lane & 3;
+  const int rowA = g, rowB = FT - 1 - g;           // tile rows of this warp (rowB skipped if <= rowA)
+  const bool hasA = rowA < FT && rowA <= rowB, hasB = rowB > rowA && rowB < FT;
+  double acc[MAXFT + 1][2];
+#pragma unroll
+  for (int i = 0; i <= MAXFT; ++i) acc[i][0] = acc[i][1] = 0.0;
+  for (int64_t k0 = 0; k0 < cnt; k0 += kMmaRows) {
+    const int rows = (int)((cnt - k0 < kMmaRows) ? cnt - k0 : kMmaRows);
+    __syncthreads();
+    stage_rows(Xs, ldx, lifts, mean, p, r0 + k0, rows, tid, blockDim.x);
+    __syncthreads();
+    const int ksteps = (rows + 3) / 4;
+    for (int ks = 0; ks < ksteps; ++ks) {
+      const double *xrow = Xs + (size_t)(4 * ks + q) * ldx + c;
+      const double xa = hasA ? xrow[8 * rowA] : 0.0, xb = hasB ? xrow[8 * rowB] : 0.0;
+      // accumulator i: i < FT - rowA -> tile (rowA, rowA + i); else tile (rowB, rowB + i - (FT - rowA))
+      const int nA = FT - rowA;
+#pragma unroll
+      for (int i = 0; i <= MAXFT; ++i) {
+        if (hasA && i < nA) {
+          dmma_e(acc[i][0], acc[i][1], xa, xrow[8 * (rowA + i)]);
+        } else if (hasB && i >= nA && i - nA < FT - rowB) {
+          dmma_e(acc[i][0], acc[i][1], xb, xrow[8 * (rowB + i - nA)]);
         }
       }
     }
   }
-  __syncthreads();
+  // C layout: lane (c, q) holds M2[8 t1 + c][8 t2 + 2q + e]; both triangles are written
+#pragma unroll
+  for (int i = 0; i <= MAXFT; ++i) {
+    const int nA = FT - rowA;
+    int t1 = -1, t2 = -1;
+    if (hasA && i < nA) {
+      t1 = rowA;
+      t2 = rowA + i;
+    } else if (hasB && i >= nA && i - nA < FT - rowB) {
+      t1 = rowB;
+      t2 = rowB + i - nA;
+    }
+    if (t1 >= 0) {
+      const int fa = 8 * t1 + c;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int fb = 8 * t2 + 2 * q + e;
+        if (fa < p && fb < p) {
+          m2[(size_t)fa * p + fb] = acc[i][e];
+          m2[(size_t)fb * p + fa] = acc[i][e];
+        }
+      }
+    }
+  }
+}
+
+// S and G: CTA = (block of kSDraws draws, batch).  A warp task = (half of the feature tiles, pair
+// of draw tiles T0, T1); the Gaussians of a row are generated in the lanes that need them: lane
+// (c, q) of k-step ks owns row 4 ks + q, even c draws the pair (T0*8 + c, T0*8 + c + 1), odd c the
+// pair (T1*8 + c - 1, T1*8 + c), and one shuffle with lane ^ 4 gives every lane column c of both.
+constexpr int kSDraws = 128;
+
+template <int MAXFT>
+__global__ void __launch_bounds__(256) part_s_mma_kernel(int p, const double *lifts, const int64_t *desc,
+                                                         uint64_t seed, double *partials, size_t pstride) {
+  extern __shared__ __align__(16) double Xs[];
+  constexpr int FH = (MAXFT + 1) / 2;
+  const int b = blockIdx.y, db = blockIdx.x;
+  const int64_t r0 = desc[3 * b], cnt = desc[3 * b + 1], gidx0 = desc[3 * b + 2];
+  double *base = partials + (size_t)b * pstride;
+  const double *mean = base + kPartHdr;
+  double *Gout = base + kPartHdr + p + (size_t)p * p;
+  double *Sout = Gout + kDraws;
+  const int FT = (p + 7) / 8, ldx = mma_ldx(FT);
+  const int fh0 = (FT + 1) / 2;                     // tiles of the first half
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int c = lane >> 2, q = lane & 3;
+  const bool even = (c & 1) == 0;
+  constexpr int kPairs = kSDraws / 16;              // draw-tile pairs per CTA
+  const int64_t nchunks = (cnt + kMmaRows - 1) / kMmaRows;
+  for (int task = w; task < 2 * kPairs; task += 8) {
+    const int half = task / kPairs, pairi = task - half * kPairs;
+    const int T0 = db * (kSDraws / 8) + 2 * pairi, T1 = T0 + 1;
+    const int tbeg = half == 0 ? 0 : fh0, tnum = half == 0 ? fh0 : FT - fh0;
+    double acc[FH][2][2];
+#pragma unroll
+    for (int i = 0; i < FH; ++i) acc[i][0][0] = acc[i][0][1] = acc[i][1][0] = acc[i][1][1] = 0.0;
+    double gs0 = 0.0, gs1 = 0.0;
+    for (int64_t ch = 0; ch < nchunks; ++ch) {
+      const int64_t k0 = ch * kMmaRows;
+      const int rows = (int)((cnt - k0 < kMmaRows) ? cnt - k0 : kMmaRows);
+      if (nchunks > 1 || task < 8) {   // one staging serves every task unless the batch needs several chunks
+        __syncthreads();
+        stage_rows(Xs, ldx, lifts, mean, p, r0 + k0, rows, tid, blockDim.x);
+        __syncthreads();
+      }
+      const int ksteps = (rows + 3) / 4;
+      const uint32_t pr = even ? (uint32_t)((T0 * 8 + c) >> 1) : (uint32_t)((T1 * 8 + c - 1) >> 1);
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const int r = 4 * ks + q;
+        float g0 = 0.f, g1 = 0.f;
+        if (r < rows) gauss_pair(seed, (uint64_t)(gidx0 + k0 + r), pr, g0, g1);
+        const float recv = __shfl_xor_sync(kFull, even ? g1 : g0, 4);
+        const double b0 = (double)(even ? g0 : recv), b1 = (double)(even ? recv : g1);
+        gs0 += b0;
+        gs1 += b1;
+        const double *xrow = Xs + (size_t)r * ldx + 8 * tbeg + c;
+#pragma unroll
+        for (int i = 0; i < FH; ++i) {
+          if (i < tnum) {
+            const double xa = xrow[8 * i];
+            dmma_e(acc[i][0][0], acc[i][0][1], xa, b0);
+            dmma_e(acc[i][1][0], acc[i][1][1], xa, b1);
+          }
+        }
+      }
+    }
+    // C layout: lane (c, q) holds S[feature 8 (tbeg + i) + c][draw 8 T + 2q + e]
+#pragma unroll
+    for (int i = 0; i < FH; ++i) {
+      const int fa = 8 * (tbeg + i) + c;
+      if (i < tnum && fa < p) {
+        *reinterpret_cast<double2 *>(Sout + (size_t)fa * kDraws + 8 * T0 + 2 * q) = make_double2(acc[i][0][0], acc[i][0][1]);
+        *reinterpret_cast<double2 *>(Sout + (size_t)fa * kDraws + 8 * T1 + 2 * q) = make_double2(acc[i][1][0], acc[i][1][1]);
+      }
+    }
+    if (half == 0) {
+      gs0 = quad_sum(gs0);
+      gs1 = quad_sum(gs1);
+      if (q == 0) {
+        Gout[8 * T0 + c] = gs0;
+        Gout[8 * T1 + c] = gs1;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- batch step
+// Order statistics of 1024 non-negative doubles held by one warp (32 per lane), without sorting:
+// the IEEE bit pattern of a non-negative double is monotone, so the k-th largest value is the
+// largest key K with count(key >= K) >= k, built bit by bit from the top; one warp-wide integer
+// reduction per bit, no barriers.
+constexpr int kPerLane = kDraws / 32;
+
+__device__ __forceinline__ unsigned long long kth_largest_key(const unsigned long long (&key)[kPerLane], int k) {
+  unsigned long long K = 0;
+  for (int bit = 62; bit >= 0; --bit) {
+    const unsigned long long trial = K | (1ULL << bit);
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < kPerLane; ++i) cnt += (key[i] >= trial) ? 1 : 0;
+    cnt = __reduce_add_sync(kFull, cnt);
+    if (cnt >= k) K = trial;
+  }
+  return K;
 }
 
 // Fold `nb` consecutive batches (partial blocks partials[slot_map[b]]) into the state, in order.
@@ -261,7 +434,7 @@ __global__ void __launch_bounds__(1024) est_absorb_kernel(double *state, int p, 
       if (zsq != nullptr && b >= own0 && b < own1) {
         const double nn = nrun[b + 1];
         const double z = s / sqrt(nn * (nn - 1.0));
-        zsq[((size_t)(b - own0) * p + f) * kDraws + tid] = z * z;
+        zsq[((size_t)(b - own0) * (p + 1) + f) * kDraws + tid] = z * z;
       }
     }
     st.S[(size_t)f * kDraws + tid] = s;
@@ -273,25 +446,70 @@ __global__ void __launch_bounds__(1024) est_absorb_kernel(double *state, int p, 
 // CTA (f < p, b): |z_sf| over the draws -> feat_out[b][f];  CTA (p, b): |z_s|_2 -> overall_out[b].
 // Sorting z^2 and taking the square root of the two order statistics before interpolating is the
 // same as numpy.quantile(|z|, 0.95).
-__global__ void __launch_bounds__(1024) est_quantile_kernel(int p, const double *zsq, double *overall_out,
-                                                             double *feat_out) {
-  __shared__ double sortbuf[kDraws];
-  const int f = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
-  const double *zb = zsq + (size_t)b * p * kDraws;
-  double v;
-  if (f < p) {
-    v = zb[(size_t)f * kDraws + tid];
-  } else {
-    v = 0.0;
-    for (int ff = 0; ff < p; ++ff) v += zb[(size_t)ff * kDraws + tid];
+// zsq[b][p][s] = sum_f zsq[b][f][s] (the squared L2 norm of draw s, for the overall error): CTA =
+// (batch, 128 draws), 8 feature groups x 128 draws, the groups are added in a fixed order.
+__global__ void __launch_bounds__(1024) est_rowsum_kernel(int p, double *zsq) {
+  __shared__ double part[8][128];
+  const int b = blockIdx.y, s = blockIdx.x * 128 + (threadIdx.x & 127), grp = threadIdx.x >> 7;
+  double *zb = zsq + (size_t)b * (p + 1) * kDraws;
+  double a0 = 0.0, a1 = 0.0;
+  int ff = grp;
+  for (; ff + 8 < p; ff += 16) {
+    a0 += zb[(size_t)ff * kDraws + s];
+    a1 += zb[(size_t)(ff + 8) * kDraws + s];
   }
-  sortbuf[tid] = v;
-  bitonic_sort_1024(sortbuf, tid);
-  if (tid == 0) {
-    const double pos = (double)(kDraws - 1) * 0.95;
-    const int lo = (int)floor(pos);
+  if (ff < p) a0 += zb[(size_t)ff * kDraws + s];
+  part[grp][threadIdx.x & 127] = a0 + a1;
+  __syncthreads();
+  if (grp == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) t += part[g][threadIdx.x];
+    zb[(size_t)p * kDraws + s] = t;
+  }
+}
+
+// One warp per (batch, feature) row of zsq, and one more per batch for the overall error (the sum
+// over the features); rows = nown * (p + 1), 8 per CTA.
+__global__ void __launch_bounds__(256) est_quantile_kernel(int p, int nown, const double *zsq, double *overall_out,
+                                                           double *feat_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t rowid = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (rowid >= (int64_t)nown * (p + 1)) return;
+  const int b = (int)(rowid / (p + 1)), f = (int)(rowid - (int64_t)b * (p + 1));
+  const double *zb = zsq + ((size_t)b * (p + 1) + f) * kDraws;   // row p = sum over the features (est_rowsum_kernel)
+  double v[kPerLane];
+#pragma unroll
+  for (int i = 0; i < kPerLane; ++i) v[i] = zb[32 * i + lane];
+  unsigned long long key[kPerLane];
+#pragma unroll
+  for (int i = 0; i < kPerLane; ++i) key[i] = (unsigned long long)__double_as_longlong(v[i] > 0.0 ? v[i] : 0.0);
+  // np.quantile(., 0.95) of the square roots (reference :340-341): linear interpolation between
+  // the ascending ranks lo and lo + 1, i.e. the (kDraws - lo)-th and (kDraws - lo - 1)-th largest
+  const double pos = (double)(kDraws - 1) * 0.95;
+  const int lo = (int)floor(pos);
+  const unsigned long long klo = kth_largest_key(key, kDraws - lo);
+  // the next rank up is klo again when ties leave fewer than kDraws - lo - 1 keys above it,
+  // otherwise the smallest key above klo
+  int n_gt = 0;
+  unsigned long long above = ~0ULL;
+#pragma unroll
+  for (int i = 0; i < kPerLane; ++i) {
+    if (key[i] > klo) {
+      ++n_gt;
+      above = key[i] < above ? key[i] : above;
+    }
+  }
+  n_gt = __reduce_add_sync(kFull, n_gt);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(kFull, above, o);
+    above = other < above ? other : above;
+  }
+  if (lane == 0) {
+    const unsigned long long khi = (n_gt >= kDraws - lo - 1) ? above : klo;
     const double t = pos - (double)lo;
-    const double a = sqrt(sortbuf[lo]), c = sqrt(sortbuf[lo + 1]);
+    const double a = sqrt(__longlong_as_double((long long)klo)), c = sqrt(__longlong_as_double((long long)khi));
     const double q = c - (c - a) * (1.0 - t);
     if (f < p) feat_out[(size_t)b * p + f] = q;
     else overall_out[b] = q;
@@ -514,6 +732,20 @@ extern "C" int64_t lsspa_estimator_partial_doubles(int p) {
   return p < 1 ? 0 : (int64_t)partial_doubles(p);
 }
 
+template <int MAXFT>
+static int launch_part_mma(int p, const double *lifts, const int64_t *desc, int nbatch, uint64_t seed, int estimate_errors,
+                           double *partials, size_t pstride, size_t smem, cudaStream_t st) {
+  LSSPA_CUDA_TRY(cudaFuncSetAttribute(part_m2_mma_kernel<MAXFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  part_m2_mma_kernel<MAXFT><<<nbatch, 256, smem, st>>>(p, lifts, desc, partials, pstride);
+  LSSPA_LAUNCH_CHECK();
+  if (estimate_errors) {
+    LSSPA_CUDA_TRY(cudaFuncSetAttribute(part_s_mma_kernel<MAXFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    part_s_mma_kernel<MAXFT><<<dim3(kDraws / kSDraws, (unsigned)nbatch), 256, smem, st>>>(p, lifts, desc, seed, partials, pstride);
+    LSSPA_LAUNCH_CHECK();
+  }
+  return LSSPA_OK;
+}
+
 extern "C" int lsspa_estimator_partials(int p, const double *lifts, const int64_t *batch_desc, int nbatch,
                                         uint64_t seed, int estimate_errors, double *partials,
                                         void *stream) {
@@ -526,6 +758,16 @@ extern "C" int lsspa_estimator_partials(int p, const double *lifts, const int64_
   if (nt < 32) nt = 32;
   part_mean_kernel<<<nbatch, nt, 0, st>>>(p, lifts, batch_desc, partials, pstride);
   LSSPA_LAUNCH_CHECK();
+  if (p >= 17 && p <= 128) {
+    // tensor-pipe versions (the scalar kernels below remain for every other width)
+    const int FT = (p + 7) / 8;
+    const size_t smem = (size_t)kMmaRows * mma_ldx(FT) * sizeof(double);
+    int rc;
+    if (FT <= 8) rc = launch_part_mma<8>(p, lifts, batch_desc, nbatch, seed, estimate_errors, partials, pstride, smem, st);
+    else if (FT <= 13) rc = launch_part_mma<13>(p, lifts, batch_desc, nbatch, seed, estimate_errors, partials, pstride, smem, st);
+    else rc = launch_part_mma<16>(p, lifts, batch_desc, nbatch, seed, estimate_errors, partials, pstride, smem, st);
+    return rc;
+  }
   dim3 g2((unsigned)ceil_div(p, 16), (unsigned)ceil_div(p, 16), (unsigned)nbatch);
   part_m2_kernel<<<g2, dim3(16, 16), 0, st>>>(p, lifts, batch_desc, partials, pstride);
   LSSPA_LAUNCH_CHECK();
@@ -561,11 +803,14 @@ extern "C" int lsspa_estimator_absorb(void *state, int p, int cur, double n_befo
   return LSSPA_OK;
 }
 
-extern "C" int lsspa_estimator_quantiles(int p, const double *zsq, int nown, double *overall_out,
+extern "C" int lsspa_estimator_quantiles(int p, double *zsq, int nown, double *overall_out,
                                          double *feat_out, void *stream) {
   if (!zsq || !overall_out || !feat_out || p < 1 || nown < 0) return LSSPA_E_BADARG;
   if (nown == 0) return LSSPA_OK;
-  est_quantile_kernel<<<dim3(p + 1, nown), kDraws, 0, as_stream(stream)>>>(p, zsq, overall_out, feat_out);
+  est_rowsum_kernel<<<dim3(kDraws / 128, (unsigned)nown), 1024, 0, as_stream(stream)>>>(p, zsq);
+  LSSPA_LAUNCH_CHECK();
+  const int64_t rows = (int64_t)nown * (p + 1);
+  est_quantile_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, as_stream(stream)>>>(p, nown, zsq, overall_out, feat_out);
   LSSPA_LAUNCH_CHECK();
   return LSSPA_OK;
 }

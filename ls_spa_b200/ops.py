@@ -382,7 +382,7 @@ class Estimator:
             o0, o1 = max(own0, pos) - pos, min(own1, pos + n) - pos
             zsq = None
             if emit and o1 > o0:
-                zsq = torch.empty((o1 - o0, self.p, ERR_DRAWS), dtype=torch.float64, device=self.device)
+                zsq = torch.empty((o1 - o0, self.p + 1, ERR_DRAWS), dtype=torch.float64, device=self.device)
             check(lib.lsspa_estimator_absorb(self.state.data_ptr(), self.p, self.cur, float(self.count),
                                              flat.data_ptr(), smap.data_ptr(), n, max(o0, 0), max(o1, 0),
                                              _ptr(zsq), 1 if self.estimate else 0, _stream()),
@@ -392,7 +392,7 @@ class Estimator:
                 lo = pos + o0 - own0
                 check(lib.lsspa_estimator_quantiles(self.p, zsq.data_ptr(), o1 - o0, overall[lo:].data_ptr(),
                                                     feat[lo:].data_ptr(), _stream()), "lsspa_estimator_quantiles")
-                _count(1)
+                _count(2)
             self.cur ^= 1
             self.count += int(sum(counts[pos:pos + n]))
             pos += n
