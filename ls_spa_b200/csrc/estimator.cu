@@ -192,14 +192,23 @@ __device__ __forceinline__ void dmma_e(double &d0, double &d1, double a, double 
 
 __host__ __device__ inline int mma_ldx(int ft) { return ((8 * ft) % 16 == 8) ? 8 * ft : 8 * ft + 8; }
 
-// rows [k0, k0 + rows) of the batch, centered, zero padded to kMmaRows x ldx
+// rows [k0, k0 + rows) of the batch, centered, zero padded to kMmaRows x ldx.  A warp takes whole
+// rows (lane -> features lane, lane + 32, ...): coalesced, no index arithmetic, 4 rows in flight.
 __device__ __forceinline__ void stage_rows(double *Xs, int ldx, const double *lifts, const double *mean, int p,
                                            int64_t row0, int rows, int tid, int nt) {
-  for (int e = tid; e < kMmaRows * ldx; e += nt) {
-    const int r = e / ldx, f = e - r * ldx;
-    double v = 0.0;
-    if (r < rows && f < p) v = lifts[(row0 + r) * p + f] - mean[f];
-    Xs[e] = v;
+  const int lane = tid & 31, w = tid >> 5, nw = nt >> 5;
+  double mu[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) mu[j] = (lane + 32 * j < p) ? mean[lane + 32 * j] : 0.0;
+#pragma unroll 4
+  for (int r = w; r < kMmaRows; r += nw) {
+    const double *src = lifts + (row0 + r) * p;
+    double *dst = Xs + (size_t)r * ldx;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int f = lane + 32 * j;
+      if (f < ldx) dst[f] = (r < rows && f < p) ? src[f] - mu[j] : 0.0;
+    }
   }
 }
 

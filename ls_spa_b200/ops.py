@@ -113,6 +113,9 @@ class CholQR2:
     and returns (slot, info): slot has the layout of tsqr_merge's result, info (device) =
     [[bad pivot 1, cond bound 1], [bad pivot 2, cond bound 2]]."""
 
+    # |R1|_F |R1^-1|_F of [X | y] up to which one Cholesky pass is kept as the factor
+    SINGLE_PASS_COND = 1e3
+
     def __init__(self, p: int, divisor: float):
         self.p, self.scale = p, 1.0 / (float(divisor) ** 2)
         self.chunks, self.parts1 = [], []
@@ -154,12 +157,23 @@ class CholQR2:
         info = torch.zeros((2, 2), dtype=torch.float64, device=dev)
         check(lib.lsspa_chol_factor(G1.data_ptr(), p, R1.data_ptr(), Rinv.data_ptr(), info[0].data_ptr(),
                                     _stream()), "lsspa_chol_factor")
+        slot = torch.empty(tsqr_slot(p), dtype=torch.float64, device=dev)
+        bad1, cond1 = (float(v) for v in info[0].cpu())
+        if bad1 == 0 and cond1 <= self.SINGLE_PASS_COND:
+            # Well conditioned: the second pass would only remove an orthogonality defect of order
+            # eps * cond^2 <= 1e-10, which is the accuracy class of everything downstream (the lifts
+            # depend on the factor through R^T R = the Gram matrix, which Cholesky reproduces to eps).
+            eye = torch.eye(q, dtype=torch.float64, device=dev)
+            check(lib.lsspa_tri_product(eye.data_ptr(), R1.data_ptr(), p, G1.data_ptr(), slot.data_ptr(),
+                                        _stream()), "lsspa_tri_product")
+            _count(2)
+            info[1, 1] = 1.0
+            return slot, info
         G2 = self._sum([self._rows(Xc, yc, Rinv) for Xc, yc in self.chunks])
         R2 = torch.empty_like(R1)
         Rinv2 = torch.empty_like(Rinv)
         check(lib.lsspa_chol_factor(G2.data_ptr(), p, R2.data_ptr(), Rinv2.data_ptr(), info[1].data_ptr(),
                                     _stream()), "lsspa_chol_factor")
-        slot = torch.empty(tsqr_slot(p), dtype=torch.float64, device=dev)
         check(lib.lsspa_tri_product(R2.data_ptr(), R1.data_ptr(), p, G1.data_ptr(), slot.data_ptr(), _stream()),
               "lsspa_tri_product")
         _count(3)
