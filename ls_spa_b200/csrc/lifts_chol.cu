@@ -115,6 +115,91 @@ __device__ __forceinline__ void diag_factor(double &t0, double &t1, double &y0, 
   y1 = (c < nf) ? y1 * rsc : 0.0;
 }
 
+// Rows 8 it .. 8 it + 7 of X = R_te[:, perm] in C / A-operand layout (lane (c, q): row 8 it + c,
+// columns 8 L + 2q + e) and the test target of the row.  Every load is issued from a valid (clamped)
+// address and masked afterwards, so all of them are in flight together.
+template <int RT>
+__device__ __forceinline__ void load_x(double (&xr)[RT][2], double &r_in, const CholParams &a, const int *perm_s,
+                                       int it, int p, int c, int q) {
+  const int row = 8 * it + c;
+  const int rowc = row < p ? row : p - 1;
+#pragma unroll
+  for (int L = 0; L < RT; ++L) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int l = 8 * L + 2 * q + e;
+      const int col = perm_s[l < p ? l : p - 1];
+      const double v = __ldg(a.Rte + (size_t)col * p + rowc);
+      xr[L][e] = (l < p && row <= col) ? v : 0.0;
+    }
+  }
+  const double t = __ldg(a.cte + rowc);
+  r_in = (row < p) ? t : 0.0;
+}
+
+// Elimination step J of one 8-row tile of X (reference :279-283): M_J = X_J R_JJ^-1 are 8 columns
+// of W = X R^-1; the running test residual of each row after each of these columns gives
+// cost_{k+1} (summed over the rows into wc); X_L -= M_J R_JL for the column tiles to the right.
+// Needs row block J of R, Dinv_J and c_J only -- i.e. it can run as soon as step J of the
+// factorisation is complete.
+template <int RT, int LD, int J>
+__device__ __forceinline__ void elim_step(double (&xr)[RT][2], double &r_in, double *wc, const double *A,
+                                          const double *Dbuf, const double *cvec, int p, int c, int q) {
+  const double2 dv = ld_tile(Dbuf + J * 64, 8, 0, 0, c, q);
+  double m0 = 0.0, m1 = 0.0;  // C layout (row, column 2q+e of the tile)
+  dmma(m0, m1, xr[J][0], dv.x);
+  dmma(m0, m1, xr[J][1], dv.y);
+  const double2 cv = *reinterpret_cast<const double2 *>(cvec + 8 * J + 2 * q);
+  const double t0 = m0 * cv.x, t1 = m1 * cv.y;
+  const double sl = t0 + t1;
+  double P = sl;
+  double up = __shfl_up_sync(kFull, P, 1, 4);
+  if (q >= 1) P += up;
+  up = __shfl_up_sync(kFull, P, 2, 4);
+  if (q >= 2) P += up;
+  const double ra = r_in - (P - sl) - t0;
+  const double rb = r_in - P;
+  double d0 = ra * ra, d1 = rb * rb;
+#pragma unroll
+  for (int o = 4; o < 32; o <<= 1) {
+    d0 += __shfl_xor_sync(kFull, d0, o);
+    d1 += __shfl_xor_sync(kFull, d1, o);
+  }
+  if (c == 0) {
+    const int k0 = 8 * J + 2 * q;
+    if (k0 < p) wc[k0] += d0;          // wc[k] collects cost_{k+1}
+    if (k0 + 1 < p) wc[k0 + 1] += d1;
+  }
+  r_in -= __shfl_sync(kFull, P, 3, 4);
+  m0 = -m0;
+  m1 = -m1;
+#pragma unroll
+  for (int L = J + 1; L < RT; ++L) {
+    const double2 rt = ld_tile(A, LD, 8 * J, 8 * L, c, q);
+    dmma(xr[L][0], xr[L][1], m0, rt.x);
+    dmma(xr[L][0], xr[L][1], m1, rt.y);
+  }
+}
+
+// run-time step index -> the statically indexed instance (the tile registers need constant indices)
+template <int RT, int LD, int J = 0>
+__device__ __forceinline__ void elim_dispatch(int s, double (&xr)[RT][2], double &r_in, double *wc, const double *A,
+                                              const double *Dbuf, const double *cvec, int p, int c, int q) {
+  if constexpr (J < RT) {
+    if (s == J) elim_step<RT, LD, J>(xr, r_in, wc, A, Dbuf, cvec, p, c, q);
+    else elim_dispatch<RT, LD, J + 1>(s, xr, r_in, wc, A, Dbuf, cvec, p, c, q);
+  }
+}
+
+template <int RT, int LD, int J = 0>
+__device__ __forceinline__ void elim_all(double (&xr)[RT][2], double &r_in, double *wc, const double *A,
+                                         const double *Dbuf, const double *cvec, int p, int c, int q) {
+  if constexpr (J < RT) {
+    elim_step<RT, LD, J>(xr, r_in, wc, A, Dbuf, cvec, p, c, q);
+    elim_all<RT, LD, J + 1>(xr, r_in, wc, A, Dbuf, cvec, p, c, q);
+  }
+}
+
 // sum_{k < kend} R(k, L)^T R(k, S) in C layout (the transpose of what tile (S, L) loses): four
 // independent accumulation chains, a dependent DMMA costs more than an issue slot
 template <int LD>
@@ -244,6 +329,16 @@ __global__ void __launch_bounds__(256, MINB) lifts_chol_kernel(CholParams a) {
       // term (F).  Tile (r, L), L > r, belongs to warp 1 + (L - r - 1) % 7; the diagonal tile of row
       // r is pre-accumulated in place by warp 1 + r % 7.
       constexpr int NSL = (PT - 1 + 6) / 7;
+      // The last NF warps also carry an 8-row tile of X in registers and eliminate it against row
+      // block s right after that block is complete (phase 2 fused into the shadow of the diagonal
+      // chain); NF is chosen so that the remaining row tiles are exactly one round of 8 warps.
+      double *wc = wcost + (size_t)warp * NR;
+      const double *cvec = A + (size_t)p * ld;
+      double xr[RT][2];
+      double r_in = 0.0;
+      constexpr int NF = (RT - 8 < 0) ? 0 : (RT - 8 > 7 ? 7 : RT - 8);  // fused tiles: the rest is one round of 8
+      const bool fused = warp >= 8 - NF;
+      if (fused) load_x<RT>(xr, r_in, a, perm_s, warp - (8 - NF), p, c, q);
       double2 tv[NSL];
 #pragma unroll
       for (int sl = 0; sl < NSL; ++sl) {
@@ -321,74 +416,15 @@ __global__ void __launch_bounds__(256, MINB) lifts_chol_kernel(CholParams a) {
             }
           }
         }
+        if (fused) elim_dispatch<RT, ld>(s, xr, r_in, wc, A, Dbuf, cvec, p, c, q);
         t_diag += clock64() - u2;
       }
 
       const long long t_c = clock64();
-      // ---- phase 2: X = R_te[:, perm] eliminated against R, one warp per 8-row tile, registers only
-      double *wc = wcost + (size_t)warp * NR;
-      const double *cvec = A + (size_t)p * ld;
-      for (int it = warp; it < RT; it += 8) {
-        const int row = 8 * it + c;  // C layout: lane (m = row, n = columns 2q+e)
-        double xr[RT][2];
-#pragma unroll
-        for (int L = 0; L < RT; ++L) {
-          xr[L][0] = 0.0;
-          xr[L][1] = 0.0;
-          {
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int l = 8 * L + 2 * q + e;
-              if (l < p) {
-                const int col = perm_s[l];
-                if (row <= col) xr[L][e] = a.Rte[(size_t)col * p + row];
-              }
-            }
-          }
-        }
-        double r_in = (row < p) ? a.cte[row] : 0.0;
-#pragma unroll
-        for (int J = 0; J < RT; ++J) {
-          {
-            const double2 dv = ld_tile(Dbuf + J * 64, 8, 0, 0, c, q);
-            double m0 = 0.0, m1 = 0.0;  // M_J = X_J R_JJ^-1, C layout (row, column 2q+e of the panel)
-            dmma(m0, m1, xr[J][0], dv.x);
-            dmma(m0, m1, xr[J][1], dv.y);
-            // running test residual of this row after each of the 8 columns of the panel
-            const double2 cv = *reinterpret_cast<const double2 *>(cvec + 8 * J + 2 * q);
-            const double t0 = m0 * cv.x, t1 = m1 * cv.y;
-            const double sl = t0 + t1;
-            double P = sl;
-            double up = __shfl_up_sync(kFull, P, 1, 4);
-            if (q >= 1) P += up;
-            up = __shfl_up_sync(kFull, P, 2, 4);
-            if (q >= 2) P += up;
-            const double ra = r_in - (P - sl) - t0;
-            const double rb = r_in - P;
-            double d0 = ra * ra, d1 = rb * rb;
-#pragma unroll
-            for (int o = 4; o < 32; o <<= 1) {
-              d0 += __shfl_xor_sync(kFull, d0, o);
-              d1 += __shfl_xor_sync(kFull, d1, o);
-            }
-            if (c == 0) {
-              const int k0 = 8 * J + 2 * q;
-              if (k0 < p) wc[k0] += d0;          // wc[k] collects cost_{k+1}
-              if (k0 + 1 < p) wc[k0 + 1] += d1;
-            }
-            r_in -= __shfl_sync(kFull, P, 3, 4);
-            m0 = -m0;
-            m1 = -m1;
-#pragma unroll
-            for (int L = 0; L < RT; ++L) {
-              if (L > J) {
-                const double2 rt = ld_tile(A, ld, 8 * J, 8 * L, c, q);
-                dmma(xr[L][0], xr[L][1], m0, rt.x);
-                dmma(xr[L][0], xr[L][1], m1, rt.y);
-              }
-            }
-          }
-        }
+      // ---- phase 2: the row tiles of X that were not carried through the factorisation
+      for (int it = NF + warp; it < RT; it += 8) {
+        load_x<RT>(xr, r_in, a, perm_s, it, p, c, q);
+        elim_all<RT, ld>(xr, r_in, wc, A, Dbuf, cvec, p, c, q);
       }
       const long long t_d = clock64();
       __syncthreads();
