@@ -53,11 +53,13 @@ def read_peaks():
     return peaks
 
 
-def lifts_dram_bytes_per_perm():
+def lifts_dram_bytes_per_perm(route=None):
     """DRAM bytes (read + write) per permutation evaluation of the lift kernel, from the committed
-    `ncu --set full` capture (profiles/r01_lifts_ncu_summary.json); None if absent."""
+    `ncu --set full` capture of the kernel of that route (profiles/r01_lifts*_ncu_summary.json);
+    None if absent."""
+    name = "r01_lifts_chol_ncu_summary.json" if route == "cholesky" else "r01_lifts_ncu_summary.json"
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_lifts_ncu_summary.json")) as f:
+        with open(os.path.join(ROOT, "profiles", name)) as f:
             d = json.load(f)
         return float(d["dram_bytes_per_launch"]) / float(d["permutation_evaluations_per_launch"])
     except Exception:
@@ -275,7 +277,7 @@ def run_gpu(args):
         # solve).  The Cholesky route executes 1/3 p^3 + p^3; frac_executed rates the pipe on that.
         chol = ops.LIFT_ROUTE == "cholesky"
         exec_flop = (4.0 / 3.0 if chol else 7.0 / 3.0) * P ** 3
-        bpp = lifts_dram_bytes_per_perm()
+        bpp = lifts_dram_bytes_per_perm(ops.LIFT_ROUTE)
         traffic = bpp * lift_perms / max(len(trace), 1) if bpp is not None else None
         out = {
             "metric": "permutations/sec (LS-SPA, p=100, N=M=1e6 rows, reduction + permutohedron samples + estimator)",
@@ -302,7 +304,7 @@ def run_gpu(args):
                          "peak_source": fp64_src, "kernel_ms_per_step": lift_ms / args.steps,
                          "kernel_share_of_step": lift_ms / ms_total,
                          "algorithmic_flop_per_permutation": FLOP_PER_PERM},
-            "roofline_reduce": {"bound": "hbm", "kernel": "gram_rows_kernel x2 (CholeskyQR2) + chol_factor_kernel",
+            "roofline_reduce": {"bound": "hbm", "kernel": "gram_rows_kernel (CholeskyQR, second pass only when cond > 1e3) + chol_factor_kernel",
                                 "achieved": red_bytes / (red_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
                                 "unit": "GB/s", "frac": red_bytes / (red_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                                 "peak_source": peaks["which"], "ms": red_ms, "algorithmic_bytes": red_bytes},
