@@ -10,9 +10,12 @@ Multi-GPU (one process per GPU, ``torch.distributed``):
   * rows of the reduction are sharded; the per-rank triangular factors are
     all-gathered and merged identically on every rank;
   * every super-batch of sample batches is cut into contiguous runs of batches, one
-    run per rank; the per-batch partial moments are all-gathered and folded into the
-    (replicated) estimator state in batch order, so every rank takes the same stop
-    decision without a broadcast.
+    run per rank; a rank folds its own run locally and ships ONE partial block (the
+    run total); every rank folds the W totals into the (replicated) estimator state
+    in rank order, computes the error estimates of its own batches from a scratch
+    copy advanced by the earlier ranks' totals, and the per-batch errors are
+    all-gathered, so every rank takes the same stop decision without a broadcast.
+    Only a stop inside a super-batch gathers the per-batch blocks (for the replay).
 """
 
 from __future__ import annotations
@@ -62,7 +65,7 @@ def contiguous_runs(nbatch: int, world: int):
 
 
 def target_samples(p: int) -> int:
-    t = int(8192 * (100.0 / max(p, 1)) ** 2)
+    t = int(16384 * (100.0 / max(p, 1)) ** 2)
     return max(256, min(t, 131072))
 
 
@@ -324,17 +327,29 @@ def run_samples(backend, coll: Collective, prob, source: PermutationSource, cfg:
             desc.append((off, n, first))
             off += n
         part = est.partials(rows, desc)
-        if W > 1:
-            if part.shape[0] < per:
-                pad = backend.zeros(per - part.shape[0], part.shape[1])
-                part = torch.cat([part, pad], 0)
-            gathered = coll.all_gather(part)                     # (W, per, PD)
-            slots = [r * per + i for r, (a, b) in enumerate(runs) for i in range(b - a)]
-        else:
-            gathered, slots = part, list(range(nb))
         counts = [n for _, n in batches]
-        snap = est.snapshot() if can_stop else None
-        overall, feat = est.absorb(gathered, slots, counts, own=(b0, b1), emit=cfg.estimate_errors)
+        if W > 1:
+            # Hierarchical merge: every rank folds its own run of batches into a scratch estimator and
+            # ships the run total as ONE partial block (W small blocks on the wire instead of every
+            # batch's block); the error estimates of the own batches come from a scratch copy of the
+            # global state advanced by the totals of the earlier ranks; the global state absorbs the
+            # W totals in rank order on every rank (replicated, deterministic).
+            own_counts, nb_r = counts[b0:b1], b1 - b0
+            run_counts = [sum(counts[a:b]) for a, b in runs]
+            loc = est.scratch()
+            loc.reset()
+            loc.absorb(part, list(range(nb_r)), own_counts, emit=False)
+            totals = coll.all_gather(loc.export_block().view(1, -1)).reshape(W, -1)
+            loc.copy_from(est)
+            if rank > 0:
+                loc.absorb(totals, list(range(rank)), run_counts[:rank], emit=False)
+            overall, feat = loc.absorb(part, list(range(nb_r)), own_counts, own=(0, nb_r),
+                                       emit=cfg.estimate_errors)
+            snap = est.snapshot() if can_stop else None
+            est.absorb(totals, list(range(W)), run_counts, emit=False)
+        else:
+            snap = est.snapshot() if can_stop else None
+            overall, feat = est.absorb(part, list(range(nb)), counts, own=(b0, b1), emit=cfg.estimate_errors)
         rows_in_order = None
         if hist_chunks is not None:
             if W > 1:
@@ -375,6 +390,15 @@ def run_samples(backend, coll: Collective, prob, source: PermutationSource, cfg:
                     nxt = None
                     if keep < nb:                                 # stop inside the super-batch: replay
                         est.restore(snap)
+                        if W > 1:                                 # now every batch's block is needed, in order
+                            padded = part
+                            if padded.shape[0] < per:
+                                pad = backend.zeros(per - padded.shape[0], padded.shape[1])
+                                padded = torch.cat([padded, pad], 0)
+                            gathered = coll.all_gather(padded)                     # (W, per, PD)
+                            slots = [r * per + i for r, (a, b) in enumerate(runs) for i in range(b - a)]
+                        else:
+                            gathered, slots = part, list(range(nb))
                         est.absorb(gathered, slots[:keep], counts[:keep], emit=False)
                 err_hist.extend(errs[:keep].tolist())
                 feat_last = feat[keep - 1]

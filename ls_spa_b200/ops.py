@@ -372,6 +372,40 @@ class Estimator:
     def snapshot(self):
         return self.state.clone(), self.cur, self.count
 
+    # -- hierarchical merging (multi-GPU): a rank folds its own run of batches into a scratch
+    #    estimator, ships the result as ONE partial block, and every rank folds the W run totals.
+    def scratch(self) -> "Estimator":
+        """A second estimator of the same shape (allocated once, reused)."""
+        sc = getattr(self, "_scratch", None)
+        if sc is None:
+            sc = Estimator.__new__(Estimator)
+            sc.__dict__.update({k: v for k, v in self.__dict__.items() if k != "_scratch"})
+            sc.state = torch.zeros_like(self.state)
+            sc.cur, sc.count = 0, 0
+            self._scratch = sc
+        return sc
+
+    def reset(self) -> None:
+        self.state.zero_()
+        self.cur, self.count = 0, 0
+
+    def copy_from(self, other: "Estimator") -> None:
+        self.state.copy_(other.state)
+        self.cur, self.count = other.cur, other.count
+
+    def export_block(self) -> torch.Tensor:
+        """The whole state as one partial block {n, mean, M2 = n * biased cov, G, S} (the layout of
+        lsspa_estimator_partials), so that it can be folded into another state by absorb()."""
+        p, st, cur = self.p, self.state, self.cur
+        o_g, o_cov, o_s = 2 * p, 2 * p + 2 * ERR_DRAWS, 2 * p + 2 * ERR_DRAWS + p * p
+        blk = torch.zeros(self.partial_doubles, dtype=torch.float64, device=self.device)
+        blk[0] = float(self.count)
+        blk[8:8 + p] = st[cur * p:(cur + 1) * p]
+        blk[8 + p:8 + p + p * p] = st[o_cov:o_s] * float(self.count)
+        blk[8 + p + p * p:8 + p + p * p + ERR_DRAWS] = st[o_g + cur * ERR_DRAWS:o_g + (cur + 1) * ERR_DRAWS]
+        blk[8 + p + p * p + ERR_DRAWS:] = st[o_s:]
+        return blk
+
     def restore(self, snap) -> None:
         self.state.copy_(snap[0])
         self.cur, self.count = snap[1], snap[2]

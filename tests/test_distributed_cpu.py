@@ -47,6 +47,24 @@ class FakeEstimator:
     def snapshot(self):
         return self.count, self.mean.copy(), self.cov.copy()
 
+    def scratch(self):
+        if not hasattr(self, "_scratch"):
+            self._scratch = FakeEstimator(self.p)
+        return self._scratch
+
+    def reset(self):
+        self.count, self.mean, self.cov = 0, np.zeros(self.p), np.zeros((self.p, self.p))
+
+    def copy_from(self, other):
+        self.count, self.mean, self.cov = other.count, other.mean.copy(), other.cov.copy()
+
+    def export_block(self):
+        blk = torch.zeros(self.partial_doubles, dtype=torch.float64)
+        blk[0] = self.count
+        blk[1:1 + self.p] = torch.from_numpy(self.mean)
+        blk[1 + self.p:] = torch.from_numpy(self.cov.reshape(-1))
+        return blk
+
     def restore(self, snap):
         self.count, self.mean, self.cov = snap[0], snap[1].copy(), snap[2].copy()
 
