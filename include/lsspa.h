@@ -139,10 +139,15 @@ LSSPA_API int lsspa_lifts(int p, const double *R_tr_cm, const double *c_tr, cons
  * the triangular factor of R_tr[:, perm] (np.linalg.qr, ls_spa/ls_spa.py:268) is computed as
  * the Cholesky factor of the permuted Gram matrix of [R_tr | c_tr], so the forward error grows
  * like eps * cond(R_tr)^2 instead of eps * cond(R_tr).
- *   lsspa_lifts_gram   once per reduced problem: gram_out[0 .. (p+1)^2) = [R_tr|c_tr]^T [R_tr|c_tr],
- *                      gram_out[(p+1)^2 + 0] = |R_tr|_F |R_tr^-1|_F  (>= cond_2, inf if singular),
- *                      gram_out[(p+1)^2 + 1] = min|R_kk| / max|R_kk|; the rest is scratch.
- *   lsspa_lifts_chol   same outputs as lsspa_lifts, reading gram_out instead of R_tr / c_tr.
+ *   lsspa_lifts_gram   once per reduced problem.  With D = diag(column norms of R_tr) and
+ *                      R' = R_tr D^-1 (the lifts do not change when train and test features are
+ *                      scaled alike, and unit columns remove the conditioning that is only units):
+ *                      gram_out[0 .. (p+1)^2)       = [R'|c_tr]^T [R'|c_tr],
+ *                      gram_out[(p+1)^2 + 0]        = |R'|_F |R'^-1|_F  (>= cond_2, inf if singular),
+ *                      gram_out[(p+1)^2 + 1]        = min|R'_kk| / max|R'_kk|,
+ *                      gram_out[(p+1)^2 + 8 .. +8+p) = D; the rest is scratch.
+ *   lsspa_lifts_chol   same outputs as lsspa_lifts, reading gram_out instead of R_tr / c_tr;
+ *                      R_te_cm must be the test factor with its columns divided by D.
  * The caller decides from the condition estimate which route to take (ls_spa_b200/ops.py uses
  * the Cholesky route when the estimate is <= 1e3, i.e. an expected error <= 1e-10). */
 LSSPA_API int lsspa_lifts_chol_supported(int p);

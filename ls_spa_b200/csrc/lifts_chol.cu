@@ -482,15 +482,29 @@ int launch_chol_rt(const CholParams &a, int grid, size_t smem, cudaStream_t st) 
   return (a.pt == RT) ? launch_chol<RT, RT, MINB>(a, grid, smem, st) : launch_chol<RT, RT + 1, MINB>(a, grid, smem, st);
 }
 
-// Gh = [R | c]^T [R | c] for upper-triangular R (column-major, ld p): block (i), thread (j)
+// Column norms of the upper-triangular R (column-major, ld p): D[j] = |R[:, j]|, 1 where the column is zero
+__global__ void lift_scale_kernel(int p, const double *__restrict__ R, double *__restrict__ D) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= p) return;
+  double s0 = 0.0;
+  for (int k = 0; k <= j; ++k) s0 = fma(R[(size_t)j * p + k], R[(size_t)j * p + k], s0);
+  D[j] = s0 > 0.0 ? sqrt(s0) : 1.0;
+}
+
+// Gh = [R D^-1 | c]^T [R D^-1 | c] for upper-triangular R (column-major, ld p): block (i), thread (j).
+// The columns are equilibrated (unit norm): the lifts are invariant under a scaling of the features
+// when the test factor is scaled alike, and the scaling removes the part of the conditioning
+// that is only due to units (within sqrt(p) of the best diagonal scaling, van der Sluis).
 __global__ void lift_gram_kernel(int p, const double *__restrict__ R, const double *__restrict__ cvec,
-                                 double *__restrict__ Gh) {
+                                 const double *__restrict__ D, double *__restrict__ Gh) {
   const int i = blockIdx.x;  // 0..p
   const double *ci = (i < p) ? R + (size_t)i * p : cvec;
   const int ni = (i < p) ? i + 1 : p;
+  const double di = (i < p) ? D[i] : 1.0;
   for (int j = threadIdx.x; j <= p; j += blockDim.x) {
     const double *cj = (j < p) ? R + (size_t)j * p : cvec;
     const int nj = (j < p) ? j + 1 : p;
+    const double dj = (j < p) ? D[j] : 1.0;
     const int n = ni < nj ? ni : nj;
     double s0 = 0.0, s1 = 0.0;
     int k = 0;
@@ -499,28 +513,31 @@ __global__ void lift_gram_kernel(int p, const double *__restrict__ R, const doub
       s1 = fma(ci[k + 1], cj[k + 1], s1);
     }
     if (k < n) s0 = fma(ci[k], cj[k], s0);
-    Gh[(size_t)i * (p + 1) + j] = s0 + s1;
+    Gh[(size_t)i * (p + 1) + j] = (s0 + s1) / (di * dj);
   }
 }
 
-// info[0] = |R|_F |R^-1|_F (>= cond_2(R)), info[1] = min |R_kk| / max |R_kk|.  One CTA; thread j
-// solves R x = e_j by back substitution (x has j + 1 non-zeros).  inf when R is singular.
-__global__ void lift_cond_kernel(int p, const double *__restrict__ R, double *__restrict__ info,
-                                 double *__restrict__ scratch /* p * p */) {
-  __shared__ double red[3][32];
+// info[0] = |R'|_F |R'^-1|_F (>= cond_2(R')) of the equilibrated factor R' = R D^-1,
+// info[1] = min |R'_kk| / max |R'_kk|.  One CTA; thread j solves R' x = e_j by back substitution
+// (x has j + 1 non-zeros).  inf when R is singular.
+__global__ void lift_cond_kernel(int p, const double *__restrict__ R, const double *__restrict__ D,
+                                 double *__restrict__ info, double *__restrict__ scratch /* p * p */) {
+  __shared__ double red[2][32];
+  __shared__ double rmin[32], rmax[32];
   double fr = 0.0, fi = 0.0, dmin = 1e300, dmax = 0.0;
   for (int j = threadIdx.x; j < p; j += blockDim.x) {
     double *x = scratch + (size_t)j * p;
+    const double dj = D[j];
     for (int i = j; i >= 0; --i) {
       double sacc = (i == j) ? 1.0 : 0.0;
-      for (int k = i + 1; k <= j; ++k) sacc = fma(-R[(size_t)k * p + i], x[k], sacc);
-      const double v = sacc / R[(size_t)i * p + i];
+      for (int k = i + 1; k <= j; ++k) sacc = fma(-R[(size_t)k * p + i] / D[k], x[k], sacc);
+      const double v = sacc / (R[(size_t)i * p + i] / D[i]);
       x[i] = v;
       fi = fma(v, v, fi);
-      const double r = R[(size_t)j * p + i];
+      const double r = R[(size_t)j * p + i] / dj;
       fr = fma(r, r, fr);
     }
-    const double d = fabs(R[(size_t)j * p + j]);
+    const double d = fabs(R[(size_t)j * p + j] / dj);
     dmin = fmin(dmin, d);
     dmax = fmax(dmax, d);
   }
@@ -531,7 +548,6 @@ __global__ void lift_cond_kernel(int p, const double *__restrict__ R, double *__
     dmax = fmax(dmax, __shfl_xor_sync(kFull, dmax, o));
   }
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  __shared__ double rmin[32], rmax[32];
   if (l == 0) {
     red[0][w] = fr;
     red[1][w] = fi;
@@ -568,16 +584,19 @@ extern "C" int lsspa_lifts_chol_supported(int p) { return lifts_chol_supported(p
 
 extern "C" int64_t lsspa_lifts_gram_doubles(int p) {
   if (p < 1) return 0;
-  return (int64_t)(p + 1) * (p + 1) + 8 + (int64_t)p * p;  // Gh, info[8], scratch of the estimate
+  return (int64_t)(p + 1) * (p + 1) + 8 + p + (int64_t)p * p;  // Gh, info[8], D[p], scratch of the estimate
 }
 
 extern "C" int lsspa_lifts_gram(int p, const double *R_tr_cm, const double *c_tr, double *gram_out, void *stream) {
   if (p < 1 || !R_tr_cm || !c_tr || !gram_out) return LSSPA_E_BADARG;
   cudaStream_t st = as_stream(stream);
-  lift_gram_kernel<<<p + 1, 128, 0, st>>>(p, R_tr_cm, c_tr, gram_out);
-  LSSPA_LAUNCH_CHECK();
   double *info = gram_out + (size_t)(p + 1) * (p + 1);
-  lift_cond_kernel<<<1, 128, 0, st>>>(p, R_tr_cm, info, info + 8);
+  double *D = info + 8;
+  lift_scale_kernel<<<(p + 127) / 128, 128, 0, st>>>(p, R_tr_cm, D);
+  LSSPA_LAUNCH_CHECK();
+  lift_gram_kernel<<<p + 1, 128, 0, st>>>(p, R_tr_cm, c_tr, D, gram_out);
+  LSSPA_LAUNCH_CHECK();
+  lift_cond_kernel<<<1, 128, 0, st>>>(p, R_tr_cm, D, info, D + p);
   LSSPA_LAUNCH_CHECK();
   return LSSPA_OK;
 }

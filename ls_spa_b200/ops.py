@@ -278,10 +278,13 @@ class ReducedProblem:
             self.gram = torch.empty(n, dtype=torch.float64, device=dev)
             check(_lib().lsspa_lifts_gram(p, self.R_tr_cm.data_ptr(), self.c_tr.data_ptr(),
                                           self.gram.data_ptr(), _stream()), "lsspa_lifts_gram")
-            _count(2)
-            info = self.gram[(p + 1) * (p + 1):(p + 1) * (p + 1) + 2].cpu()
-            self.cond_estimate = float(info[0])
+            _count(3)
+            base = (p + 1) * (p + 1)
+            info = self.gram[base:base + 2].cpu()
+            self.cond_estimate = float(info[0])    # of the column-equilibrated train factor
             self.use_chol = forced == "chol" or self.cond_estimate <= CHOL_COND_LIMIT
+            # the Cholesky route works on unit-norm train columns: scale the test columns alike
+            self.R_te_scaled_cm = self.R_te_cm / self.gram[base + 8:base + 8 + p].unsqueeze(1)
 
     def workspace(self, count: int):
         nbytes = _lib().lsspa_lifts_workspace_bytes(self.p, count)
@@ -310,7 +313,7 @@ def lifts(prob: ReducedProblem, perms: torch.Tensor, antithetical: bool, out: to
     global LIFT_ROUTE
     LIFT_ROUTE = "cholesky" if prob.use_chol else "householder"
     if prob.use_chol:
-        check(_lib().lsspa_lifts_chol(p, prob.gram.data_ptr(), prob.R_te_cm.data_ptr(), prob.c_te.data_ptr(),
+        check(_lib().lsspa_lifts_chol(p, prob.gram.data_ptr(), prob.R_te_scaled_cm.data_ptr(), prob.c_te.data_ptr(),
                                       prob.y_norm_sq, perms.data_ptr(), count, 1 if antithetical else 0,
                                       out.data_ptr(), _stream()), "lsspa_lifts_chol")
     else:

@@ -165,7 +165,22 @@ def test_lift_route_selection(T):
             prob.use_chol = False
             b = ops.lifts(prob, perms, anti).cpu().numpy()
             assert scaled_err(a, b) < 1e-11, (p, anti, scaled_err(a, b))
+    # badly scaled features (units): the Cholesky route equilibrates the columns, so it is still taken,
+    # and the lifts equal those of the unscaled problem (they are invariant under feature scaling)
     p = 100
+    R1 = np.linalg.qr(rng.standard_normal((3 * p, p)) / np.sqrt(3 * p), mode="r")
+    R2 = np.linalg.qr(rng.standard_normal((3 * p, p)), mode="r")
+    c1, c2 = rng.standard_normal(p), rng.standard_normal(p)
+    scale = 10.0 ** rng.uniform(-4, 4, p)
+    plain = ops.ReducedProblem(f(R1), f(c1), f(R2), f(c2), float(c2 @ c2) * 1.5)
+    scaled = ops.ReducedProblem(f(R1 * scale), f(c1), f(R2 * scale), f(c2), float(c2 @ c2) * 1.5)
+    assert np.linalg.cond(R1 * scale) > 1e6 and scaled.use_chol and scaled.cond_estimate < 1e3
+    perms = samplers.ArgsortSource(p, 3, None, dev).take(500)
+    plain.use_chol = False
+    want = ops.lifts(plain, perms, True).cpu().numpy()
+    got = ops.lifts(scaled, perms, True).cpu().numpy()
+    assert scaled_err(got, want) < 1e-10, scaled_err(got, want)
+
     R2 = np.linalg.qr(rng.standard_normal((3 * p, p)), mode="r")
     c1, c2 = rng.standard_normal(p), rng.standard_normal(p)
     U, _, Vt = np.linalg.svd(rng.standard_normal((p, p)))
