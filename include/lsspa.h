@@ -77,7 +77,9 @@ LSSPA_API int lsspa_tsqr_merge(const double *parts, int count, int group, int p,
  *   pass 1: lsspa_gram_rows(Rinv = NULL) -> partial Grams; lsspa_gram_finish sums them (fixed
  *           order) and scales by 1/divisor^2 -> G1 ((8*ceil((p+1)/8))^2 doubles, row-major);
  *           lsspa_chol_factor -> R1 (q x q row-major), R1^-1 (padded, the layout pass 2 wants),
- *           info[2] = {0 ok / 1 bad pivot, |R|_F |R^-1|_F >= cond_2};
+ *           info[2] = {0 ok / 1 bad pivot, |R'|_F |R'^-1|_F >= cond_2 of the column-equilibrated
+ *           factor R' = R diag(|R[:,j]|)^-1 -- the conditioning that governs Cholesky's accuracy};
+ *           when that bound is small (<= 1e3) the caller may keep R1 as the factor (one pass);
  *   pass 2: lsspa_gram_rows(Rinv = R1^-1) accumulates (Z R1^-1)^T (Z R1^-1) -> G2 -> R2;
  *   lsspa_tri_product: factor = R2 R1 in the slot layout of lsspa_tsqr_merge.
  * The caller falls back to lsspa_tsqr_rows when info reports a bad pivot or cond > ~1e6. */

@@ -189,7 +189,10 @@ __global__ void gram_sum_kernel(const double *parts, int count, int n2, double s
 }
 
 // Cholesky G = R^T R (upper, G row-major nc x nc, leading q x q block used), then R^-1.
-// info[0] = 0 ok / 1 non-positive or tiny pivot, info[1] = |R|_F |R^-1|_F (>= cond_2(R)).
+// info[0] = 0 ok / 1 non-positive or tiny pivot (relative to the column's own norm),
+// info[1] = |R'|_F |R'^-1|_F (>= cond_2(R')) of the column-equilibrated factor R' = R D^-1,
+// D = diag(sqrt(G_jj)): the accuracy of a Cholesky factor is governed by the conditioning of the
+// equilibrated matrix (van der Sluis / Demmel), so units of the columns must not count.
 // R is written row-major q x q (slot layout of reduce.cu); Rinv row-major [nc][ldr], zero padded.
 __global__ void __launch_bounds__(256) chol_factor_kernel(const double *G, int q, int nc, int ldr, double *R_out,
                                                           double *Rinv_out, double *info) {
@@ -210,7 +213,7 @@ __global__ void __launch_bounds__(256) chol_factor_kernel(const double *G, int q
   for (int k = 0; k < q; ++k) {
     if (tid == 0) {
       const double d = A[(size_t)k * nc + k];
-      if (!(d > 1e-14 * dmax)) s_fail = 1.0;
+      if (!(d > 1e-14 * G[(size_t)k * nc + k]) || !(dmax > 0.0)) s_fail = 1.0;
       const double r = sqrt(d > 0.0 ? d : 1.0);
       A[(size_t)k * nc + k] = r;
       s_piv = 1.0 / r;
@@ -243,8 +246,14 @@ __global__ void __launch_bounds__(256) chol_factor_kernel(const double *G, int q
   __syncthreads();
   double fr = 0.0, fi = 0.0;
   for (int e = tid; e < nc * nc; e += nt) {
-    fr = fma(A[e], A[e], fr);
-    fi = fma(Vi[e], Vi[e], fi);
+    const int i = e / nc, j = e - i * nc;
+    if (i < q && j < q) {
+      const double di = sqrt(fmax(G[(size_t)i * nc + i], 0.0)), dj = sqrt(fmax(G[(size_t)j * nc + j], 0.0));
+      const double r = (dj > 0.0) ? A[e] / dj : 0.0;
+      const double v = Vi[e] * di;
+      fr = fma(r, r, fr);
+      fi = fma(v, v, fi);
+    }
   }
   fr = warp_sum(fr);
   fi = warp_sum(fi);
