@@ -8,6 +8,8 @@
 // The arithmetic restated here is third-party (numpy 2.3.5 PCG64 / Generator.shuffle,
 // scipy 1.18.1 qmc.Sobol and MultivariateNormalQMC); the reference only calls it.
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace lsspa {
@@ -167,6 +169,134 @@ __global__ void pcg64_scan_kernel(int p, int64_t count, const uint32_t *raw, int
   }
 }
 
+// ---- parallel resolution of the masked rejection -------------------------------------------
+// Which draws are accepted depends on the Fisher-Yates step m = (acceptances so far) mod (p - 1):
+// a finite-state machine over the draw stream.  It is evaluated in parallel the standard way:
+//   1. every chunk of kChunk draws is simulated from EVERY start state (block = chunk, thread =
+//      state): acc_tab[chunk][m0] = acceptances inside the chunk;
+//   2. the same per group of kGroup chunks (composition of the chunk maps), then one short serial
+//      walk over the groups gives the global acceptance count at every group start;
+//   3. every chunk is replayed from its now known start state (one thread per chunk) and writes
+//      the accepted values; the thread that produces the last needed acceptance records how many
+//      draws the stream consumed.
+constexpr int kChunk = 256;
+constexpr int kGroup = 64;
+
+__device__ __forceinline__ bool fy_accept(uint32_t d, int steps, int m, uint32_t &val) {
+  const uint32_t i = (uint32_t)(steps - m);  // Fisher-Yates index p-1 .. 1
+  val = d & (0xffffffffu >> __clz(i));
+  return val <= i;
+}
+
+__global__ void __launch_bounds__(128) pcg64_fsm_kernel(int steps, const uint32_t *raw, int64_t ndraws,
+                                                        uint16_t *acc_tab) {
+  __shared__ uint32_t d[kChunk];
+  const int64_t c = blockIdx.x, n0 = c * kChunk;
+  const int nvalid = (int)((ndraws - n0 < kChunk) ? ndraws - n0 : kChunk);
+  for (int i = threadIdx.x; i < nvalid; i += blockDim.x) d[i] = raw[n0 + i];
+  __syncthreads();
+  for (int m0 = threadIdx.x; m0 < steps; m0 += blockDim.x) {
+    int m = m0, a = 0;
+    for (int n = 0; n < nvalid; ++n) {
+      uint32_t v;
+      if (fy_accept(d[n], steps, m, v)) {
+        ++a;
+        m = (m + 1 == steps) ? 0 : m + 1;
+      }
+    }
+    acc_tab[c * steps + m0] = (uint16_t)a;
+  }
+}
+
+__global__ void __launch_bounds__(128) pcg64_group_kernel(int steps, int64_t nchunks, const uint16_t *acc_tab,
+                                                          uint32_t *grp_tab) {
+  const int64_t g = blockIdx.x, c0 = g * kGroup;
+  const int64_t c1 = (c0 + kGroup < nchunks) ? c0 + kGroup : nchunks;
+  for (int m0 = threadIdx.x; m0 < steps; m0 += blockDim.x) {
+    int m = m0;
+    uint32_t t = 0;
+    for (int64_t c = c0; c < c1; ++c) {
+      const int a = acc_tab[c * steps + m];
+      t += (uint32_t)a;
+      m = (m + a) % steps;
+    }
+    grp_tab[g * steps + m0] = t;
+  }
+}
+
+// Tg[g] = acceptances before group g (Tg[ngroups] = all of them); consumed = -1 (not yet known)
+__global__ void pcg64_prefix_kernel(int steps, int64_t ngroups, const uint32_t *grp_tab, int64_t *Tg,
+                                    int64_t *consumed) {
+  int64_t t = 0;
+  for (int64_t g = 0; g < ngroups; ++g) {
+    Tg[g] = t;
+    t += grp_tab[g * steps + (int)(t % steps)];
+  }
+  Tg[ngroups] = t;
+  *consumed = -1;
+}
+
+__global__ void __launch_bounds__(kGroup) pcg64_emit_kernel(int steps, int64_t total, const uint32_t *raw,
+                                                            int64_t ndraws, int64_t nchunks, const uint16_t *acc_tab,
+                                                            const int64_t *Tg, int32_t *accepted, int64_t *consumed) {
+  __shared__ int64_t tc[kGroup];
+  const int64_t g = blockIdx.x, c0 = g * kGroup;
+  if (threadIdx.x == 0) {
+    int64_t t = Tg[g];
+    for (int k = 0; k < kGroup; ++k) {
+      tc[k] = t;
+      if (c0 + k < nchunks) t += acc_tab[(c0 + k) * steps + (int)(t % steps)];
+    }
+  }
+  __syncthreads();
+  const int64_t c = c0 + threadIdx.x;
+  if (c >= nchunks) return;
+  int64_t t = tc[threadIdx.x];
+  if (t >= total) return;
+  int m = (int)(t % steps);
+  const int64_t n0 = c * kChunk;
+  const int nvalid = (int)((ndraws - n0 < kChunk) ? ndraws - n0 : kChunk);
+  for (int n = 0; n < nvalid; ++n) {
+    uint32_t v;
+    if (fy_accept(raw[n0 + n], steps, m, v)) {
+      accepted[t] = (int32_t)v;
+      ++t;
+      m = (m + 1 == steps) ? 0 : m + 1;
+      if (t == total) {
+        *consumed = n0 + n + 1;
+        break;
+      }
+    }
+  }
+}
+
+// advance the generator by the draws the stream consumed (the buffered half word included)
+__global__ void pcg64_finish_kernel(int64_t ndraws, const int64_t *consumed_in, uint64_t *gen_state,
+                                    int *status_flag) {
+  int64_t consumed = *consumed_in;
+  if (consumed < 0) {  // raw budget exhausted (caller sized it too small)
+    *status_flag = 1;
+    consumed = ndraws;
+  }
+  const u128 s0 = ((u128)gen_state[0] << 64) | gen_state[1];
+  const u128 inc = ((u128)gen_state[2] << 64) | gen_state[3];
+  const int has = gen_state[4] != 0;
+  const int64_t from_outputs = consumed - ((has && consumed > 0) ? 1 : 0);
+  if (consumed > 0) {
+    const uint64_t nout = (uint64_t)((from_outputs + 1) / 2);
+    const u128 s = pcg_advance(s0, inc, nout);
+    gen_state[0] = (uint64_t)(s >> 64);
+    gen_state[1] = (uint64_t)s;
+    if (from_outputs & 1) {
+      gen_state[4] = 1;
+      gen_state[5] = pcg_output(s) >> 32;
+    } else {
+      gen_state[4] = 0;
+      gen_state[5] = 0;
+    }
+  }
+}
+
 // thread per permutation: a = arange(p); for i = p-1..1: swap(a[i], a[j_i])
 __global__ void pcg64_shuffle_kernel(int p, int64_t count, const int32_t *accepted, int32_t *out) {
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -303,11 +433,35 @@ extern "C" int lsspa_perms_exact(int p, uint64_t first_rank, int64_t count, int3
   return LSSPA_OK;
 }
 
+// workspace: raw draws | accepted values | chunk tables | group tables | group prefix | consumed
+struct PcgLayout {
+  int64_t budget, nchunks, ngroups, steps;
+  size_t off_acc, off_tab, off_grp, off_tg, off_cons, bytes;
+};
+static PcgLayout pcg64_layout(int p, int64_t count) {
+  PcgLayout L;
+  L.steps = p > 1 ? p - 1 : 1;
+  L.budget = pcg64_raw_budget(p, count);
+  L.nchunks = ceil_div(L.budget, kChunk);
+  L.ngroups = ceil_div(L.nchunks, kGroup);
+  auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  size_t o = up((size_t)(L.budget + 2) * sizeof(uint32_t));
+  L.off_acc = o;
+  o = up(o + (size_t)count * L.steps * sizeof(int32_t));
+  L.off_tab = o;
+  o = up(o + (size_t)L.nchunks * L.steps * sizeof(uint16_t));
+  L.off_grp = o;
+  o = up(o + (size_t)L.ngroups * L.steps * sizeof(uint32_t));
+  L.off_tg = o;
+  o = up(o + (size_t)(L.ngroups + 1) * sizeof(int64_t));
+  L.off_cons = o;
+  L.bytes = o + 256;
+  return L;
+}
+
 extern "C" size_t lsspa_perms_pcg64_workspace_bytes(int p, int64_t count) {
   if (p < 1 || count < 1) return 0;
-  const int64_t nraw = pcg64_raw_budget(p, count) + 2;
-  const int64_t nacc = count * (int64_t)(p > 1 ? p - 1 : 1);
-  return (size_t)(nraw + nacc) * sizeof(uint32_t) + 256;
+  return pcg64_layout(p, count).bytes;
 }
 
 extern "C" int lsspa_perms_pcg64(int p, uint64_t *gen_state, int64_t count, int32_t *perms_out,
@@ -316,11 +470,12 @@ extern "C" int lsspa_perms_pcg64(int p, uint64_t *gen_state, int64_t count, int3
   if (p < 1 || count < 0 || !gen_state || !perms_out || !status_flag) return LSSPA_E_BADARG;
   if (count == 0) return LSSPA_OK;
   cudaStream_t st = as_stream(stream);
-  const size_t need = lsspa_perms_pcg64_workspace_bytes(p, count);
-  if (!workspace || workspace_bytes < need) return LSSPA_E_WORKSPACE;
-  const int64_t budget = pcg64_raw_budget(p, count);  // even number of 32-bit draws
-  uint32_t *raw = reinterpret_cast<uint32_t *>(workspace);
-  int32_t *accepted = reinterpret_cast<int32_t *>(raw + budget + 2);
+  const PcgLayout L = pcg64_layout(p, count);
+  if (!workspace || workspace_bytes < L.bytes) return LSSPA_E_WORKSPACE;
+  char *ws = reinterpret_cast<char *>(workspace);
+  const int64_t budget = L.budget;  // even number of 32-bit draws
+  uint32_t *raw = reinterpret_cast<uint32_t *>(ws);
+  int32_t *accepted = reinterpret_cast<int32_t *>(ws + L.off_acc);
   const int nt = 128;
   if (p > 1) {
     const int64_t nout = budget / 2;
@@ -328,8 +483,31 @@ extern "C" int lsspa_perms_pcg64(int p, uint64_t *gen_state, int64_t count, int3
     pcg64_raw_kernel<<<(unsigned)ceil_div(nthreads, nt), nt, 0, st>>>(gen_state, nout, raw);
     LSSPA_LAUNCH_CHECK();
     // `budget` draws come from outputs; a buffered uinteger (if any) adds one more in front
-    pcg64_scan_kernel<<<1, 32, 0, st>>>(p, count, raw, budget, accepted, gen_state, status_flag);
-    LSSPA_LAUNCH_CHECK();
+    static const bool serial = [] {
+      const char *e = getenv("LSSPA_PCG_SCAN");
+      return e && e[0] == 's';
+    }();
+    if (serial) {  // the single-warp walk (A/B timing, debugging)
+      pcg64_scan_kernel<<<1, 32, 0, st>>>(p, count, raw, budget, accepted, gen_state, status_flag);
+      LSSPA_LAUNCH_CHECK();
+    } else {
+      const int steps = (int)L.steps;
+      uint16_t *tab = reinterpret_cast<uint16_t *>(ws + L.off_tab);
+      uint32_t *grp = reinterpret_cast<uint32_t *>(ws + L.off_grp);
+      int64_t *Tg = reinterpret_cast<int64_t *>(ws + L.off_tg);
+      int64_t *cons = reinterpret_cast<int64_t *>(ws + L.off_cons);
+      pcg64_fsm_kernel<<<(unsigned)L.nchunks, 128, 0, st>>>(steps, raw, budget, tab);
+      LSSPA_LAUNCH_CHECK();
+      pcg64_group_kernel<<<(unsigned)L.ngroups, 128, 0, st>>>(steps, L.nchunks, tab, grp);
+      LSSPA_LAUNCH_CHECK();
+      pcg64_prefix_kernel<<<1, 1, 0, st>>>(steps, L.ngroups, grp, Tg, cons);
+      LSSPA_LAUNCH_CHECK();
+      pcg64_emit_kernel<<<(unsigned)L.ngroups, kGroup, 0, st>>>(steps, count * (int64_t)steps, raw, budget, L.nchunks,
+                                                                tab, Tg, accepted, cons);
+      LSSPA_LAUNCH_CHECK();
+      pcg64_finish_kernel<<<1, 1, 0, st>>>(budget, cons, gen_state, status_flag);
+      LSSPA_LAUNCH_CHECK();
+    }
   }
   pcg64_shuffle_kernel<<<(unsigned)ceil_div(count, nt), nt, 0, st>>>(p, count, accepted, perms_out);
   LSSPA_LAUNCH_CHECK();

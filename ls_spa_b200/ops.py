@@ -225,7 +225,7 @@ def perms_pcg64(p: int, gen_state: torch.Tensor, count: int, status_flag: torch.
     ws = torch.empty(nbytes, dtype=torch.uint8, device=gen_state.device)
     check(lib.lsspa_perms_pcg64(p, gen_state.data_ptr(), count, out.data_ptr(), ws.data_ptr(), nbytes,
                                 status_flag.data_ptr(), _stream()), "lsspa_perms_pcg64")
-    _count(3)
+    _count(7)
     return out
 
 
