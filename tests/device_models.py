@@ -108,6 +108,93 @@ def pcg64_scan(p, count, raw, ndraws, gen_state):
     return accepted, flag, max_iters
 
 
+def _fy_accept(d, steps, m):
+    i = steps - m
+    val = d & (0xFFFFFFFF >> (32 - i.bit_length()))
+    return val <= i, val
+
+
+def pcg64_scan_fsm(p, count, raw, ndraws, gen_state, chunk=256, group=64):
+    """pcg64_fsm / group / prefix / emit / finish kernels: the acceptance automaton evaluated by
+    chunks from every start state, chunk maps composed per group, short serial walk over the
+    groups, replay of every chunk from its true start state.  Returns (accepted, flag)."""
+    steps = p - 1
+    total = count * steps
+    nchunks = -(-ndraws // chunk)
+    ngroups = -(-nchunks // group)
+    acc_tab = np.zeros((nchunks, steps), dtype=np.int64)
+    for c in range(nchunks):                       # pcg64_fsm_kernel: block = chunk, thread = start state
+        n0 = c * chunk
+        nvalid = min(chunk, ndraws - n0)
+        for m0 in range(steps):
+            m = m0
+            a = 0
+            for n in range(nvalid):
+                ok, _ = _fy_accept(raw[n0 + n], steps, m)
+                if ok:
+                    a += 1
+                    m = 0 if m + 1 == steps else m + 1
+            acc_tab[c, m0] = a
+    grp_tab = np.zeros((ngroups, steps), dtype=np.int64)
+    for g in range(ngroups):                       # pcg64_group_kernel
+        for m0 in range(steps):
+            m, t = m0, 0
+            for c in range(g * group, min((g + 1) * group, nchunks)):
+                a = int(acc_tab[c, m])
+                t += a
+                m = (m + a) % steps
+            grp_tab[g, m0] = t
+    Tg = [0] * (ngroups + 1)                       # pcg64_prefix_kernel
+    t = 0
+    for g in range(ngroups):
+        Tg[g] = t
+        t += int(grp_tab[g, t % steps])
+    Tg[ngroups] = t
+    consumed = -1
+    accepted = [None] * total
+    for g in range(ngroups):                       # pcg64_emit_kernel: block = group, thread = chunk
+        tc = []
+        t = Tg[g]
+        for k in range(group):
+            tc.append(t)
+            if g * group + k < nchunks:
+                t += int(acc_tab[g * group + k, t % steps])
+        for k in range(group):
+            c = g * group + k
+            if c >= nchunks:
+                continue
+            t = tc[k]
+            if t >= total:
+                continue
+            m = t % steps
+            n0 = c * chunk
+            for n in range(min(chunk, ndraws - n0)):
+                ok, val = _fy_accept(raw[n0 + n], steps, m)
+                if ok:
+                    accepted[t] = val
+                    t += 1
+                    m = 0 if m + 1 == steps else m + 1
+                    if t == total:
+                        consumed = n0 + n + 1
+                        break
+    flag = 0                                       # pcg64_finish_kernel
+    if consumed < 0:
+        flag, consumed = 1, ndraws
+    s0 = (gen_state[0] << 64) | gen_state[1]
+    inc = (gen_state[2] << 64) | gen_state[3]
+    has = bool(gen_state[4])
+    from_outputs = consumed - (1 if (has and consumed > 0) else 0)
+    if consumed > 0:
+        nout = (from_outputs + 1) // 2
+        s = pcg_advance(s0, inc, nout)
+        gen_state[0], gen_state[1] = s >> 64, s & MASK64
+        if from_outputs & 1:
+            gen_state[4], gen_state[5] = 1, pcg_output(s) >> 32
+        else:
+            gen_state[4], gen_state[5] = 0, 0
+    return accepted, flag
+
+
 def pcg64_shuffle(p, count, accepted):
     out = np.empty((count, p), dtype=np.int64)
     for n in range(count):
@@ -119,12 +206,17 @@ def pcg64_shuffle(p, count, accepted):
     return out
 
 
-def pcg64_perms(p, count, gen_state):
-    """Whole lsspa_perms_pcg64 call; gen_state (list of 6 ints) is advanced in place."""
+def pcg64_perms(p, count, gen_state, fsm=False, budget=None):
+    """Whole lsspa_perms_pcg64 call; gen_state (list of 6 ints) is advanced in place.  fsm selects
+    the parallel automaton kernels (the default of the library), else the single-warp walk."""
     if p > 1:
-        budget = raw_budget(p, count)
+        budget = raw_budget(p, count) if budget is None else budget
         raw = pcg64_raw(gen_state, budget // 2)
-        accepted, flag, iters = pcg64_scan(p, count, raw, budget, gen_state)
+        if fsm:
+            accepted, flag = pcg64_scan_fsm(p, count, raw, budget, gen_state)
+            iters = 0
+        else:
+            accepted, flag, iters = pcg64_scan(p, count, raw, budget, gen_state)
         assert flag == 0
     else:
         accepted, iters = [], 0

@@ -30,6 +30,25 @@ def test_pcg64_scan_matches_numpy(p, count):
         assert st[5] == after["uinteger"]
 
 
+@pytest.mark.parametrize("p,count", [(9, 300), (37, 64), (100, 40), (2, 16), (3, 50)])
+def test_pcg64_fsm_scan_matches_numpy(p, count):
+    """The parallel automaton version (pcg64_fsm / group / prefix / emit / finish kernels)."""
+    st = dm.state_from_numpy(42)
+    budget = 2 * (count * 3 * p // 2 + 700)   # several chunks of 256 draws and a partial one
+    got, _ = dm.pcg64_perms(p, count, st, fsm=True, budget=budget)
+    rng = np.random.default_rng(42)
+    want = np.array([rng.permutation(p) for _ in range(count)])
+    assert np.array_equal(got, want)
+    got2, _ = dm.pcg64_perms(p, 7, st, fsm=True)
+    want2 = np.array([rng.permutation(p) for _ in range(7)])
+    assert np.array_equal(got2, want2)
+    after = rng.bit_generator.state
+    assert st[4] == after["has_uint32"]
+    assert ((st[0] << 64) | st[1]) == after["state"]["state"]
+    if st[4]:
+        assert st[5] == after["uinteger"]
+
+
 def test_pcg64_golden_p100_and_p1000():
     g = load_golden("streams")
     st = dm.state_from_numpy(42)
