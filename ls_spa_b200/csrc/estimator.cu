@@ -85,9 +85,11 @@ __device__ __forceinline__ void gauss_pair(uint64_t seed, uint64_t sample, uint3
   z = mix64(z + 0xD1B54A32D192ED03ULL);
   const float u1 = (float)((uint32_t)(z >> 40) + 1u) * 5.9604644775390625e-8f;  // (0,1]
   const float u2 = (float)((uint32_t)z & 0xFFFFFFu) * 5.9604644775390625e-8f;   // [0,1)
-  const float r = sqrtf(-2.0f * logf(u1));
+  // fast intrinsics (MUFU): ~1e-6 relative, far below the Monte-Carlo noise of 1024 draws, and a
+  // third of the instructions of the IEEE-accurate routines (the generator feeds DMMA tiles)
+  const float r = __fsqrt_rn(-2.0f * __logf(u1));
   float s, c;
-  sincospif(2.0f * u2, &s, &c);
+  __sincosf(6.283185307179586f * u2, &s, &c);
   g0 = r * c;
   g1 = r * s;
 }
@@ -389,26 +391,38 @@ __global__ void __launch_bounds__(1024) est_absorb_kernel(double *state, int p, 
   extern __shared__ double smem[];
   double *mrun = smem;                           // (nb+1) x p running means
   double *nrun = mrun + (size_t)(nb + 1) * p;    // nb+1 running counts
+  double *n2s = nrun + (nb + 1);                 // nb batch counts
+  int *slots = reinterpret_cast<int *>(n2s + nb + (nb & 1));  // nb block indices
   StateView st = view_state(state, p);
   const int nxt = cur ^ 1;
   const int tid = threadIdx.x;
   const int f = blockIdx.x;
+  // The folds below are serial in b, but nothing they load depends on the running values: block
+  // indices and counts go to shared memory first, and the loops are unrolled so that the global
+  // loads of several batches are in flight together (they used to be one latency per batch).
+  for (int b = tid; b < nb; b += blockDim.x) {
+    const int sl = slot_map[b];
+    slots[b] = sl;
+    n2s[b] = partials[(size_t)sl * pstride];
+  }
+  for (int j = tid; j < p; j += blockDim.x) mrun[j] = st.mean[cur][j];
+  __syncthreads();
   if (tid == 0) {
     double n = n_before;
     nrun[0] = n;
     for (int b = 0; b < nb; ++b) {
-      n += partials[(size_t)slot_map[b] * pstride];
+      n += n2s[b];
       nrun[b + 1] = n;
     }
   }
-  for (int j = tid; j < p; j += blockDim.x) mrun[j] = st.mean[cur][j];
   __syncthreads();
   for (int j = tid; j < p; j += blockDim.x) {
     double m = mrun[j];
+#pragma unroll 8
     for (int b = 0; b < nb; ++b) {
-      const PartView pv = view_part(partials + (size_t)slot_map[b] * pstride, p);
-      const double n1 = nrun[b], n2 = pv.hdr[0], nn = nrun[b + 1];
-      if (n2 > 0.0) m = (n1 / nn) * m + (n2 / nn) * pv.mean[j];
+      const double pm = partials[(size_t)slots[b] * pstride + kPartHdr + j];
+      const double n1 = nrun[b], n2 = n2s[b], nn = nrun[b + 1];
+      if (n2 > 0.0) m = (n1 / nn) * m + (n2 / nn) * pm;
       mrun[(size_t)(b + 1) * p + j] = m;
     }
   }
@@ -416,13 +430,15 @@ __global__ void __launch_bounds__(1024) est_absorb_kernel(double *state, int p, 
   // ---- covariance row f (biased): Chan merge batch by batch (reference merge_sample_cov)
   for (int j = tid; j < p; j += blockDim.x) {
     double c = st.cov[(size_t)f * p + j];
+#pragma unroll 8
     for (int b = 0; b < nb; ++b) {
-      const PartView pv = view_part(partials + (size_t)slot_map[b] * pstride, p);
-      const double n1 = nrun[b], n2 = pv.hdr[0], nn = nrun[b + 1];
+      const double *blk = partials + (size_t)slots[b] * pstride + kPartHdr;
+      const double pmf = blk[f], pmj = blk[j], pm2 = blk[p + (size_t)f * p + j];
+      const double n1 = nrun[b], n2 = n2s[b], nn = nrun[b + 1];
       if (n2 > 0.0) {
-        const double df = mrun[(size_t)b * p + f] - pv.mean[f];
-        const double dj = mrun[(size_t)b * p + j] - pv.mean[j];
-        c = (n1 / nn) * c + pv.m2[(size_t)f * p + j] / nn + (n1 / nn) * (n2 / nn) * df * dj;
+        const double df = mrun[(size_t)b * p + f] - pmf;
+        const double dj = mrun[(size_t)b * p + j] - pmj;
+        c = (n1 / nn) * c + pm2 / nn + (n1 / nn) * (n2 / nn) * df * dj;
       }
     }
     st.cov[(size_t)f * p + j] = c;
@@ -432,12 +448,15 @@ __global__ void __launch_bounds__(1024) est_absorb_kernel(double *state, int p, 
   if (with_draws) {
     double s = st.S[(size_t)f * kDraws + tid];
     double gr = st.G[cur][tid];
+#pragma unroll 4
     for (int b = 0; b < nb; ++b) {
-      const PartView pv = view_part(partials + (size_t)slot_map[b] * pstride, p);
-      if (pv.hdr[0] > 0.0) {
+      const double *blk = partials + (size_t)slots[b] * pstride + kPartHdr;
+      const double pmf = blk[f];
+      const double g2 = blk[p + (size_t)p * p + tid];
+      const double ps = blk[p + (size_t)p * p + kDraws + (size_t)f * kDraws + tid];
+      if (n2s[b] > 0.0) {
         const double m_old = mrun[(size_t)b * p + f], m_new = mrun[(size_t)(b + 1) * p + f];
-        const double g2 = pv.G[tid];
-        s += (m_old - m_new) * gr + pv.S[(size_t)f * kDraws + tid] + (pv.mean[f] - m_new) * g2;
+        s += (m_old - m_new) * gr + ps + (pmf - m_new) * g2;
         gr += g2;
       }
       if (zsq != nullptr && b >= own0 && b < own1) {
@@ -789,10 +808,11 @@ extern "C" int lsspa_estimator_partials(int p, const double *lifts, const int64_
 }
 
 extern "C" int lsspa_estimator_max_batches(int p) {
-  // running means of all batches of one absorb call live in shared memory: (nb + 1) * (p + 1) doubles
+  // running means, counts and block indices of all batches of one absorb call live in shared
+  // memory: (nb + 1) * (p + 1) + 2 nb + 16 doubles
   const DeviceInfo &d = device_info();
   const size_t limit = (size_t)(d.smem_optin > 0 ? d.smem_optin : 227 * 1024) - 1024;
-  long nb = (long)(limit / ((size_t)(p + 1) * sizeof(double))) - 1;
+  long nb = (long)(limit / ((size_t)(p + 3) * sizeof(double))) - 3;
   if (nb > 4096) nb = 4096;
   return nb < 1 ? 0 : (int)nb;
 }
@@ -803,7 +823,7 @@ extern "C" int lsspa_estimator_absorb(void *state, int p, int cur, double n_befo
   if (!state || !partials || !slot_map || p < 1 || nb < 0 || (cur != 0 && cur != 1)) return LSSPA_E_BADARG;
   if (nb == 0) return LSSPA_OK;
   if (nb > lsspa_estimator_max_batches(p)) return LSSPA_E_UNSUPPORTED;
-  const size_t smem = ((size_t)(nb + 1) * p + (nb + 1) + 8) * sizeof(double);
+  const size_t smem = ((size_t)(nb + 1) * p + (nb + 1) + 2 * (size_t)nb + 16) * sizeof(double);
   LSSPA_CUDA_TRY(cudaFuncSetAttribute(est_absorb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   est_absorb_kernel<<<p, kDraws, smem, as_stream(stream)>>>(reinterpret_cast<double *>(state), p, cur, n_before,
                                                             partials, partial_doubles(p), slot_map, nb, own0,

@@ -518,28 +518,40 @@ __global__ void lift_gram_kernel(int p, const double *__restrict__ R, const doub
 }
 
 // info[0] = |R'|_F |R'^-1|_F (>= cond_2(R')) of the equilibrated factor R' = R D^-1,
-// info[1] = min |R'_kk| / max |R'_kk|.  One CTA; thread j solves R' x = e_j by back substitution
-// (x has j + 1 non-zeros).  inf when R is singular.
-__global__ void lift_cond_kernel(int p, const double *__restrict__ R, const double *__restrict__ D,
-                                 double *__restrict__ info, double *__restrict__ scratch /* p * p */) {
+// info[1] = min |R'_kk| / max |R'_kk|.  One CTA of 32 warps; a warp solves R' x = e_j by back
+// substitution for its columns j (x in shared memory, the row dot products across the lanes).
+// inf when R is singular.
+__global__ void __launch_bounds__(1024) lift_cond_kernel(int p, const double *__restrict__ R,
+                                                         const double *__restrict__ D, double *__restrict__ info) {
+  extern __shared__ double xs[];  // 32 x p
   __shared__ double red[2][32];
   __shared__ double rmin[32], rmax[32];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  double *x = xs + (size_t)w * p;
   double fr = 0.0, fi = 0.0, dmin = 1e300, dmax = 0.0;
-  for (int j = threadIdx.x; j < p; j += blockDim.x) {
-    double *x = scratch + (size_t)j * p;
+  for (int j = w; j < p; j += 32) {
     const double dj = D[j];
     for (int i = j; i >= 0; --i) {
-      double sacc = (i == j) ? 1.0 : 0.0;
-      for (int k = i + 1; k <= j; ++k) sacc = fma(-R[(size_t)k * p + i] / D[k], x[k], sacc);
-      const double v = sacc / (R[(size_t)i * p + i] / D[i]);
-      x[i] = v;
-      fi = fma(v, v, fi);
+      double sacc = 0.0;
+      for (int k = i + 1 + l; k <= j; k += 32) sacc = fma(-R[(size_t)k * p + i] / D[k], x[k], sacc);
+      sacc = warp_sum(sacc);
+      const double v = (sacc + ((i == j) ? 1.0 : 0.0)) / (R[(size_t)i * p + i] / D[i]);
+      __syncwarp();
+      if (l == 0) {
+        x[i] = v;
+        fi = fma(v, v, fi);
+      }
+      __syncwarp();
+    }
+    for (int i = l; i <= j; i += 32) {
       const double r = R[(size_t)j * p + i] / dj;
       fr = fma(r, r, fr);
     }
-    const double d = fabs(R[(size_t)j * p + j] / dj);
-    dmin = fmin(dmin, d);
-    dmax = fmax(dmax, d);
+    if (l == 0) {
+      const double d = fabs(R[(size_t)j * p + j] / dj);
+      dmin = fmin(dmin, d);
+      dmax = fmax(dmax, d);
+    }
   }
   fr = warp_sum(fr);
   fi = warp_sum(fi);
@@ -547,7 +559,6 @@ __global__ void lift_cond_kernel(int p, const double *__restrict__ R, const doub
     dmin = fmin(dmin, __shfl_xor_sync(kFull, dmin, o));
     dmax = fmax(dmax, __shfl_xor_sync(kFull, dmax, o));
   }
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   if (l == 0) {
     red[0][w] = fr;
     red[1][w] = fi;
@@ -556,9 +567,8 @@ __global__ void lift_cond_kernel(int p, const double *__restrict__ R, const doub
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    const int nw = (blockDim.x + 31) / 32;
     double a = 0.0, b = 0.0, mn = 1e300, mx = 0.0;
-    for (int k = 0; k < nw; ++k) {
+    for (int k = 0; k < 32; ++k) {
       a += red[0][k];
       b += red[1][k];
       mn = fmin(mn, rmin[k]);
@@ -589,6 +599,7 @@ extern "C" int64_t lsspa_lifts_gram_doubles(int p) {
 
 extern "C" int lsspa_lifts_gram(int p, const double *R_tr_cm, const double *c_tr, double *gram_out, void *stream) {
   if (p < 1 || !R_tr_cm || !c_tr || !gram_out) return LSSPA_E_BADARG;
+  if (!lifts_chol_supported(p)) return LSSPA_E_UNSUPPORTED;
   cudaStream_t st = as_stream(stream);
   double *info = gram_out + (size_t)(p + 1) * (p + 1);
   double *D = info + 8;
@@ -596,7 +607,9 @@ extern "C" int lsspa_lifts_gram(int p, const double *R_tr_cm, const double *c_tr
   LSSPA_LAUNCH_CHECK();
   lift_gram_kernel<<<p + 1, 128, 0, st>>>(p, R_tr_cm, c_tr, D, gram_out);
   LSSPA_LAUNCH_CHECK();
-  lift_cond_kernel<<<1, 128, 0, st>>>(p, R_tr_cm, D, info, D + p);
+  LSSPA_CUDA_TRY(cudaFuncSetAttribute(lift_cond_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(32 * (size_t)p * sizeof(double))));
+  lift_cond_kernel<<<1, 1024, 32 * (size_t)p * sizeof(double), st>>>(p, R_tr_cm, D, info);
   LSSPA_LAUNCH_CHECK();
   return LSSPA_OK;
 }
