@@ -523,19 +523,25 @@ __global__ void lift_gram_kernel(int p, const double *__restrict__ R, const doub
 // inf when R is singular.
 __global__ void __launch_bounds__(1024) lift_cond_kernel(int p, const double *__restrict__ R,
                                                          const double *__restrict__ D, double *__restrict__ info) {
-  extern __shared__ double xs[];  // 32 x p
+  extern __shared__ double xs[];  // 32 x p solution vectors, then the equilibrated factor (row-major p x p)
   __shared__ double red[2][32];
   __shared__ double rmin[32], rmax[32];
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   double *x = xs + (size_t)w * p;
+  double *Rs = xs + (size_t)32 * p;   // Rs[i * p + k] = R'[i][k] = R[i][k] / D[k]
+  for (int e = threadIdx.x; e < p * p; e += blockDim.x) {
+    const int k = e / p, i = e - k * p;   // R is column-major: element e = R[i][k]
+    Rs[(size_t)i * p + k] = (i <= k) ? R[e] / D[k] : 0.0;
+  }
+  __syncthreads();
   double fr = 0.0, fi = 0.0, dmin = 1e300, dmax = 0.0;
   for (int j = w; j < p; j += 32) {
-    const double dj = D[j];
     for (int i = j; i >= 0; --i) {
+      const double *row = Rs + (size_t)i * p;
       double sacc = 0.0;
-      for (int k = i + 1 + l; k <= j; k += 32) sacc = fma(-R[(size_t)k * p + i] / D[k], x[k], sacc);
+      for (int k = i + 1 + l; k <= j; k += 32) sacc = fma(-row[k], x[k], sacc);
       sacc = warp_sum(sacc);
-      const double v = (sacc + ((i == j) ? 1.0 : 0.0)) / (R[(size_t)i * p + i] / D[i]);
+      const double v = (sacc + ((i == j) ? 1.0 : 0.0)) / row[i];
       __syncwarp();
       if (l == 0) {
         x[i] = v;
@@ -544,11 +550,11 @@ __global__ void __launch_bounds__(1024) lift_cond_kernel(int p, const double *__
       __syncwarp();
     }
     for (int i = l; i <= j; i += 32) {
-      const double r = R[(size_t)j * p + i] / dj;
+      const double r = Rs[(size_t)i * p + j];
       fr = fma(r, r, fr);
     }
     if (l == 0) {
-      const double d = fabs(R[(size_t)j * p + j] / dj);
+      const double d = fabs(Rs[(size_t)j * p + j]);
       dmin = fmin(dmin, d);
       dmax = fmax(dmax, d);
     }
@@ -607,9 +613,9 @@ extern "C" int lsspa_lifts_gram(int p, const double *R_tr_cm, const double *c_tr
   LSSPA_LAUNCH_CHECK();
   lift_gram_kernel<<<p + 1, 128, 0, st>>>(p, R_tr_cm, c_tr, D, gram_out);
   LSSPA_LAUNCH_CHECK();
-  LSSPA_CUDA_TRY(cudaFuncSetAttribute(lift_cond_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(32 * (size_t)p * sizeof(double))));
-  lift_cond_kernel<<<1, 1024, 32 * (size_t)p * sizeof(double), st>>>(p, R_tr_cm, D, info);
+  const size_t cond_smem = ((size_t)32 * p + (size_t)p * p) * sizeof(double);
+  LSSPA_CUDA_TRY(cudaFuncSetAttribute(lift_cond_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cond_smem));
+  lift_cond_kernel<<<1, 1024, cond_smem, st>>>(p, R_tr_cm, D, info);
   LSSPA_LAUNCH_CHECK();
   return LSSPA_OK;
 }
