@@ -144,6 +144,28 @@ def test_lifts_bitwise_reproducible(T):
             np.testing.assert_allclose(base.sum(axis=1), float(g["argsort_anti0_r_squared"]), atol=1e-10)
 
 
+def test_lift_routes_agree_every_width(T):
+    """Every instantiation of the Cholesky lift kernel (p = 49..128: tile geometry is a template
+    parameter) against the Householder kernel, with launch sizes below, at and above the grid."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from quick_bench import synth_problem
+    from ls_spa_b200 import ops, samplers
+    dev = T.device("cuda")
+    for p in range(49, 129):
+        prob = synth_problem(p, dev, seed=p)
+        assert prob.gram is not None
+        for count, anti in ((1, False), (3, True), (301, True)):
+            perms = samplers.ArgsortSource(p, p + count, None, dev).take(count)
+            prob.use_chol = True
+            a = ops.lifts(prob, perms, anti)
+            prob.use_chol = False
+            b = ops.lifts(prob, perms, anti)
+            assert not bool(T.isnan(a).any())
+            err = float((a - b).abs().max() / b.abs().max())
+            assert err < 1e-11, (p, count, anti, err)
+
+
 def test_lift_route_selection(T):
     """The Cholesky route (error ~ eps cond^2) is only taken for well-conditioned train factors;
     both routes agree there for every tile count, and ill-conditioned or singular factors keep
