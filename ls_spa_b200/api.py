@@ -30,6 +30,15 @@ from .samplers import make_source
 _SOURCE_POOL = None
 
 
+def _seed_int(seed) -> int:
+    """Seed of the device's own streams (error-estimate Gaussians).  A numpy Generator handed in as
+    ``seed`` (the permutation stream continues from it) contributes a value derived from its state
+    without consuming from it."""
+    if isinstance(seed, np.random.Generator):
+        return int(seed.bit_generator.state["state"]["state"] & ((1 << 62) - 1))
+    return int(seed)
+
+
 def _source_pool():
     global _SOURCE_POOL
     if _SOURCE_POOL is None:
@@ -209,13 +218,15 @@ def ls_spa(X_train, X_test, y_train, y_test, reg: float = 0.0, method: str | Non
         ready = make_source(meth, p, seed, total, device, perms=perms)
         get_source = lambda: ready
     cfg = engine.JobConfig(p=p, batch_size=bs, max_samples=total, tolerance=float(tolerance),
-                           seed=int(seed), antithetical=anti, estimate_errors=estimate,
+                           seed=_seed_int(seed), antithetical=anti, estimate_errors=estimate,
                            return_history=want_history, penultimate_check=penultimate)
 
     prob = engine.reduce_problem(backend, coll, X_train, X_test, y_train, y_test, float(reg), p,
                                  row_sharded=row_sharded)
     source = get_source()
     res, history, done = engine.run_samples(backend, coll, prob, source, cfg)
+    if getattr(source, "host_generator", None) is not None:
+        source.sync_generator()      # the caller's generator moves past the permutations drawn
     if done == 0 and p >= 9:
         raise ValueError("no permutations were supplied")
     theta, r2 = backend.theta_r2(prob)

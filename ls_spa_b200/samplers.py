@@ -81,10 +81,16 @@ class RandomSource(PermutationSource):
     method = "random"
 
     def __init__(self, p, seed, total, device):
+        """seed: an int (the stream of ``default_rng(seed)``, reference :168) or a numpy
+        ``Generator``: the device stream then continues exactly where that generator stands (the
+        reference's experiment scripts draw data and permutations from one generator); call
+        ``sync_generator`` afterwards to move the host generator past what the device consumed."""
         super().__init__(p, total)
-        st = np.random.default_rng(seed).bit_generator.state
+        self.host_generator = seed if isinstance(seed, np.random.Generator) else None
+        st = (self.host_generator if self.host_generator is not None
+              else np.random.default_rng(seed)).bit_generator.state
         if st["bit_generator"] != "PCG64":
-            raise LsSpaCudaError("numpy default_rng is not PCG64 on this installation")
+            raise LsSpaCudaError("the permutation stream needs a PCG64 bit generator (numpy's default_rng)")
         s, inc = st["state"]["state"], st["state"]["inc"]
         words = [s >> 64, s & _MASK64, inc >> 64, inc & _MASK64, int(st["has_uint32"]), int(st["uinteger"])]
         self.gen_state = _as_i64(words).to(device)
@@ -99,6 +105,17 @@ class RandomSource(PermutationSource):
     def check(self):
         if int(self.flag.item()) != 0:
             raise LsSpaCudaError("PCG64 raw-draw budget exhausted on the device (should not happen)")
+
+    def sync_generator(self, rng=None):
+        """Write the device stream position back into the numpy generator it was started from."""
+        rng = rng if rng is not None else self.host_generator
+        if rng is None:
+            return
+        w = [int(v) & _MASK64 for v in self.gen_state.cpu().tolist()]
+        st = rng.bit_generator.state
+        st["state"]["state"] = (w[0] << 64) | w[1]
+        st["has_uint32"], st["uinteger"] = int(w[4] != 0), int(w[5])
+        rng.bit_generator.state = st
 
 
 class _SobolBacked(PermutationSource):

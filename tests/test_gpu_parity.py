@@ -502,3 +502,43 @@ def test_full_size_properties(T, L):
     assert np.max(np.abs(a.attribution - b.attribution)) < 5 * max(a.overall_error, b.overall_error)
     assert a.error_history.shape == (64,) and b.error_history.shape == (128,)
     assert a.error_history[-1] < a.error_history[0]
+
+
+def test_generator_continuation(T, L):
+    """seed=<numpy Generator>: the device PCG64 stream continues exactly where the host generator
+    stands (the reference's experiment scripts draw data and permutations from one generator), and
+    the host generator ends up where the reference's would."""
+    from oracle import samplers_oracle as so
+    rng = np.random.default_rng(5)
+    p = 24
+    Xtr, Xte, ytr, yte, _, _ = so.gen_data(rng, p, 900, 700)
+    rng.integers(0, 10, 3)                      # leaves a buffered half word behind
+    twin = np.random.default_rng(0)
+    twin.bit_generator.state = rng.bit_generator.state
+    got = L.ls_spa(Xtr, Xte, ytr, yte, max_samples=96, batch_size=16, tolerance=0.0, seed=rng, antithetical=False)
+    perms = [twin.permutation(p) for _ in range(96)]
+    want = L.ls_spa(Xtr, Xte, ytr, yte, perms=perms, batch_size=16, tolerance=0.0, antithetical=False)
+    # same permutations, same lifts; the batch cuts differ by the reference's max_samples - 1 quirk
+    assert scaled_err(got.attribution, want.attribution) < 1e-14
+    a, b = rng.bit_generator.state, twin.bit_generator.state
+    assert a["state"] == b["state"] and a["has_uint32"] == b["has_uint32"]
+    assert not a["has_uint32"] or a["uinteger"] == b["uinteger"]    # stale when no half word is buffered
+    assert np.array_equal(rng.permutation(p), twin.permutation(p))
+    assert np.array_equal(rng.integers(0, 1000, 5), twin.integers(0, 1000, 5))
+
+
+def test_ground_truth_experiment_script(T):
+    """experiments/ground_truth_medium.py on a small shape: the true error of every
+    sampler falls with the number of samples and the antithetic quasi-Monte-Carlo samplers beat
+    plain Monte Carlo at equal cost."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "experiments"))
+    import ground_truth_medium as gtm
+    out = gtm.run(p=20, n=4000, m=3000, gt_log2=14, samples_log2=10, data="device", quiet=True)
+    assert out["ground_truth_error_estimate"] < 2e-3
+    finals = {k: c["final_true_error"] for k, c in out["curves"].items()}
+    for k, c in out["curves"].items():
+        assert all(np.isfinite(c["true_error"])) and c["true_error"][-1] < c["true_error"][0], k
+        assert abs(c["r_squared"] - out["r_squared"]) < 1e-12
+    assert finals["apermutohedron"] < finals["random"] and finals["aargsort"] < finals["random"], finals
+    assert max(finals.values()) < 0.05, finals
