@@ -542,3 +542,17 @@ def test_ground_truth_experiment_script(T):
         assert abs(c["r_squared"] - out["r_squared"]) < 1e-12
     assert finals["apermutohedron"] < finals["random"] and finals["aargsort"] < finals["random"], finals
     assert max(finals.values()) < 0.05, finals
+
+
+def test_naive_comparator_against_device(T, L):
+    """the device path against the naive method on the unreduced data (small N)."""
+    from oracle import naive_oracle as no
+    from oracle import samplers_oracle as so
+    rng = np.random.default_rng(3)
+    p = 12
+    Xtr, Xte, ytr, yte, _, _ = so.gen_data(rng, p, 400, 300)
+    perms = [rng.permutation(p) for _ in range(24)]
+    for reg in (0.0, 1e-2):
+        want = no.naive_attribution(Xtr, Xte, ytr, yte, perms, reg=reg)
+        got = L.ls_spa(Xtr, Xte, ytr, yte, reg=reg, perms=perms, tolerance=0.0, antithetical=False)
+        assert scaled_err(got.attribution, want) < 1e-9, (reg, scaled_err(got.attribution, want))

@@ -116,3 +116,18 @@ def test_online_stats_merge():
     c = lo.merge_sample_cov(b1.mean(0), b2.mean(0), np.cov(b1, rowvar=False, bias=True),
                             np.cov(b2, rowvar=False, bias=True), 2 * n, 3 * n)
     np.testing.assert_almost_equal(c, np.cov(x, rowvar=False, bias=True))
+
+
+@pytest.mark.parametrize("name", ["syn_p10", "syn_p33", "syn_p100_reg"])
+def test_naive_comparator_matches_reference_lifts(name):
+    """the naive method (p full-data least-squares fits per permutation, reference
+    notebooks/medium_experiment.py:251-312) reproduces the reference's own per-permutation lifts
+    stored in the goldens -- an independent check of the reduction trick."""
+    from oracle import naive_oracle as no
+    g = load_golden(name)
+    Xtr, Xte, ytr, yte = regen(g)
+    reg = float(g["reg"])
+    perms = g["perms_random"][:3]
+    for k, perm in enumerate(perms):
+        got = no.naive_lifts(Xtr, Xte, ytr, yte, perm, reg=reg)
+        assert scaled_err(got, g["lifts_random"][k]) < 1e-9, (name, k)
