@@ -478,7 +478,7 @@ int launch_chol(const CholParams &a, int grid, size_t smem, cudaStream_t st) {
 
 template <int RT>
 int launch_chol_rt(const CholParams &a, int grid, size_t smem, cudaStream_t st) {
-  constexpr int MINB = RT <= 13 ? 2 : 1;
+  constexpr int MINB = RT <= 6 ? 3 : (RT <= 13 ? 2 : 1);   // resident CTAs per SM the register budget is cut for
   return (a.pt == RT) ? launch_chol<RT, RT, MINB>(a, grid, smem, st) : launch_chol<RT, RT + 1, MINB>(a, grid, smem, st);
 }
 
@@ -590,7 +590,7 @@ __global__ void __launch_bounds__(1024) lift_cond_kernel(int p, const double *__
 
 extern long long *g_lifts_dbg;  // lifts_mma.cu
 
-bool lifts_chol_supported(int p) { return p >= 49 && p <= 128; }
+bool lifts_chol_supported(int p) { return p >= 17 && p <= 128; }
 
 }  // namespace lsspa
 
@@ -646,11 +646,16 @@ extern "C" int lsspa_lifts_chol(int p, const double *gram, const double *R_te_cm
   const int sms = d.sm_count > 0 ? d.sm_count : 148;
   int per_sm = (int)((227 * 1024) / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
-  if (per_sm > 2) per_sm = 2;
+  const int cap = a.rt <= 6 ? 3 : 2;   // = MINB of the instantiation
+  if (per_sm > cap) per_sm = cap;
   int64_t grid = (int64_t)per_sm * sms;
   if (grid > count) grid = count;
   cudaStream_t st = as_stream(stream);
   switch (a.rt) {
+    case 3: return launch_chol_rt<3>(a, (int)grid, smem, st);
+    case 4: return launch_chol_rt<4>(a, (int)grid, smem, st);
+    case 5: return launch_chol_rt<5>(a, (int)grid, smem, st);
+    case 6: return launch_chol_rt<6>(a, (int)grid, smem, st);
     case 7: return launch_chol_rt<7>(a, (int)grid, smem, st);
     case 8: return launch_chol_rt<8>(a, (int)grid, smem, st);
     case 9: return launch_chol_rt<9>(a, (int)grid, smem, st);
