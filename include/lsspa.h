@@ -137,7 +137,7 @@ LSSPA_API int lsspa_lifts(int p, const double *R_tr_cm, const double *c_tr, cons
                 int antithetical, double *lifts_out, void *workspace, size_t workspace_bytes,
                 void *stream);
 
-/* Fast route of the same function for well-conditioned reduced problems (17 <= p <= 128):
+/* Fast route of the same function for well-conditioned reduced problems (17 <= p <= 152):
  * the triangular factor of R_tr[:, perm] (np.linalg.qr, ls_spa/ls_spa.py:268) is computed as
  * the Cholesky factor of the permuted Gram matrix of [R_tr | c_tr], so the forward error grows
  * like eps * cond(R_tr)^2 instead of eps * cond(R_tr).

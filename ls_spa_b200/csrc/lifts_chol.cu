@@ -262,10 +262,11 @@ __global__ void __launch_bounds__(256, MINB) lifts_chol_kernel(CholParams a) {
       // All loads of a batch of column tiles are issued from valid addresses before the first store
       // and masked afterwards, so they are in flight together.
       {
-        int pr[2][2];
-        bool pv[2][2];
+        constexpr int NRR = (NR + 63) / 64;   // lane -> rows 2 lane + 64 r, r < NRR
+        int pr[NRR][2];
+        bool pv[NRR][2];
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        for (int r = 0; r < NRR; ++r) {
           const int i0 = 2 * lane + 64 * r;
           pv[r][0] = i0 < p;
           pv[r][1] = i0 + 1 < p;
@@ -275,18 +276,19 @@ __global__ void __launch_bounds__(256, MINB) lifts_chol_kernel(CholParams a) {
         constexpr int GB = (PT + 1) / 2;
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
-          double vv[GB][2][2];
+          double vv[GB][NRR][2];
 #pragma unroll
           for (int gg = 0; gg < GB; ++gg) {
             const int g = b * GB + gg;
             if (g < PT) {
               const int l = warp + 8 * g;
               const double *src = a.Gh + (size_t)perm_s[(l <= p) ? l : p] * ldg;
-              vv[gg][0][0] = __ldg(src + pr[0][0]);
-              vv[gg][0][1] = __ldg(src + pr[0][1]);
-              if (8 * g + 8 > 64) {  // compile-time: the column tile reaches below row 64
-                vv[gg][1][0] = __ldg(src + pr[1][0]);
-                vv[gg][1][1] = __ldg(src + pr[1][1]);
+#pragma unroll
+              for (int r = 0; r < NRR; ++r) {
+                if (8 * g + 8 > 64 * r) {  // compile-time: the column tile reaches below row 64 r
+                  vv[gg][r][0] = __ldg(src + pr[r][0]);
+                  vv[gg][r][1] = __ldg(src + pr[r][1]);
+                }
               }
             }
           }
@@ -297,7 +299,7 @@ __global__ void __launch_bounds__(256, MINB) lifts_chol_kernel(CholParams a) {
               const int l = warp + 8 * g;
               const bool colv = l <= p;
 #pragma unroll
-              for (int r = 0; r < 2; ++r) {
+              for (int r = 0; r < NRR; ++r) {
                 const int i0 = 2 * lane + 64 * r;
                 if (64 * r < 8 * g + 8 && i0 < 8 * g + 8 && i0 < NR) {
                   double2 v;
@@ -590,7 +592,7 @@ __global__ void __launch_bounds__(1024) lift_cond_kernel(int p, const double *__
 
 extern long long *g_lifts_dbg;  // lifts_mma.cu
 
-bool lifts_chol_supported(int p) { return p >= 17 && p <= 128; }
+bool lifts_chol_supported(int p) { return p >= 17 && p <= 152; }   // 152: the tile array of 19 row tiles still fits one SM
 
 }  // namespace lsspa
 
@@ -666,6 +668,9 @@ extern "C" int lsspa_lifts_chol(int p, const double *gram, const double *R_te_cm
     case 14: return launch_chol_rt<14>(a, (int)grid, smem, st);
     case 15: return launch_chol_rt<15>(a, (int)grid, smem, st);
     case 16: return launch_chol_rt<16>(a, (int)grid, smem, st);
+    case 17: return launch_chol_rt<17>(a, (int)grid, smem, st);
+    case 18: return launch_chol_rt<18>(a, (int)grid, smem, st);
+    case 19: return launch_chol_rt<19>(a, (int)grid, smem, st);
   }
   return LSSPA_E_UNSUPPORTED;
 }

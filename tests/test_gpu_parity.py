@@ -145,15 +145,15 @@ def test_lifts_bitwise_reproducible(T):
 
 
 def test_lift_routes_agree_every_width(T):
-    """Every instantiation of the Cholesky lift kernel (p = 17..128: tile geometry is a template
-    parameter) against the Householder route (scalar kernel below p = 49, DMMA kernel above), with
+    """Every instantiation of the Cholesky lift kernel (p = 17..152: tile geometry is a template
+    parameter) against the Householder route (DMMA kernel for 49 <= p <= 128, scalar kernel elsewhere), with
     launch sizes below, at and above the grid."""
     import sys, os
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
     from quick_bench import synth_problem
     from ls_spa_b200 import ops, samplers
     dev = T.device("cuda")
-    for p in range(17, 129):
+    for p in range(17, 153):
         prob = synth_problem(p, dev, seed=p)
         assert prob.gram is not None
         for count, anti in ((1, False), (3, True), (301, True)):

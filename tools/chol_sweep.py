@@ -7,7 +7,7 @@ from ls_spa_b200 import ops, samplers
 
 dev = torch.device("cuda")
 worst = 0.0
-for p in range(17, 129):
+for p in range(17, 153):
     prob = synth_problem(p, dev, seed=p)
     for count, anti in ((1, False), (3, True), (301, True), (700, False)):
         perms = samplers.ArgsortSource(p, p + count, None, dev).take(count)
@@ -20,11 +20,11 @@ for p in range(17, 129):
         worst = max(worst, err)
         if err > 1e-11 or bad:
             print("MISMATCH p", p, "count", count, "anti", anti, err, bad, flush=True)
-print("worst scaled difference over p = 17..128:", worst)
+print("worst scaled difference over p = 17..152:", worst)
 from quick_bench import ev_time
-for p in (20, 33, 48):
+for p in (33, 136, 152):
     prob = synth_problem(p, dev, seed=1)
-    perms = samplers.ArgsortSource(p, 3, None, dev).take(1 << 16)
+    perms = samplers.ArgsortSource(p, 3, None, dev).take(1 << 13)
     buf = torch.empty((perms.shape[0], p), dtype=torch.float64, device=dev)
     for name, flag in (("scalar/householder", False), ("chol", True)):
         prob.use_chol = flag
