@@ -269,6 +269,21 @@ def run_gpu(args):
     r = last["e2e"]
     d2h = 8 * (r.attribution.size + r.theta.size + r.attribution_errors.size + r.error_history.size + 2)
 
+    # time to tolerance (the second half of BASELINE.json's metric): the same job, device-resident
+    # inputs, stopped by the error estimate at the reference's default tolerance 1e-2 and at 2e-3
+    # (outside the timed region; every rank runs it, the stop decision is collective)
+    ttt = []
+    for tol in (1e-2, 2e-3):
+        kw_t = dict(kw, tolerance=tol)
+        L.ls_spa(Xtr, Xte, ytr, yte, **kw_t)
+        barrier()
+        t0 = time.perf_counter()
+        rt = L.ls_spa(Xtr, Xte, ytr, yte, **kw_t)
+        barrier()
+        ttt.append({"tolerance": tol, "seconds": time.perf_counter() - t0,
+                    "estimated_error_at_stop": float(rt.overall_error),
+                    "batches": int(rt.error_history.size), "pairs": int(rt.error_history.size) * BATCH})
+
     if rank == 0:
         peaks = read_peaks()
         fp64_peak, fp64_src = fp64_peak_tflops()
@@ -309,6 +324,7 @@ def run_gpu(args):
                                 "unit": "GB/s", "frac": red_bytes / (red_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                                 "peak_source": peaks["which"], "ms": red_ms, "algorithmic_bytes": red_bytes},
             "clocks": clocks,
+            "time_to_tolerance": ttt,
             "result_check": {"sum_attribution_minus_r2": float(abs(last["res"].attribution.sum() - last["res"].r_squared)),
                              "overall_error": float(last["res"].overall_error)},
         }

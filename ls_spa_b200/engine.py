@@ -278,6 +278,11 @@ def run_samples(backend, coll: Collective, prob, source: PermutationSource, cfg:
     bs_eff = cfg.batch_size if cfg.estimate_errors else min(tgt, 1024)
     g_local = max(1, -(-tgt // bs_eff))
     sb_samples = g_local * W * bs_eff
+    # When the job can stop early the super-batches ramp up (2048 samples per rank, doubling to the
+    # full size): a loose tolerance is then reached after little more than the work it needs,
+    # instead of after one full super-batch, at the price of two or three extra (pipelined) rounds.
+    ramp = {"next": 0}
+    g_first = max(1, min(g_local, -(-2048 // bs_eff)))
     est = backend.make_estimator(cfg)
     quirk = (cfg.max_samples - 1) if (cfg.penultimate_check and cfg.max_samples and cfg.estimate_errors) else None
     can_stop = cfg.estimate_errors and cfg.tolerance > 0.0
@@ -289,7 +294,11 @@ def run_samples(backend, coll: Collective, prob, source: PermutationSource, cfg:
     def launch_lifts(pos):
         """Stage A of a super-batch: permutations and lift rows of this rank's run of batches.
         Touches neither the estimator nor the host, so it can be issued one super-batch ahead."""
-        want = sb_samples if limit is None else min(sb_samples, limit - pos)
+        size = sb_samples
+        if cfg.estimate_errors and cfg.tolerance > 0.0:
+            size = min(sb_samples, (g_first << ramp["next"]) * W * bs_eff)
+            ramp["next"] = min(ramp["next"] + 1, 30)
+        want = size if limit is None else min(size, limit - pos)
         perms_all = None
         if not source.random_access:
             perms_all = source.take(want)        # sequential stream: every rank walks it
