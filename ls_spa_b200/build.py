@@ -45,13 +45,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
     nvcc = find_nvcc()
-    objs = []
-    for src in SOURCES:
+    def compile_one(src):
         obj = os.path.join(LIB_DIR, src.replace(".cu", ".o"))
         cmd = [nvcc, *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-I", CSRC,
                "-Xptxas", "-v" if verbose else "-warn-spills",
                "-c", os.path.join(CSRC, src), "-o", obj]
         res = subprocess.run(cmd, capture_output=True, text=True)
+        return src, obj, res
+
+    # the translation units are independent: compile them side by side (lifts_chol.cu alone holds
+    # 34 instantiations of the hot kernel and takes over a minute)
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    objs = []
+    for src, obj, res in results:
         if verbose or res.returncode != 0:
             sys.stderr.write(res.stdout + res.stderr)
         if res.returncode != 0:
