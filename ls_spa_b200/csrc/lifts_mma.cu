@@ -2,13 +2,15 @@
 // tcgen05 has no fp64, so this is the tensor path the FP64 pipe offers).
 //
 // Replaces square_shapley (reference ls_spa/ls_spa.py:256-287) and the antithetic pair average
-// (:205-208) for 9 <= p <= 128.  Same mathematics as lifts.cu, reorganised so that almost all
+// (:205-208) for 49 <= p <= 128, any conditioning (the Householder route; well-conditioned problems
+// take lifts_chol.cu).  Same mathematics as lifts.cu, reorganised so that almost all
 // flops are 8x8x4 matrix products and the number of block-wide barriers drops from 2p to 2p/8:
 //
 //  phase 1  blocked Householder QR of A = [R_tr[:, perm] | c_tr] (shared memory, column-major,
-//           ld % 16 == 8).  Per panel of 8 columns: warp 0 factors the panel in registers
-//           (reflectors V, compact-WY factor T from G = V^T V), then every warp takes whole
-//           trailing column tiles:  W^T = (A2^T V) T  and  A2^T -= W^T V^T, all DMMA.
+//           ld % 16 == 8).  Per panel of 8 columns: four warps factor the panel cooperatively in
+//           registers (reflectors V, compact-WY factor T from G = V^T V) one panel ahead, while
+//           the other four take whole trailing column tiles:  W^T = (A2^T V) T  and
+//           A2^T -= W^T V^T, all DMMA.
 //  phase 2  elimination of X = R_te[:, perm] against the rows of R, one warp per 8-row tile of
 //           X held entirely in registers (rows of X are independent):  M_J = X_J R_JJ^-1,
 //           X_L -= M_J R_JL.  The multipliers M are the columns of W = X R^-1 (reference :279),
@@ -63,198 +65,6 @@ constexpr int kVS = 10;  // row stride (doubles) of the row-major V buffers: row
 __device__ __forceinline__ double2 ld_vfrag(const double *V, int r0, int c, int q) {
   const double *ptr = V + (size_t)(r0 + 2 * q) * kVS + c;
   return make_double2(ptr[0], ptr[kVS]);
-}
-
-// ---------------------------------------------------------------- panel factorisation (one warp)
-// Strip = column tile s, row tiles s..RT-1, held in registers relative to the top tile
-// (vr[k] = tile s+k, k < KT).  KT is a compile-time bound >= nt = RT - s: tiles k >= nt are kept
-// identically zero (registers and scratch), so the arithmetic loops carry no per-tile guard
-// (a guarded `k < nt` loop costs ~2x the instructions); the kernel picks the smallest KT variant.
-// Reflectors are kept UNNORMALISED: H = I - tt u u^T with u = x - beta e1, tt = -1 / (beta u1), so
-// no scaling pass is needed; u is broadcast to the other columns through a contiguous scratch
-// column (16-byte accesses) and the norm of the next column is accumulated while the current
-// reflector is applied.  Outputs: R (top tile) back to A, U row-major into V[row][0..7] (explicit
-// zeros above the diagonal), compact-WY factor T (column-major 8x8) in Tb.
-template <int KT>
-__device__ __noinline__ void panel_factor(double *A, double *V, double *Tb, double *Gs, double *vs, int ld,
-                                          int p, int RT, int s, int lane) {
-  const int c = lane >> 2, q = lane & 3;
-  const int j0 = 8 * s;
-  const int nf = (p - j0 < 8) ? p - j0 : 8;
-  const int nt = RT - s;  // tiles in the strip, 1 <= nt <= KT
-  const int r0 = 8 * s;
-  const int l0 = 2 * q, l1 = 2 * q + 1;
-  double vr[KT][2];
-  double na = 0.0, nb = 0.0;  // |own column below own pivot row c|^2, partial over this lane's rows
-  const double *Acol = A + (size_t)(j0 + c) * ld + r0 + 2 * q;
-#pragma unroll
-  for (int k = 0; k < KT; ++k) {
-    double2 v = make_double2(0.0, 0.0);
-    if (k < nt) v = *reinterpret_cast<const double2 *>(Acol + 8 * k);
-    vr[k][0] = v.x;
-    vr[k][1] = v.y;
-    if (k > 0) {
-      na = fma(v.x, v.x, na);
-      nb = fma(v.y, v.y, nb);
-    } else {
-      if (l0 > c) na = v.x * v.x;
-      if (l1 > c) nb = v.y * v.y;
-    }
-  }
-  double tau_r[8];
-  double dg = 0.0, du = 0.0;  // beta (diagonal of R) and u1 of this lane's column
-  double2 *vs2 = reinterpret_cast<double2 *>(vs) + q;
-#pragma unroll
-  for (int cc = 0; cc < 8; ++cc) {
-    tau_r[cc] = 0.0;
-    if (cc < nf) {
-      const double sig = __shfl_sync(kFull, quad_sum(na + nb), 4 * cc);
-      const double pv = (cc & 1) ? vr[0][1] : vr[0][0];
-      const double x0 = __shfl_sync(kFull, pv, 4 * cc + (cc >> 1));
-      if (sig > kTinySig) {  // warp-uniform
-        const double nrm = sqrt(fma(x0, x0, sig));
-        const double beta = (x0 >= 0.0) ? -nrm : nrm;
-        const double u1 = x0 - beta;
-        const double tt = -1.0 / (beta * u1);
-        tau_r[cc] = tt;
-        if (c == cc) {
-          dg = beta;
-          du = u1;
-          // publish u: zeros above the pivot, u1 on it, the raw entries below
-          vs2[0] = make_double2((l0 < cc) ? 0.0 : ((l0 == cc) ? u1 : vr[0][0]),
-                                (l1 < cc) ? 0.0 : ((l1 == cc) ? u1 : vr[0][1]));
-#pragma unroll
-          for (int k = 1; k < KT; ++k) vs2[4 * k] = make_double2(vr[k][0], vr[k][1]);
-        }
-        __syncwarp();
-        double wa = 0.0, wb = 0.0, wc = 0.0, wd = 0.0;
-#pragma unroll
-        for (int k = 0; k < KT; ++k) {
-          const double2 u = vs2[4 * k];
-          if (k & 1) {
-            wc = fma(u.x, vr[k][0], wc);
-            wd = fma(u.y, vr[k][1], wd);
-          } else {
-            wa = fma(u.x, vr[k][0], wa);
-            wb = fma(u.y, vr[k][1], wb);
-          }
-        }
-        const double w = quad_sum((wa + wb) + (wc + wd)) * tt;
-        if (c > cc) {
-          double nc = 0.0, nd = 0.0;
-          na = 0.0;
-          nb = 0.0;
-#pragma unroll
-          for (int k = 0; k < KT; ++k) {
-            const double2 u = vs2[4 * k];
-            vr[k][0] = fma(-w, u.x, vr[k][0]);
-            vr[k][1] = fma(-w, u.y, vr[k][1]);
-            if (k == 0) {
-              if (l0 > c) na = vr[0][0] * vr[0][0];
-              if (l1 > c) nb = vr[0][1] * vr[0][1];
-            } else if (k & 1) {
-              nc = fma(vr[k][0], vr[k][0], nc);
-              nd = fma(vr[k][1], vr[k][1], nd);
-            } else {
-              na = fma(vr[k][0], vr[k][0], na);
-              nb = fma(vr[k][1], vr[k][1], nb);
-            }
-          }
-          na += nc;
-          nb += nd;
-        }
-        __syncwarp();
-      } else if (c == cc) {
-        dg = x0;  // column already zero below the pivot: H = I
-        du = 0.0;
-      }
-    }
-  }
-  // U (row-major) for the trailing updates and R / untouched columns back to A
-  {
-    const bool refl = (c < nf) && (du != 0.0);
-    const bool fact = c < nf;
-    double *Vc = V + (size_t)(r0 + l0) * kVS + c;
-    double *Aw = A + (size_t)(j0 + c) * ld + r0 + 2 * q;
-    Vc[0] = refl ? ((l0 < c) ? 0.0 : ((l0 == c) ? du : vr[0][0])) : 0.0;
-    Vc[kVS] = refl ? ((l1 < c) ? 0.0 : ((l1 == c) ? du : vr[0][1])) : 0.0;
-    double2 v = make_double2(vr[0][0], vr[0][1]);
-    if (fact) {
-      v.x = (l0 < c) ? vr[0][0] : ((l0 == c) ? dg : 0.0);
-      v.y = (l1 < c) ? vr[0][1] : ((l1 == c) ? dg : 0.0);
-    }
-    *reinterpret_cast<double2 *>(Aw) = v;
-#pragma unroll
-    for (int k = 1; k < KT; ++k) {
-      if (k < nt) {
-        Vc[(size_t)8 * k * kVS] = refl ? vr[k][0] : 0.0;
-        Vc[(size_t)8 * k * kVS + kVS] = refl ? vr[k][1] : 0.0;
-        *reinterpret_cast<double2 *>(Aw + 8 * k) =
-            fact ? make_double2(0.0, 0.0) : make_double2(vr[k][0], vr[k][1]);
-      }
-    }
-  }
-  __syncwarp();
-  // G = U^T U: the same fragment is the A operand (U^T) and the B operand (U)
-  double ga0 = 0.0, ga1 = 0.0, gb0 = 0.0, gb1 = 0.0;
-  {
-    const double *Vf = V + (size_t)(r0 + 2 * q) * kVS + c;
-#pragma unroll
-    for (int k = 0; k < KT; ++k) {
-      if (k < nt) {
-        const double vx = Vf[(size_t)8 * k * kVS];
-        const double vy = Vf[(size_t)8 * k * kVS + kVS];
-        if (k & 1) {
-          dmma(gb0, gb1, vx, vx);
-          dmma(gb0, gb1, vy, vy);
-        } else {
-          dmma(ga0, ga1, vx, vx);
-          dmma(ga0, ga1, vy, vy);
-        }
-      }
-    }
-  }
-  *reinterpret_cast<double2 *>(Gs + c * 8 + 2 * q) = make_double2(ga0 + gb0, ga1 + gb1);  // Gs[m][n] row-major
-  __syncwarp();
-  // T (dlarft, forward / columnwise): lane u owns row u; stored column-major for ld_tile
-  if (lane < 8) {
-    const int u = lane;
-    double tr[8];
-#pragma unroll
-    for (int cc = 0; cc < 8; ++cc) {
-      double val = 0.0;
-      if (cc == u) {
-        val = tau_r[cc];
-      } else if (cc > u) {
-        double acc = 0.0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          if (k >= u && k < cc) acc = fma(tr[k], Gs[k * 8 + cc], acc);
-        val = -tau_r[cc] * acc;
-      }
-      tr[cc] = val;
-      Tb[cc * 8 + u] = val;
-    }
-  }
-  __syncwarp();
-}
-
-// smallest compiled strip height that holds nt tiles
-template <int MAXT>
-__device__ __forceinline__ void panel_dispatch(double *A, double *V, double *Tb, double *Gs, double *vs, int ld,
-                                               int p, int RT, int s, int lane) {
-  const int nt = RT - s;
-  if (MAXT > 10 && nt > 10) {
-    panel_factor<MAXT>(A, V, Tb, Gs, vs, ld, p, RT, s, lane);
-  } else if (MAXT > 7 && nt > 7) {
-    panel_factor<(MAXT < 10 ? MAXT : 10)>(A, V, Tb, Gs, vs, ld, p, RT, s, lane);
-  } else if (MAXT > 4 && nt > 4) {
-    panel_factor<(MAXT < 7 ? MAXT : 7)>(A, V, Tb, Gs, vs, ld, p, RT, s, lane);
-  } else if (nt > 2) {
-    panel_factor<(MAXT < 4 ? MAXT : 4)>(A, V, Tb, Gs, vs, ld, p, RT, s, lane);
-  } else {
-    panel_factor<2>(A, V, Tb, Gs, vs, ld, p, RT, s, lane);
-  }
 }
 
 // ---------------------------------------------------------------- trailing column tile j
