@@ -160,6 +160,18 @@ LSSPA_API int lsspa_lifts_chol(int p, const double *gram, const double *R_te_cm,
                      double y_norm_sq, const int32_t *perms, int64_t count, int antithetical,
                      double *lifts_out, void *stream);
 
+/* The same route in two launches (49 <= p <= 128), for jobs whose inputs arrive over PCIe: the
+ * factorisation of R_tr[:, perm] (np.linalg.qr, ls_spa/ls_spa.py:268-270) needs the train side
+ * only, so it can run while the test rows are still being copied; the elimination against the
+ * test factor (:279-283) follows.  factors: lsspa_lifts_chol_factor_doubles(p) doubles per
+ * permutation evaluation (count, or 2 * count with antithetical != 0: perm and its reverse). */
+LSSPA_API int64_t lsspa_lifts_chol_factor_doubles(int p);
+LSSPA_API int lsspa_lifts_chol_factor(int p, const double *gram, const int32_t *perms, int64_t count,
+                            int antithetical, double *factors_out, void *stream);
+LSSPA_API int lsspa_lifts_chol_eliminate(int p, const double *factors, const double *R_te_cm,
+                               const double *c_te, double y_norm_sq, const int32_t *perms,
+                               int64_t count, int antithetical, double *lifts_out, void *stream);
+
 /* ------------------------------------------------------------------------
  * 4. Estimator                        replaces ls_spa/ls_spa.py:186-236
  *    (merge_sample_mean/cov :103-119, error_estimates :321-341, stop test :229).

@@ -45,6 +45,9 @@ SIGNATURES = {
     "lsspa_lifts_gram_doubles": (c_i64, [c_i32]),
     "lsspa_lifts_gram": (c_i32, [c_i32, vp, vp, vp, vp]),
     "lsspa_lifts_chol": (c_i32, [c_i32, vp, vp, vp, c_f64, vp, c_i64, c_i32, vp, vp]),
+    "lsspa_lifts_chol_factor_doubles": (c_i64, [c_i32]),
+    "lsspa_lifts_chol_factor": (c_i32, [c_i32, vp, vp, c_i64, c_i32, vp, vp]),
+    "lsspa_lifts_chol_eliminate": (c_i32, [c_i32, vp, vp, vp, c_f64, vp, c_i64, c_i32, vp, vp]),
     "lsspa_estimator_state_bytes": (sz, [c_i32]),
     "lsspa_estimator_partial_doubles": (c_i64, [c_i32]),
     "lsspa_estimator_max_batches": (c_i32, [c_i32]),

@@ -18,6 +18,7 @@ device the calls raise ``LsSpaCudaError`` (there is no CPU fallback).
 
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -221,10 +222,17 @@ def ls_spa(X_train, X_test, y_train, y_test, reg: float = 0.0, method: str | Non
                            seed=_seed_int(seed), antithetical=anti, estimate_errors=estimate,
                            return_history=want_history, penultimate_check=penultimate)
 
+    # Host-resident test rows, single process, device permutation source, bounded job: factor the
+    # permutations of the first super-batches (train side only) while the test rows cross PCIe.
+    pre = None
+    test_on_host = not (isinstance(X_test, torch.Tensor) and X_test.is_cuda)
+    if (coll.world == 1 and test_on_host and perms is None and meth != "exact" and total is not None
+            and ops.split_route_supported(p) and os.environ.get("LSSPA_SPLIT_ROUTE", "1") != "0"):
+        pre = engine.Prefactor(backend, cfg, get_source, 8 * int(X_test.shape[0]) * (p + 1))
     prob = engine.reduce_problem(backend, coll, X_train, X_test, y_train, y_test, float(reg), p,
-                                 row_sharded=row_sharded)
-    source = get_source()
-    res, history, done = engine.run_samples(backend, coll, prob, source, cfg)
+                                 row_sharded=row_sharded, prefactor=pre)
+    source = pre.source if (pre is not None and pre.source is not None) else get_source()
+    res, history, done = engine.run_samples(backend, coll, prob, source, cfg, pre=pre)
     if getattr(source, "host_generator", None) is not None:
         source.sync_generator()      # the caller's generator moves past the permutations drawn
     if done == 0 and p >= 9:

@@ -35,6 +35,7 @@ struct CholParams {
   int64_t count;
   int anti;
   double *out;
+  double *fact;        // split route: per-evaluation factors (R upper tiles, c, inverses of the diagonal blocks)
   long long *dbg;  // optional cycle counters of block 0 (development aid), else nullptr
 };
 
@@ -230,7 +231,17 @@ __host__ __device__ constexpr int chol_ld(int rt) { return ((8 * rt) % 16 == 8) 
 
 // The tile geometry (RT row tiles, PT = RT or RT + 1 column tiles) is a template parameter: every
 // tile address is then base + immediate and no tile loop carries a run-time guard.
-template <int RT, int PT, int MINB>
+// MODE 0: the whole evaluation (factor + eliminate, fused).  MODE 1: factor only -- needs only the
+// train side; R (upper tiles, with c) and the inverses of its diagonal blocks go to a.fact.
+// MODE 2: eliminate only -- loads them back and runs phase 2 against the test factor.  The split
+// lets the factorisations of a host-resident job run while the test rows are still crossing PCIe.
+__host__ __device__ constexpr int64_t chol_fact_doubles(int rt, int pt) {
+  int64_t t = 0;
+  for (int L = 0; L < pt; ++L) t += (L < rt ? L : rt - 1) + 1;
+  return 64 * t + 64 * rt;
+}
+
+template <int RT, int PT, int MINB, int MODE>
 __global__ void __launch_bounds__(256, MINB) lifts_chol_kernel(CholParams a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int p = a.p;
@@ -257,68 +268,99 @@ __global__ void __launch_bounds__(256, MINB) lifts_chol_kernel(CholParams a) {
         perm_s[k] = (k == p) ? p : a.perms[sidx * p + (h == 0 ? k : p - 1 - k)];
       __syncthreads();
       const long long t_a = clock64();
+      constexpr int64_t FD = chol_fact_doubles(RT, PT);
+      const int64_t eval = sidx * halves + h;
+      if constexpr (MODE == 2) {
+        // ---- phase 0 (split route): R, c and the diagonal inverses of this evaluation from global
+        // (tile column L holds 8 columns of 8 (min(L, RT-1) + 1) rows; every bound below is a
+        // compile-time constant after unrolling, and all loads are issued before the first use)
+        const double2 *src = reinterpret_cast<const double2 *>(a.fact + eval * FD);
+#pragma unroll
+        for (int L = 0; L < PT; ++L) {
+          const int nrow2 = 4 * ((L < RT ? L : RT - 1) + 1);   // double2 per column
+          int off2 = 0;
+#pragma unroll
+          for (int k = 0; k < L; ++k) off2 += 32 * ((k < RT ? k : RT - 1) + 1);
+#pragma unroll
+          for (int e0 = 0; e0 < 8 * nrow2; e0 += 256) {
+            const int e = e0 + tid;
+            if (e < 8 * nrow2) {
+              const int cc = e / nrow2, r2 = e - cc * nrow2;
+              *reinterpret_cast<double2 *>(A + (size_t)(8 * L + cc) * ld + 2 * r2) = __ldg(src + off2 + e);
+            }
+          }
+        }
+#pragma unroll
+        for (int e0 = 0; e0 < 32 * RT; e0 += 256) {
+          const int e = e0 + tid;
+          if (e < 32 * RT) reinterpret_cast<double2 *>(Dbuf)[e] = __ldg(src + (FD - 64 * RT) / 2 + e);
+        }
+      } else {
       // ---- phase 0: gather the upper tiles of Gh[pi^, pi^] (rows < p, columns <= p), zero padding.
-      // Warp w takes the columns l = w + 8 g (column tile g); lane -> rows 2 lane, 2 lane + 1 (+ 64).
-      // All loads of a batch of column tiles are issued from valid addresses before the first store
-      // and masked afterwards, so they are in flight together.
-      {
-        constexpr int NRR = (NR + 63) / 64;   // lane -> rows 2 lane + 64 r, r < NRR
-        int pr[NRR][2];
-        bool pv[NRR][2];
+        // Warp w takes the columns l = w + 8 g (column tile g); lane -> rows 2 lane, 2 lane + 1 (+ 64).
+        // All loads of a batch of column tiles are issued from valid addresses before the first store
+        // and masked afterwards, so they are in flight together.
+        {
+          constexpr int NRR = (NR + 63) / 64;   // lane -> rows 2 lane + 64 r, r < NRR
+          int pr[NRR][2];
+          bool pv[NRR][2];
 #pragma unroll
-        for (int r = 0; r < NRR; ++r) {
-          const int i0 = 2 * lane + 64 * r;
-          pv[r][0] = i0 < p;
-          pv[r][1] = i0 + 1 < p;
-          pr[r][0] = pv[r][0] ? perm_s[i0] : 0;
-          pr[r][1] = pv[r][1] ? perm_s[i0 + 1] : 0;
-        }
-        constexpr int GB = (PT + 1) / 2;
+          for (int r = 0; r < NRR; ++r) {
+            const int i0 = 2 * lane + 64 * r;
+            pv[r][0] = i0 < p;
+            pv[r][1] = i0 + 1 < p;
+            pr[r][0] = pv[r][0] ? perm_s[i0] : 0;
+            pr[r][1] = pv[r][1] ? perm_s[i0 + 1] : 0;
+          }
+          constexpr int GB = (PT + 1) / 2;
 #pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          double vv[GB][NRR][2];
+          for (int b = 0; b < 2; ++b) {
+            double vv[GB][NRR][2];
 #pragma unroll
-          for (int gg = 0; gg < GB; ++gg) {
-            const int g = b * GB + gg;
-            if (g < PT) {
-              const int l = warp + 8 * g;
-              const double *src = a.Gh + (size_t)perm_s[(l <= p) ? l : p] * ldg;
+            for (int gg = 0; gg < GB; ++gg) {
+              const int g = b * GB + gg;
+              if (g < PT) {
+                const int l = warp + 8 * g;
+                const double *src = a.Gh + (size_t)perm_s[(l <= p) ? l : p] * ldg;
 #pragma unroll
-              for (int r = 0; r < NRR; ++r) {
-                if (8 * g + 8 > 64 * r) {  // compile-time: the column tile reaches below row 64 r
-                  vv[gg][r][0] = __ldg(src + pr[r][0]);
-                  vv[gg][r][1] = __ldg(src + pr[r][1]);
+                for (int r = 0; r < NRR; ++r) {
+                  if (8 * g + 8 > 64 * r) {  // compile-time: the column tile reaches below row 64 r
+                    vv[gg][r][0] = __ldg(src + pr[r][0]);
+                    vv[gg][r][1] = __ldg(src + pr[r][1]);
+                  }
                 }
               }
             }
-          }
 #pragma unroll
-          for (int gg = 0; gg < GB; ++gg) {
-            const int g = b * GB + gg;
-            if (g < PT) {
-              const int l = warp + 8 * g;
-              const bool colv = l <= p;
+            for (int gg = 0; gg < GB; ++gg) {
+              const int g = b * GB + gg;
+              if (g < PT) {
+                const int l = warp + 8 * g;
+                const bool colv = l <= p;
 #pragma unroll
-              for (int r = 0; r < NRR; ++r) {
-                const int i0 = 2 * lane + 64 * r;
-                if (64 * r < 8 * g + 8 && i0 < 8 * g + 8 && i0 < NR) {
-                  double2 v;
-                  v.x = (colv && pv[r][0]) ? vv[gg][r][0] : 0.0;
-                  v.y = (colv && pv[r][1]) ? vv[gg][r][1] : 0.0;
-                  *reinterpret_cast<double2 *>(A + (size_t)l * ld + i0) = v;
+                for (int r = 0; r < NRR; ++r) {
+                  const int i0 = 2 * lane + 64 * r;
+                  if (64 * r < 8 * g + 8 && i0 < 8 * g + 8 && i0 < NR) {
+                    double2 v;
+                    v.x = (colv && pv[r][0]) ? vv[gg][r][0] : 0.0;
+                    v.y = (colv && pv[r][1]) ? vv[gg][r][1] : 0.0;
+                    *reinterpret_cast<double2 *>(A + (size_t)l * ld + i0) = v;
+                  }
                 }
               }
             }
           }
         }
       }
-      if (warp == 7) {
-        double s0 = 0.0;
-        for (int i = lane; i < p; i += 32) s0 = fma(a.cte[i], a.cte[i], s0);
-        s0 = warp_sum(s0);
-        if (lane == 0) cost[0] = s0;
+      if constexpr (MODE != 1) {
+        if (warp == 7) {
+          double s0 = 0.0;
+          for (int i = lane; i < p; i += 32) s0 = fma(a.cte[i], a.cte[i], s0);
+          s0 = warp_sum(s0);
+          if (lane == 0) cost[0] = s0;
+        }
+        for (int e = tid; e < 8 * NR; e += 256) wcost[e] = 0.0;
       }
-      for (int e = tid; e < 8 * NR; e += 256) wcost[e] = 0.0;
       __syncthreads();
 
       const long long t_b = clock64();
@@ -338,94 +380,122 @@ __global__ void __launch_bounds__(256, MINB) lifts_chol_kernel(CholParams a) {
       const double *cvec = A + (size_t)p * ld;
       double xr[RT][2];
       double r_in = 0.0;
-      constexpr int NF = (RT - 8 < 0) ? 0 : (RT - 8 > 6 ? 6 : RT - 8);  // fused tiles: the rest is one round of 8
+      constexpr int NF = (MODE != 0 || RT - 8 < 0) ? 0 : (RT - 8 > 6 ? 6 : RT - 8);  // fused tiles: the rest is one round of 8
       // fused warps: 7, 6, 5, 3, 2, 1 in that order -- never warp 4, which issues on the same SM
       // sub-partition as the diagonal chain of warp 0 (measured: 3 % faster than warps 3..7)
       const int frank = (warp == 0 || warp == 4) ? 99 : (warp > 4 ? 7 - warp : 6 - warp);
       const bool fused = frank < NF;
       if (fused) load_x<RT>(xr, r_in, a, perm_s, frank, p, c, q);
-      double2 tv[NSL];
+      if constexpr (MODE != 2) {
+        double2 tv[NSL];
 #pragma unroll
-      for (int sl = 0; sl < NSL; ++sl) {
-        const int L = warp + 7 * sl;  // row block 0
-        tv[sl] = make_double2(0.0, 0.0);
-        if (warp != 0 && L < PT) tv[sl] = ld_tile(A, ld, 0, 8 * L, c, q);
-      }
-      for (int s = 0; s < RT; ++s) {
-        const int nf = (p - 8 * s < 8) ? p - 8 * s : 8;
-        const long long u0 = clock64();
-        double2 tvn[NSL];
-        if (warp == 0) {
-          double2 t = ld_tile(A, ld, 8 * s, 8 * s, c, q);
-          if (s > 0) {
-            const double2 xa = ld_tile(A, ld, 8 * (s - 1), 8 * s, c, q);
-            double p0 = 0.0, p1 = 0.0, e0 = 0.0, e1 = 0.0;
-            dmma(p0, p1, xa.x, xa.x);
-            dmma(e0, e1, xa.y, xa.y);
-            t.x -= p0 + e0;
-            t.y -= p1 + e1;
-          }
-          double y0, y1;
-          diag_factor(t.x, t.y, y0, y1, nf, lane);
-          st_tile(A, ld, 8 * s, 8 * s, c, q, t);
-          *reinterpret_cast<double2 *>(Dbuf + s * 64 + c * 8 + 2 * q) = make_double2(y0, y1);
-        } else if (s + 1 < RT) {
-#pragma unroll
-          for (int sl = 0; sl < NSL; ++sl) {
-            const int L = s + 1 + warp + 7 * sl;
-            tvn[sl] = make_double2(0.0, 0.0);
-            if (L < PT) {
-              const double2 g = ld_tile(A, ld, 8 * (s + 1), 8 * L, c, q);
-              const double2 z = acc_tile<ld>(A, s, L, s + 1, c, q);
-              tvn[sl] = make_double2(g.x - z.x, g.y - z.y);
-            }
-          }
-          if (warp == 1 + (s + 1) % 7 && s > 0) {
-            const double2 g = ld_tile(A, ld, 8 * (s + 1), 8 * (s + 1), c, q);
-            const double2 z = acc_tile<ld>(A, s, s + 1, s + 1, c, q);
-            st_tile(A, ld, 8 * (s + 1), 8 * (s + 1), c, q, make_double2(g.x - z.x, g.y - z.y));
-          }
+        for (int sl = 0; sl < NSL; ++sl) {
+          const int L = warp + 7 * sl;  // row block 0
+          tv[sl] = make_double2(0.0, 0.0);
+          if (warp != 0 && L < PT) tv[sl] = ld_tile(A, ld, 0, 8 * L, c, q);
         }
-        const long long u1 = clock64();
-        t_acc += u1 - u0;
-        __syncthreads();
-        const long long u2 = clock64();
-        t_wait += u2 - u1;
-        if (warp != 0) {
-          const double2 dv = ld_tile(Dbuf + s * 64, 8, 0, 0, c, q);
-#pragma unroll
-          for (int sl = 0; sl < NSL; ++sl) {
-            const int L = s + warp + 7 * sl;
-            if (L < PT) {
-              double r0 = 0.0, r1 = 0.0;
-              dmma(r0, r1, tv[sl].x, dv.x);
-              dmma(r0, r1, tv[sl].y, dv.y);
-              st_tile(A, ld, 8 * s, 8 * L, c, q, make_double2(r0, r1));
-            }
-          }
-        }
-        __syncthreads();
-        if (warp != 0 && s + 1 < RT) {
-#pragma unroll
-          for (int sl = 0; sl < NSL; ++sl) {
-            const int L = s + 1 + warp + 7 * sl;
-            tv[sl] = tvn[sl];
-            if (L < PT) {
-              const double2 xa = ld_tile(A, ld, 8 * s, 8 * L, c, q);
-              const double2 xb = ld_tile(A, ld, 8 * s, 8 * (s + 1), c, q);
+        for (int s = 0; s < RT; ++s) {
+          const int nf = (p - 8 * s < 8) ? p - 8 * s : 8;
+          const long long u0 = clock64();
+          double2 tvn[NSL];
+          if (warp == 0) {
+            double2 t = ld_tile(A, ld, 8 * s, 8 * s, c, q);
+            if (s > 0) {
+              const double2 xa = ld_tile(A, ld, 8 * (s - 1), 8 * s, c, q);
               double p0 = 0.0, p1 = 0.0, e0 = 0.0, e1 = 0.0;
-              dmma(p0, p1, xa.x, xb.x);
-              dmma(e0, e1, xa.y, xb.y);
-              tv[sl].x -= p0 + e0;
-              tv[sl].y -= p1 + e1;
+              dmma(p0, p1, xa.x, xa.x);
+              dmma(e0, e1, xa.y, xa.y);
+              t.x -= p0 + e0;
+              t.y -= p1 + e1;
+            }
+            double y0, y1;
+            diag_factor(t.x, t.y, y0, y1, nf, lane);
+            st_tile(A, ld, 8 * s, 8 * s, c, q, t);
+            *reinterpret_cast<double2 *>(Dbuf + s * 64 + c * 8 + 2 * q) = make_double2(y0, y1);
+          } else if (s + 1 < RT) {
+#pragma unroll
+            for (int sl = 0; sl < NSL; ++sl) {
+              const int L = s + 1 + warp + 7 * sl;
+              tvn[sl] = make_double2(0.0, 0.0);
+              if (L < PT) {
+                const double2 g = ld_tile(A, ld, 8 * (s + 1), 8 * L, c, q);
+                const double2 z = acc_tile<ld>(A, s, L, s + 1, c, q);
+                tvn[sl] = make_double2(g.x - z.x, g.y - z.y);
+              }
+            }
+            if (warp == 1 + (s + 1) % 7 && s > 0) {
+              const double2 g = ld_tile(A, ld, 8 * (s + 1), 8 * (s + 1), c, q);
+              const double2 z = acc_tile<ld>(A, s, s + 1, s + 1, c, q);
+              st_tile(A, ld, 8 * (s + 1), 8 * (s + 1), c, q, make_double2(g.x - z.x, g.y - z.y));
             }
           }
+          const long long u1 = clock64();
+          t_acc += u1 - u0;
+          __syncthreads();
+          const long long u2 = clock64();
+          t_wait += u2 - u1;
+          if (warp != 0) {
+            const double2 dv = ld_tile(Dbuf + s * 64, 8, 0, 0, c, q);
+#pragma unroll
+            for (int sl = 0; sl < NSL; ++sl) {
+              const int L = s + warp + 7 * sl;
+              if (L < PT) {
+                double r0 = 0.0, r1 = 0.0;
+                dmma(r0, r1, tv[sl].x, dv.x);
+                dmma(r0, r1, tv[sl].y, dv.y);
+                st_tile(A, ld, 8 * s, 8 * L, c, q, make_double2(r0, r1));
+              }
+            }
+          }
+          __syncthreads();
+          if (warp != 0 && s + 1 < RT) {
+#pragma unroll
+            for (int sl = 0; sl < NSL; ++sl) {
+              const int L = s + 1 + warp + 7 * sl;
+              tv[sl] = tvn[sl];
+              if (L < PT) {
+                const double2 xa = ld_tile(A, ld, 8 * s, 8 * L, c, q);
+                const double2 xb = ld_tile(A, ld, 8 * s, 8 * (s + 1), c, q);
+                double p0 = 0.0, p1 = 0.0, e0 = 0.0, e1 = 0.0;
+                dmma(p0, p1, xa.x, xb.x);
+                dmma(e0, e1, xa.y, xb.y);
+                tv[sl].x -= p0 + e0;
+                tv[sl].y -= p1 + e1;
+              }
+            }
+          }
+          if (fused) elim_dispatch<RT, ld>(s, xr, r_in, wc, A, Dbuf, cvec, p, c, q);
+          t_diag += clock64() - u2;
         }
-        if (fused) elim_dispatch<RT, ld>(s, xr, r_in, wc, A, Dbuf, cvec, p, c, q);
-        t_diag += clock64() - u2;
       }
 
       const long long t_c = clock64();
+      if constexpr (MODE == 1) {
+        // ---- split route: R (upper tiles, with c) and the diagonal inverses go to global memory
+        double2 *dst = reinterpret_cast<double2 *>(a.fact + eval * FD);
+#pragma unroll
+        for (int L = 0; L < PT; ++L) {
+          const int nrow2 = 4 * ((L < RT ? L : RT - 1) + 1);   // double2 per column
+          int off2 = 0;
+#pragma unroll
+          for (int k = 0; k < L; ++k) off2 += 32 * ((k < RT ? k : RT - 1) + 1);
+#pragma unroll
+          for (int e0 = 0; e0 < 8 * nrow2; e0 += 256) {
+            const int e = e0 + tid;
+            if (e < 8 * nrow2) {
+              const int cc = e / nrow2, r2 = e - cc * nrow2;
+              dst[off2 + e] = *reinterpret_cast<const double2 *>(A + (size_t)(8 * L + cc) * ld + 2 * r2);
+            }
+          }
+        }
+#pragma unroll
+        for (int e0 = 0; e0 < 32 * RT; e0 += 256) {
+          const int e = e0 + tid;
+          if (e < 32 * RT) dst[(FD - 64 * RT) / 2 + e] = reinterpret_cast<const double2 *>(Dbuf)[e];
+        }
+        (void)t_a; (void)t_b; (void)t_c; (void)t_acc; (void)t_diag; (void)t_wait;
+        (void)wc; (void)cvec; (void)xr; (void)r_in; (void)weight;
+      } else {
       // ---- phase 2: the row tiles of X that were not carried through the factorisation
       for (int it = NF + warp; it < RT; it += 8) {
         load_x<RT>(xr, r_in, a, perm_s, it, p, c, q);
@@ -454,9 +524,11 @@ __global__ void __launch_bounds__(256, MINB) lifts_chol_kernel(CholParams a) {
         const int f = perm_s[k];
         acc[f] = (h == 0 ? 0.0 : acc[f]) + weight * lift;
       }
+      }
     }
     __syncthreads();
-    for (int f = tid; f < p; f += 256) a.out[sidx * p + f] = acc[f];
+    if constexpr (MODE != 1)
+      for (int f = tid; f < p; f += 256) a.out[sidx * p + f] = acc[f];
   }
 }
 
@@ -467,21 +539,28 @@ size_t chol_smem_bytes(int p) {
   return d * sizeof(double) + (size_t)(p + 1) * sizeof(int) + 32;
 }
 
-template <int RT, int PT, int MINB>
+template <int RT, int PT, int MINB, int MODE>
 int launch_chol(const CholParams &a, int grid, size_t smem, cudaStream_t st) {
-  LSSPA_CUDA_TRY(cudaFuncSetAttribute(lifts_chol_kernel<RT, PT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  LSSPA_CUDA_TRY(cudaFuncSetAttribute(lifts_chol_kernel<RT, PT, MINB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
-  LSSPA_CUDA_TRY(cudaFuncSetAttribute(lifts_chol_kernel<RT, PT, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                      cudaSharedmemCarveoutMaxShared));
-  lifts_chol_kernel<RT, PT, MINB><<<grid, 256, smem, st>>>(a);
+  LSSPA_CUDA_TRY(cudaFuncSetAttribute(lifts_chol_kernel<RT, PT, MINB, MODE>,
+                                      cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  lifts_chol_kernel<RT, PT, MINB, MODE><<<grid, 256, smem, st>>>(a);
   LSSPA_LAUNCH_CHECK();
   return LSSPA_OK;
 }
 
 template <int RT>
-int launch_chol_rt(const CholParams &a, int grid, size_t smem, cudaStream_t st) {
+int launch_chol_rt(const CholParams &a, int grid, size_t smem, int mode, cudaStream_t st) {
   constexpr int MINB = RT <= 6 ? 3 : (RT <= 13 ? 2 : 1);   // resident CTAs per SM the register budget is cut for
-  return (a.pt == RT) ? launch_chol<RT, RT, MINB>(a, grid, smem, st) : launch_chol<RT, RT + 1, MINB>(a, grid, smem, st);
+  if constexpr (RT >= 7 && RT <= 16) {   // the split route is instantiated where the DMMA estimator also works
+    if (mode == 1)
+      return (a.pt == RT) ? launch_chol<RT, RT, MINB, 1>(a, grid, smem, st) : launch_chol<RT, RT + 1, MINB, 1>(a, grid, smem, st);
+    if (mode == 2)
+      return (a.pt == RT) ? launch_chol<RT, RT, MINB, 2>(a, grid, smem, st) : launch_chol<RT, RT + 1, MINB, 2>(a, grid, smem, st);
+  }
+  if (mode != 0) return LSSPA_E_UNSUPPORTED;
+  return (a.pt == RT) ? launch_chol<RT, RT, MINB, 0>(a, grid, smem, st) : launch_chol<RT, RT + 1, MINB, 0>(a, grid, smem, st);
 }
 
 // Column norms of the upper-triangular R (column-major, ld p): D[j] = |R[:, j]|, 1 where the column is zero
@@ -622,11 +701,15 @@ extern "C" int lsspa_lifts_gram(int p, const double *R_tr_cm, const double *c_tr
   return LSSPA_OK;
 }
 
-extern "C" int lsspa_lifts_chol(int p, const double *gram, const double *R_te_cm, const double *c_te,
-                                double y_norm_sq, const int32_t *perms, int64_t count, int antithetical,
-                                double *lifts_out, void *stream) {
+// mode 0: fused; 1: factor only (fact written); 2: eliminate only (fact read)
+static int chol_run(int mode, int p, const double *gram, const double *R_te_cm, const double *c_te, double y_norm_sq,
+                    const int32_t *perms, int64_t count, int antithetical, double *lifts_out, double *fact,
+                    void *stream) {
   if (!lifts_chol_supported(p)) return LSSPA_E_UNSUPPORTED;
-  if (!gram || !R_te_cm || !c_te || !lifts_out || (count > 0 && !perms) || !(y_norm_sq > 0.0)) return LSSPA_E_BADARG;
+  if (count > 0 && !perms) return LSSPA_E_BADARG;
+  if (mode != 2 && !gram) return LSSPA_E_BADARG;
+  if (mode != 1 && (!R_te_cm || !c_te || !lifts_out || !(y_norm_sq > 0.0))) return LSSPA_E_BADARG;
+  if (mode != 0 && !fact) return LSSPA_E_BADARG;
   if (count == 0) return LSSPA_OK;
   if (count < 0) return LSSPA_E_BADARG;
   CholParams a;
@@ -637,12 +720,13 @@ extern "C" int lsspa_lifts_chol(int p, const double *gram, const double *R_te_cm
   a.Gh = gram;
   a.Rte = R_te_cm;
   a.cte = c_te;
-  a.inv_ynsq = 1.0 / y_norm_sq;
+  a.inv_ynsq = (mode != 1) ? 1.0 / y_norm_sq : 0.0;
   a.perms = perms;
   a.count = count;
   a.anti = antithetical ? 1 : 0;
   a.out = lifts_out;
-  a.dbg = g_lifts_dbg;
+  a.fact = fact;
+  a.dbg = (mode == 0) ? g_lifts_dbg : nullptr;
   const size_t smem = chol_smem_bytes(p);
   const DeviceInfo &d = device_info();
   const int sms = d.sm_count > 0 ? d.sm_count : 148;
@@ -654,23 +738,48 @@ extern "C" int lsspa_lifts_chol(int p, const double *gram, const double *R_te_cm
   if (grid > count) grid = count;
   cudaStream_t st = as_stream(stream);
   switch (a.rt) {
-    case 3: return launch_chol_rt<3>(a, (int)grid, smem, st);
-    case 4: return launch_chol_rt<4>(a, (int)grid, smem, st);
-    case 5: return launch_chol_rt<5>(a, (int)grid, smem, st);
-    case 6: return launch_chol_rt<6>(a, (int)grid, smem, st);
-    case 7: return launch_chol_rt<7>(a, (int)grid, smem, st);
-    case 8: return launch_chol_rt<8>(a, (int)grid, smem, st);
-    case 9: return launch_chol_rt<9>(a, (int)grid, smem, st);
-    case 10: return launch_chol_rt<10>(a, (int)grid, smem, st);
-    case 11: return launch_chol_rt<11>(a, (int)grid, smem, st);
-    case 12: return launch_chol_rt<12>(a, (int)grid, smem, st);
-    case 13: return launch_chol_rt<13>(a, (int)grid, smem, st);
-    case 14: return launch_chol_rt<14>(a, (int)grid, smem, st);
-    case 15: return launch_chol_rt<15>(a, (int)grid, smem, st);
-    case 16: return launch_chol_rt<16>(a, (int)grid, smem, st);
-    case 17: return launch_chol_rt<17>(a, (int)grid, smem, st);
-    case 18: return launch_chol_rt<18>(a, (int)grid, smem, st);
-    case 19: return launch_chol_rt<19>(a, (int)grid, smem, st);
+    case 3: return launch_chol_rt<3>(a, (int)grid, smem, mode, st);
+    case 4: return launch_chol_rt<4>(a, (int)grid, smem, mode, st);
+    case 5: return launch_chol_rt<5>(a, (int)grid, smem, mode, st);
+    case 6: return launch_chol_rt<6>(a, (int)grid, smem, mode, st);
+    case 7: return launch_chol_rt<7>(a, (int)grid, smem, mode, st);
+    case 8: return launch_chol_rt<8>(a, (int)grid, smem, mode, st);
+    case 9: return launch_chol_rt<9>(a, (int)grid, smem, mode, st);
+    case 10: return launch_chol_rt<10>(a, (int)grid, smem, mode, st);
+    case 11: return launch_chol_rt<11>(a, (int)grid, smem, mode, st);
+    case 12: return launch_chol_rt<12>(a, (int)grid, smem, mode, st);
+    case 13: return launch_chol_rt<13>(a, (int)grid, smem, mode, st);
+    case 14: return launch_chol_rt<14>(a, (int)grid, smem, mode, st);
+    case 15: return launch_chol_rt<15>(a, (int)grid, smem, mode, st);
+    case 16: return launch_chol_rt<16>(a, (int)grid, smem, mode, st);
+    case 17: return launch_chol_rt<17>(a, (int)grid, smem, mode, st);
+    case 18: return launch_chol_rt<18>(a, (int)grid, smem, mode, st);
+    case 19: return launch_chol_rt<19>(a, (int)grid, smem, mode, st);
   }
   return LSSPA_E_UNSUPPORTED;
+}
+
+extern "C" int lsspa_lifts_chol(int p, const double *gram, const double *R_te_cm, const double *c_te,
+                                double y_norm_sq, const int32_t *perms, int64_t count, int antithetical,
+                                double *lifts_out, void *stream) {
+  return chol_run(0, p, gram, R_te_cm, c_te, y_norm_sq, perms, count, antithetical, lifts_out, nullptr, stream);
+}
+
+extern "C" int64_t lsspa_lifts_chol_factor_doubles(int p) {
+  if (p < 49 || p > 128) return 0;   // the split route
+  return chol_fact_doubles((p + 7) / 8, (p + 8) / 8);
+}
+
+extern "C" int lsspa_lifts_chol_factor(int p, const double *gram, const int32_t *perms, int64_t count,
+                                       int antithetical, double *factors_out, void *stream) {
+  if (lsspa_lifts_chol_factor_doubles(p) == 0) return LSSPA_E_UNSUPPORTED;
+  return chol_run(1, p, gram, nullptr, nullptr, 0.0, perms, count, antithetical, nullptr, factors_out, stream);
+}
+
+extern "C" int lsspa_lifts_chol_eliminate(int p, const double *factors, const double *R_te_cm, const double *c_te,
+                                          double y_norm_sq, const int32_t *perms, int64_t count, int antithetical,
+                                          double *lifts_out, void *stream) {
+  if (lsspa_lifts_chol_factor_doubles(p) == 0) return LSSPA_E_UNSUPPORTED;
+  return chol_run(2, p, nullptr, R_te_cm, c_te, y_norm_sq, perms, count, antithetical, lifts_out,
+                  const_cast<double *>(factors), stream);
 }

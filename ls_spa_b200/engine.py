@@ -110,7 +110,7 @@ class CudaBackend:
         self.use_cholqr2 = os.environ.get("LSSPA_REDUCE", "cholqr2") != "householder"
 
     # -- reduction ----------------------------------------------------------
-    def _row_chunks(self, X, y, lo, hi, p, keep=False):
+    def _row_chunks(self, X, y, lo, hi, p, keep=False, staging=None, fence=None):
         """Yield device (X_chunk, y_chunk) covering rows [lo, hi); host inputs are streamed on a copy
         stream so that the copy of chunk i+1 overlaps the work on chunk i.  keep=False recycles two
         staging buffers (single-pass consumers); keep=True lands the chunks in one resident device
@@ -131,15 +131,23 @@ class CudaBackend:
             self.copy_stream = torch.cuda.Stream(device=self.device)
         main = torch.cuda.current_stream()
         if keep:
-            bigX = torch.empty((rows, p), dtype=torch.float64, device=self.device)
-            bigy = torch.empty(rows, dtype=torch.float64, device=self.device)
+            if staging is not None:
+                bigX, bigy = staging
+            else:
+                bigX = torch.empty((rows, p), dtype=torch.float64, device=self.device)
+                bigy = torch.empty(rows, dtype=torch.float64, device=self.device)
             bufs = None
         else:
             bufs = [(torch.empty((chunk, p), dtype=torch.float64, device=self.device),
                      torch.empty(chunk, dtype=torch.float64, device=self.device)) for _ in range(2)]
         # the buffers come from the main stream's allocator pool: whatever used that memory before
-        # (e.g. the previous reduction's kernels) must finish before we copy into it
-        self.copy_stream.wait_stream(main)
+        # (e.g. the previous reduction's kernels) must finish before we copy into it.  A caller that
+        # allocated the staging arrays itself passes the event recorded right after the allocation,
+        # so that work it enqueued on the main stream since then does not hold the copies back.
+        if fence is not None:
+            self.copy_stream.wait_event(fence)
+        else:
+            self.copy_stream.wait_stream(main)
         free_ev = [None, None]
         for i, r0 in enumerate(range(lo, hi, chunk)):
             r1 = min(r0 + chunk, hi)
@@ -164,13 +172,22 @@ class CudaBackend:
     # Householder up to ~1e7); beyond it, or on a failed pivot, the Householder TSQR takes over
     CHOLQR2_MAX_COND = 1e6
 
-    def reduce_rows(self, X, y, lo, hi, p, divisor):
+    def alloc_staging(self, rows, p):
+        """Resident device arrays for `rows` host rows plus the event after which they are free to be
+        written by the copy stream."""
+        bigX = torch.empty((rows, p), dtype=torch.float64, device=self.device)
+        bigy = torch.empty(rows, dtype=torch.float64, device=self.device)
+        fence = torch.cuda.Event()
+        fence.record()
+        return (bigX, bigy), fence
+
+    def reduce_rows(self, X, y, lo, hi, p, divisor, staging=None, fence=None):
         """Rows [lo, hi) of [X|y]/divisor -> one triangular factor in slot layout (device)."""
         if hi - lo <= 0:
             return torch.zeros(ops.tsqr_slot(p), dtype=torch.float64, device=self.device)
         if self.use_cholqr2 and ops.gram_supported(p) and hi - lo >= 4 * (p + 1):
             fac = ops.CholQR2(p, divisor)
-            for Xc, yc, _ in self._row_chunks(X, y, lo, hi, p, keep=True):
+            for Xc, yc, _ in self._row_chunks(X, y, lo, hi, p, keep=True, staging=staging, fence=fence):
                 fac.add_chunk(Xc, yc)          # pass 1 on this chunk overlaps the next copy
             chunks = fac.chunks
             slot, info = fac.finish()          # pass 2 re-reads the resident rows
@@ -192,14 +209,17 @@ class CudaBackend:
     def ridge(self, p, reg):
         return ops.ridge_factor(p, reg, self.device)
 
-    def make_problem(self, train_slot, test_slot, p):
+    def make_problem(self, train_slot, test_slot, p, train=None):
         R_tr, c_tr, _ = ops.split_factor(train_slot, p)
         R_te, c_te, ysq = ops.split_factor(test_slot, p)
-        return ops.ReducedProblem(R_tr, c_tr, R_te, c_te, float(ysq.item()))
+        return ops.ReducedProblem(R_tr, c_tr, R_te, c_te, float(ysq.item()), train=train)
 
     # -- sample loop --------------------------------------------------------
     def lifts(self, prob, perms, antithetical):
         return ops.lifts(prob, perms, antithetical)
+
+    def lifts_eliminate(self, prob, factors, perms, antithetical):
+        return ops.lifts_eliminate(prob, factors, perms, antithetical)
 
     def make_estimator(self, cfg: JobConfig):
         return ops.Estimator(cfg.p, cfg.seed, cfg.estimate_errors, self.device)
@@ -234,7 +254,7 @@ class CudaBackend:
 # the job
 # ---------------------------------------------------------------------------
 def reduce_problem(backend, coll: Collective, X_train, X_test, y_train, y_test, reg, p,
-                   n_train_global=None, row_sharded=False):
+                   n_train_global=None, row_sharded=False, prefactor=None):
     """Both tall-skinny reductions, row-sharded over the ranks of `coll`.
 
     With row_sharded=False every rank was handed the full arrays and reduces its own
@@ -252,37 +272,104 @@ def reduce_problem(backend, coll: Collective, X_train, X_test, y_train, y_test, 
     lo, hi = local_range(n_tr_local)
     # train side: rows scaled by 1/sqrt(N) (reference ls_spa/ls_spa.py:309,311)
     f_tr = backend.reduce_rows(X_train, y_train, lo, hi, p, math.sqrt(n_train_global))
-    lo, hi = local_range(int(X_test.shape[0]))
-    f_te = backend.reduce_rows(X_test, y_test, lo, hi, p, 1.0)       # :315 unscaled
     g_tr = coll.all_gather(f_tr)
-    g_te = coll.all_gather(f_te)
     if reg != 0.0:
         g_tr = torch.cat([g_tr, backend.ridge(p, reg).unsqueeze(0)], 0)    # :310
     train_slot = backend.merge_factors(g_tr, p) if g_tr.shape[0] > 1 else g_tr[0]
+    train = None
+    lo, hi = local_range(int(X_test.shape[0]))
+    if prefactor is not None:
+        # single process, host-resident test rows: the train factor is complete, so permutations
+        # can already be drawn and factored while the test rows cross PCIe.  The staging arrays of
+        # the test rows are allocated first: the copies then only wait for what was enqueued before
+        # the factorisations, and no block freed during them can end up under a copy.
+        staging, fence = backend.alloc_staging(hi - lo, p)
+        train = prefactor.run(train_slot, p)
+        f_te = backend.reduce_rows(X_test, y_test, lo, hi, p, 1.0, staging=staging, fence=fence)
+    else:
+        f_te = backend.reduce_rows(X_test, y_test, lo, hi, p, 1.0)       # :315 unscaled
+    g_te = coll.all_gather(f_te)
     test_slot = backend.merge_factors(g_te, p) if g_te.shape[0] > 1 else g_te[0]
+    if train is not None:
+        return backend.make_problem(train_slot, test_slot, p, train=train)
     return backend.make_problem(train_slot, test_slot, p)
 
 
-def run_samples(backend, coll: Collective, prob, source: PermutationSource, cfg: JobConfig):
+class Prefactor:
+    """Cholesky route of a host-resident job, first half ahead of time: as soon as the train factor
+    exists, the permutations of the first super-batches are drawn and factored (lsspa_lifts_chol_factor
+    needs the train side only).  The kernels run while the copy engine streams the test rows; the
+    sample loop then only eliminates (lsspa_lifts_chol_eliminate).  table: first sample -> (perms,
+    factors)."""
+
+    MAX_BYTES = 12 << 30          # device memory spent on stored factors
+    FACTOR_RATE = 9e6             # evaluations/s assumed for sizing the overlap window
+    LINK_RATE = 50e9              # bytes/s assumed for the host link
+
+    def __init__(self, backend, cfg: JobConfig, get_source, test_bytes: int):
+        self.backend, self.cfg, self.get_source, self.test_bytes = backend, cfg, get_source, test_bytes
+        self.table, self.train, self.source = {}, None, None
+
+    def run(self, train_slot, p):
+        from . import ops as _ops
+        R_tr, c_tr, _ = _ops.split_factor(train_slot, p)
+        self.train = train = _ops.TrainSide(R_tr, c_tr)
+        if not (train.use_chol and _ops.split_route_supported(p)):
+            return train
+        cfg = self.cfg
+        self.source = source = self.get_source()
+        limit, bs_eff, sb_size = superbatch_geometry(cfg, 1, source.total)
+        if limit is None:
+            return train
+        per_sample = 2 if cfg.antithetical else 1
+        fd = int(_ops._lib().lsspa_lifts_chol_factor_doubles(p))
+        budget = min(self.MAX_BYTES // (8 * fd), int(self.FACTOR_RATE * self.test_bytes / self.LINK_RATE))
+        pos, index, evals = 0, 0, 0
+        while pos < limit:
+            want = min(sb_size(index), limit - pos)
+            if evals + want * per_sample > budget:
+                break
+            if source.random_access:
+                source.position = pos
+            perms = source.take(want)
+            if int(perms.shape[0]) != want:
+                break                                   # stream ran dry: leave the rest to the loop
+            self.table[pos] = (perms, _ops.lifts_factor(train, perms, cfg.antithetical))
+            pos, index, evals = pos + want, index + 1, evals + want * per_sample
+        return train
+
+
+def superbatch_geometry(cfg: JobConfig, world: int, source_total):
+    """-> (limit, effective batch size, size(index)): how many samples super-batch `index` asks for
+    (before clipping to the limit).  Deterministic, so that work can be prepared ahead of the loop."""
+    limit = cfg.max_samples
+    if source_total is not None:
+        limit = source_total if limit is None else min(limit, source_total)
+    tgt = target_samples(cfg.p)
+    # without error estimates batch boundaries are irrelevant: cut the super-batch into 1024-sample
+    # batches so that the per-batch moment kernels run in parallel
+    bs_eff = cfg.batch_size if cfg.estimate_errors else min(tgt, 1024)
+    g_local = max(1, -(-tgt // bs_eff))
+    # When the job can stop early the super-batches ramp up (2048 samples per rank, then 4x per
+    # round up to the full size): a loose tolerance is then reached after little more than the work
+    # it needs instead of after one full super-batch, at the price of two extra (pipelined) rounds.
+    g_first = max(1, min(g_local, -(-2048 // bs_eff)))
+    ramps = cfg.estimate_errors and cfg.tolerance > 0.0
+
+    def size(index: int) -> int:
+        g = min(g_local, g_first << min(2 * index, 30)) if ramps else g_local
+        return g * world * bs_eff
+    return limit, bs_eff, size
+
+
+def run_samples(backend, coll: Collective, prob, source: PermutationSource, cfg: JobConfig, pre=None):
     """The estimator loop (reference ls_spa/ls_spa.py:196-236), one super-batch at a time.
 
     Returns (result dict, history or None, samples drawn).  result: count, mean, overall_error,
     attribution_errors, error_history (numpy)."""
     p, W, rank = cfg.p, coll.world, coll.rank
-    limit = cfg.max_samples
-    if source.total is not None:
-        limit = source.total if limit is None else min(limit, source.total)
-    tgt = target_samples(p)
-    # without error estimates batch boundaries are irrelevant: cut the super-batch into 1024-sample
-    # batches so that the per-batch moment kernels run in parallel
-    bs_eff = cfg.batch_size if cfg.estimate_errors else min(tgt, 1024)
-    g_local = max(1, -(-tgt // bs_eff))
-    sb_samples = g_local * W * bs_eff
-    # When the job can stop early the super-batches ramp up (2048 samples per rank, doubling to the
-    # full size): a loose tolerance is then reached after little more than the work it needs,
-    # instead of after one full super-batch, at the price of two or three extra (pipelined) rounds.
-    ramp = {"next": 0}
-    g_first = max(1, min(g_local, -(-2048 // bs_eff)))
+    limit, bs_eff, sb_size = superbatch_geometry(cfg, W, source.total)
+    sb_index = {"next": 0}
     est = backend.make_estimator(cfg)
     quirk = (cfg.max_samples - 1) if (cfg.penultimate_check and cfg.max_samples and cfg.estimate_errors) else None
     can_stop = cfg.estimate_errors and cfg.tolerance > 0.0
@@ -294,11 +381,23 @@ def run_samples(backend, coll: Collective, prob, source: PermutationSource, cfg:
     def launch_lifts(pos):
         """Stage A of a super-batch: permutations and lift rows of this rank's run of batches.
         Touches neither the estimator nor the host, so it can be issued one super-batch ahead."""
-        size = sb_samples
-        if cfg.estimate_errors and cfg.tolerance > 0.0:
-            size = min(sb_samples, (g_first << ramp["next"]) * W * bs_eff)
-            ramp["next"] = min(ramp["next"] + 1, 30)
+        size = sb_size(sb_index["next"])
+        sb_index["next"] += 1
         want = size if limit is None else min(size, limit - pos)
+        hit = pre.table.pop(pos, None) if pre is not None else None
+        if hit is not None:
+            # permutations of this super-batch were drawn and factored (train side) while the test
+            # rows were still being copied: only the elimination against the test factor is left
+            perms, factors = hit
+            assert int(perms.shape[0]) == want, "prefactored super-batch does not match the plan"
+            n_sb = want
+            if source.random_access:
+                source.position = pos + n_sb
+            batches = split_batches(pos, n_sb, bs_eff, quirk)
+            runs, per = contiguous_runs(len(batches), W)
+            rows = backend.lifts_eliminate(prob, factors, perms, cfg.antithetical)
+            return dict(pos=pos, n_sb=n_sb, dry=False, batches=batches, runs=runs, per=per, mine=batches,
+                        my_count=n_sb, rows=rows)
         perms_all = None
         if not source.random_access:
             perms_all = source.take(want)        # sequential stream: every rank walks it

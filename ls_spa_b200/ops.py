@@ -248,28 +248,22 @@ def perms_permutohedron(p, sv, shift, bits, first_index, count) -> torch.Tensor:
 # ---------------------------------------------------------------------------
 # per-permutation core
 # ---------------------------------------------------------------------------
-class ReducedProblem:
-    """The p x p reduced factors in the layout the lift kernel wants (column-major)."""
+class TrainSide:
+    """Train half of the reduced problem and what the Cholesky route derives from it: the
+    equilibrated Gram matrix, its column scales and the condition bound that picks the route.
+    It needs no test data, so a host-resident job builds it (and pre-factors permutations with it)
+    while the test rows are still crossing PCIe."""
 
-    def __init__(self, R_tr, c_tr, R_te, c_te, y_norm_sq: float):
+    def __init__(self, R_tr, c_tr):
         dev = R_tr.device
-        self.p = int(R_tr.shape[0])
-        p = self.p
-        R_te = _dev_f64(R_te, "R_te")
-        if R_te.shape[0] < p:  # M < p: the reference keeps an M x p factor; zero rows change nothing
-            pad = torch.zeros((p - R_te.shape[0], p), dtype=torch.float64, device=dev)
-            R_te = torch.cat([R_te, pad], 0)
-            c_te = torch.cat([_dev_f64(c_te, "c_te"), pad[:, 0]], 0)
+        self.p = p = int(R_tr.shape[0])
         # row-major (p,p) -> column-major storage == contiguous transpose
         self.R_tr_cm = _dev_f64(R_tr, "R_tr").t().contiguous()
-        self.R_te_cm = R_te.t().contiguous()
         self.c_tr = _dev_f64(c_tr, "c_tr").contiguous()
-        self.c_te = _dev_f64(c_te, "c_te").contiguous()
-        self.y_norm_sq = float(y_norm_sq)
-        self._ws = None
         # Route of the per-permutation core: Cholesky of the permuted Gram matrix when the
         # train factor is well conditioned (error ~ eps * cond^2), Householder otherwise.
         self.gram = None
+        self.scale = None
         self.cond_estimate = float("inf")
         self.use_chol = False
         forced = os.environ.get("LSSPA_LIFTS_IMPL", "")
@@ -283,8 +277,31 @@ class ReducedProblem:
             info = self.gram[base:base + 2].cpu()
             self.cond_estimate = float(info[0])    # of the column-equilibrated train factor
             self.use_chol = forced == "chol" or self.cond_estimate <= CHOL_COND_LIMIT
+            self.scale = self.gram[base + 8:base + 8 + p]
+
+
+class ReducedProblem:
+    """The p x p reduced factors in the layout the lift kernel wants (column-major)."""
+
+    def __init__(self, R_tr, c_tr, R_te, c_te, y_norm_sq: float, train: TrainSide | None = None):
+        train = train if train is not None else TrainSide(R_tr, c_tr)
+        self.train = train
+        dev = train.c_tr.device
+        self.p = p = train.p
+        R_te = _dev_f64(R_te, "R_te")
+        if R_te.shape[0] < p:  # M < p: the reference keeps an M x p factor; zero rows change nothing
+            pad = torch.zeros((p - R_te.shape[0], p), dtype=torch.float64, device=dev)
+            R_te = torch.cat([R_te, pad], 0)
+            c_te = torch.cat([_dev_f64(c_te, "c_te"), pad[:, 0]], 0)
+        self.R_tr_cm, self.c_tr = train.R_tr_cm, train.c_tr
+        self.R_te_cm = R_te.t().contiguous()
+        self.c_te = _dev_f64(c_te, "c_te").contiguous()
+        self.y_norm_sq = float(y_norm_sq)
+        self._ws = None
+        self.gram, self.cond_estimate, self.use_chol = train.gram, train.cond_estimate, train.use_chol
+        if train.scale is not None:
             # the Cholesky route works on unit-norm train columns: scale the test columns alike
-            self.R_te_scaled_cm = self.R_te_cm / self.gram[base + 8:base + 8 + p].unsqueeze(1)
+            self.R_te_scaled_cm = self.R_te_cm / train.scale.unsqueeze(1)
 
     def workspace(self, count: int):
         nbytes = _lib().lsspa_lifts_workspace_bytes(self.p, count)
@@ -321,6 +338,49 @@ def lifts(prob: ReducedProblem, perms: torch.Tensor, antithetical: bool, out: to
                                  prob.c_te.data_ptr(), prob.y_norm_sq, perms.data_ptr(), count,
                                  1 if antithetical else 0, out.data_ptr(), _ptr(ws), nbytes, _stream()),
               "lsspa_lifts")
+    _count(1)
+    if trace is not None:
+        e1.record()
+        trace.append((e0, e1, count * (2 if antithetical else 1)))
+    return out
+
+
+def split_route_supported(p: int) -> bool:
+    return int(_lib().lsspa_lifts_chol_factor_doubles(p)) > 0
+
+
+def lifts_factor(train: TrainSide, perms: torch.Tensor, antithetical: bool) -> torch.Tensor:
+    """First half of the Cholesky route (train side only): one factor block per permutation
+    evaluation, (count * (2 if antithetical else 1), factor_doubles)."""
+    perms = perms.contiguous()
+    count, p = perms.shape
+    fd = int(_lib().lsspa_lifts_chol_factor_doubles(p))
+    evals = count * (2 if antithetical else 1)
+    out = torch.empty((evals, fd), dtype=torch.float64, device=perms.device)
+    check(_lib().lsspa_lifts_chol_factor(p, train.gram.data_ptr(), perms.data_ptr(), count,
+                                         1 if antithetical else 0, out.data_ptr(), _stream()),
+          "lsspa_lifts_chol_factor")
+    _count(1)
+    return out
+
+
+def lifts_eliminate(prob: ReducedProblem, factors: torch.Tensor, perms: torch.Tensor, antithetical: bool,
+                    out: torch.Tensor | None = None) -> torch.Tensor:
+    """Second half: eliminate the test factor against the stored factors -> lift rows."""
+    global LIFT_ROUTE
+    LIFT_ROUTE = "cholesky"
+    perms = perms.contiguous()
+    count, p = perms.shape
+    if out is None:
+        out = torch.empty((count, p), dtype=torch.float64, device=perms.device)
+    trace = LIFT_TRACE
+    if trace is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    check(_lib().lsspa_lifts_chol_eliminate(p, factors.data_ptr(), prob.R_te_scaled_cm.data_ptr(),
+                                            prob.c_te.data_ptr(), prob.y_norm_sq, perms.data_ptr(), count,
+                                            1 if antithetical else 0, out.data_ptr(), _stream()),
+          "lsspa_lifts_chol_eliminate")
     _count(1)
     if trace is not None:
         e1.record()
