@@ -557,3 +557,45 @@ def test_naive_comparator_against_device(T, L):
         want = no.naive_attribution(Xtr, Xte, ytr, yte, perms, reg=reg)
         got = L.ls_spa(Xtr, Xte, ytr, yte, reg=reg, perms=perms, tolerance=0.0, antithetical=False)
         assert scaled_err(got.attribution, want) < 1e-9, (reg, scaled_err(got.attribution, want))
+
+
+def test_split_route_host_inputs(T, L, monkeypatch):
+    """Host-resident inputs on the Cholesky route: the factorisations run ahead (train side only,
+    overlapping the copy of the test rows) and the sample loop only eliminates.  Same results as the
+    fused kernel, for every device sampler, with and without early stop."""
+    from ls_spa_b200 import ops
+    from oracle import samplers_oracle as so
+    rng = np.random.default_rng(21)
+    p = 64
+    Xtr, Xte, ytr, yte, _, _ = so.gen_data(rng, p, 5000, 4000)
+    calls = {"n": 0}
+    real = ops.lifts_eliminate
+
+    def counting(*a, **k):
+        calls["n"] += 1
+        return real(*a, **k)
+    monkeypatch.setattr(ops, "lifts_eliminate", counting)
+    from ls_spa_b200 import engine
+    monkeypatch.setattr(engine.Prefactor, "FACTOR_RATE", 1e15)   # tiny test rows: lift the overlap-window cap
+    for method, anti, tol in (("permutohedron", True, 0.0), ("argsort", False, 0.0), ("random", True, 0.0),
+                              ("permutohedron", True, 5e-3)):
+        kw = dict(reg=1e-3, method=method, batch_size=32, num_batches=40, tolerance=tol, seed=9, antithetical=anti,
+                  return_history=True)
+        calls["n"] = 0
+        monkeypatch.setenv("LSSPA_SPLIT_ROUTE", "1")
+        a = L.ls_spa(Xtr, Xte, ytr, yte, **kw)
+        assert calls["n"] > 0, "the split route was not taken"
+        monkeypatch.setenv("LSSPA_SPLIT_ROUTE", "0")
+        calls["n"] = 0
+        b = L.ls_spa(Xtr, Xte, ytr, yte, **kw)
+        assert calls["n"] == 0
+        assert scaled_err(a.attribution, b.attribution) < 1e-13, (method, anti, tol)
+        assert a.error_history.shape == b.error_history.shape
+        np.testing.assert_allclose(a.error_history, b.error_history, rtol=1e-9)
+        assert scaled_err(a.attribution_history, b.attribution_history) < 1e-13
+        # device-resident inputs never take it
+        monkeypatch.setenv("LSSPA_SPLIT_ROUTE", "1")
+        dev = [T.from_numpy(np.ascontiguousarray(v)).cuda() for v in (Xtr, Xte, ytr, yte)]
+        calls["n"] = 0
+        c = L.ls_spa(*dev, **kw)
+        assert calls["n"] == 0 and scaled_err(c.attribution, b.attribution) < 1e-12
