@@ -134,6 +134,10 @@ class OracleBackend:
             out.append(l)
         return torch.from_numpy(np.array(out).reshape(-1, perms.shape[1]))
 
+    def lifts_eliminate(self, prob, factors, perms, anti):
+        assert factors == "factored"               # stand-in for the stored factor blocks
+        return self.lifts(prob, perms, anti)
+
     def make_estimator(self, cfg):
         return FakeEstimator(cfg.p)
 
@@ -234,3 +238,53 @@ def test_two_ranks_early_stop_is_replicated():
     other = [g for g in got if len(g) == 2][0]
     assert full[1] == other[1] == 4 * stop_at
     assert len(full[2]) == stop_at and full[3].shape[0] == 4 * stop_at
+
+
+class FakePre:
+    """Stand-in for engine.Prefactor: permutations of the first super-batches drawn ahead of the
+    loop with the same plan (superbatch_geometry) the loop will follow."""
+
+    def __init__(self, cfg, source, rounds):
+        self.table, self.source = {}, source
+        limit, _, size = engine.superbatch_geometry(cfg, 1, source.total)
+        pos = 0
+        for index in range(rounds):
+            if pos >= limit:
+                break
+            want = min(size(index), limit - pos)
+            source.position = pos
+            self.table[pos] = (source.take(want), "factored")
+            pos += want
+
+
+@pytest.mark.parametrize("rounds,tol", [(0, 0.0), (2, 0.0), (99, 0.0), (3, None)])
+def test_prefactored_superbatches_follow_the_plan(rounds, tol):
+    """The split route prepares super-batches ahead of the sample loop; the loop must find them at
+    exactly the positions and sizes it would have asked for (ramp-up included), use the rest of
+    the stream normally, and produce the same result as without preparation."""
+    Xtr, Xte, ytr, yte = problem()
+    p = Xtr.shape[1]
+    perms = so.perms_random(p, 150, 9)
+    backend, coll = OracleBackend(), engine.Collective(None)
+    prob = engine.reduce_problem(backend, coll, Xtr, Xte, ytr, yte, 0.05, p)
+    import ls_spa_b200.engine as E
+    old = E.target_samples
+    E.target_samples = lambda p: 32
+    try:
+        base_cfg = dict(p=p, batch_size=4, max_samples=None, seed=1, antithetical=True, estimate_errors=True,
+                        return_history=True)
+        ref = engine.run_samples(backend, coll, prob, RangeSource(perms),
+                                 engine.JobConfig(tolerance=0.0, **base_cfg))
+        if tol is None:                               # an early stop inside the prepared range
+            tol = float(np.sort(ref[0]["error_history"])[::-1][6]) * 1.000001
+        cfg = engine.JobConfig(tolerance=tol, **base_cfg)
+        want = engine.run_samples(backend, coll, prob, RangeSource(perms), cfg)
+        src = RangeSource(perms)
+        pre = FakePre(cfg, src, rounds)
+        got = engine.run_samples(backend, coll, prob, src, cfg, pre=pre)
+        assert got[2] == want[2] and got[0]["count"] == want[0]["count"]
+        assert np.array_equal(got[0]["mean"], want[0]["mean"])
+        assert np.array_equal(got[0]["error_history"], want[0]["error_history"])
+        assert np.array_equal(got[1], want[1])
+    finally:
+        E.target_samples = old
