@@ -194,13 +194,15 @@ __global__ void gram_sum_kernel(const double *parts, int count, int n2, double s
 // D = diag(sqrt(G_jj)): the accuracy of a Cholesky factor is governed by the conditioning of the
 // equilibrated matrix (van der Sluis / Demmel), so units of the columns must not count.
 // R is written row-major q x q (slot layout of reduce.cu); Rinv row-major [nc][ldr], zero padded.
-__global__ void __launch_bounds__(256) chol_factor_kernel(const double *G, int q, int nc, int ldr, double *R_out,
-                                                          double *Rinv_out, double *info) {
+__global__ void __launch_bounds__(1024) chol_factor_kernel(const double *G, int q, int nc, int ldr, double *R_out,
+                                                           double *Rinv_out, double *info) {
   extern __shared__ double sm[];
-  double *A = sm;                        // nc x nc working copy (upper part)
-  double *Vi = A + (size_t)nc * nc;      // nc x nc inverse
-  __shared__ double s_piv, s_fail, red[16];
+  double *A = sm;                        // nc x nc working copy (upper part), row-major
+  double *Vi = A + (size_t)nc * nc;      // nc x nc inverse, row-major
+  __shared__ double rk[128];             // scaled pivot row of the current column
+  __shared__ double s_fail, red[64];
   const int tid = threadIdx.x, nt = blockDim.x;
+  const int tx = tid & 31, ty = tid >> 5, lane = tx, w = ty;
   for (int e = tid; e < nc * nc; e += nt) {
     const int i = e / nc, j = e - i * nc;
     A[e] = (i < q && j < q && j >= i) ? G[e] : 0.0;
@@ -210,37 +212,34 @@ __global__ void __launch_bounds__(256) chol_factor_kernel(const double *G, int q
   __syncthreads();
   double dmax = 0.0;
   for (int i = 0; i < q; ++i) dmax = fmax(dmax, A[(size_t)i * nc + i]);
+  // right-looking Cholesky, two barriers per column: (a) the pivot row is scaled into rk,
+  // (b) the trailing block is updated by a 32 x 32 thread grid (no index divisions)
   for (int k = 0; k < q; ++k) {
-    if (tid == 0) {
-      const double d = A[(size_t)k * nc + k];
-      if (!(d > 1e-14 * G[(size_t)k * nc + k]) || !(dmax > 0.0)) s_fail = 1.0;
-      const double r = sqrt(d > 0.0 ? d : 1.0);
-      A[(size_t)k * nc + k] = r;
-      s_piv = 1.0 / r;
-    }
-    __syncthreads();
-    const double ri = s_piv;
-    for (int j = k + 1 + tid; j < q; j += nt) A[(size_t)k * nc + j] *= ri;
-    __syncthreads();
+    const double d = A[(size_t)k * nc + k];
+    const double r = sqrt(d > 0.0 ? d : 1.0), ri = 1.0 / r;
+    if (tid == 0 && (!(d > 1e-14 * G[(size_t)k * nc + k]) || !(dmax > 0.0))) s_fail = 1.0;
     const int m = q - k - 1;
-    for (int e = tid; e < m * m; e += nt) {
-      const int i = k + 1 + e / m, j = k + 1 + e % m;
-      if (j >= i) A[(size_t)i * nc + j] = fma(-A[(size_t)k * nc + i], A[(size_t)k * nc + j], A[(size_t)i * nc + j]);
+    for (int j = tid; j < m; j += nt) rk[j] = A[(size_t)k * nc + k + 1 + j] * ri;
+    __syncthreads();
+    if (tid == 0) A[(size_t)k * nc + k] = r;
+    for (int j = tid; j < m; j += nt) A[(size_t)k * nc + k + 1 + j] = rk[j];
+    for (int i = ty; i < m; i += 32) {
+      const double ai = rk[i];
+      double *row = A + (size_t)(k + 1 + i) * nc + k + 1;
+      for (int j = i + tx; j < m; j += 32) row[j] = fma(-ai, rk[j], row[j]);   // upper part: j >= i
     }
     __syncthreads();
   }
-  // inverse: thread j solves R x = e_j by back substitution (column j of R^-1)
-  for (int j = tid; j < q; j += nt) {
-    Vi[(size_t)j * nc + j] = 1.0 / A[(size_t)j * nc + j];
-    for (int i = j - 1; i >= 0; --i) {
-      double s0 = 0.0, s1 = 0.0;
-      int k = i + 1;
-      for (; k + 1 <= j; k += 2) {
-        s0 = fma(A[(size_t)i * nc + k], Vi[(size_t)k * nc + j], s0);
-        s1 = fma(A[(size_t)i * nc + k + 1], Vi[(size_t)(k + 1) * nc + j], s1);
-      }
-      if (k <= j) s0 = fma(A[(size_t)i * nc + k], Vi[(size_t)k * nc + j], s0);
-      Vi[(size_t)i * nc + j] = -(s0 + s1) / A[(size_t)i * nc + i];
+  // inverse: warp w solves R x = e_j for its columns j by back substitution, the row dot products
+  // across the lanes (column j of R^-1 lives in column j of Vi)
+  for (int j = w; j < q; j += 32) {
+    for (int i = j; i >= 0; --i) {
+      const double *row = A + (size_t)i * nc;
+      double sacc = 0.0;
+      for (int k = i + 1 + lane; k <= j; k += 32) sacc = fma(-row[k], Vi[(size_t)k * nc + j], sacc);
+      sacc = warp_sum(sacc);
+      if (lane == 0) Vi[(size_t)i * nc + j] = (sacc + ((i == j) ? 1.0 : 0.0)) / row[i];
+      __syncwarp();
     }
   }
   __syncthreads();
@@ -249,24 +248,24 @@ __global__ void __launch_bounds__(256) chol_factor_kernel(const double *G, int q
     const int i = e / nc, j = e - i * nc;
     if (i < q && j < q) {
       const double di = sqrt(fmax(G[(size_t)i * nc + i], 0.0)), dj = sqrt(fmax(G[(size_t)j * nc + j], 0.0));
-      const double r = (dj > 0.0) ? A[e] / dj : 0.0;
+      const double rr = (dj > 0.0) ? A[e] / dj : 0.0;
       const double v = Vi[e] * di;
-      fr = fma(r, r, fr);
+      fr = fma(rr, rr, fr);
       fi = fma(v, v, fi);
     }
   }
   fr = warp_sum(fr);
   fi = warp_sum(fi);
-  if ((tid & 31) == 0) {
-    red[tid >> 5] = fr;
-    red[8 + (tid >> 5)] = fi;
+  if (lane == 0) {
+    red[w] = fr;
+    red[32 + w] = fi;
   }
   __syncthreads();
   if (tid == 0) {
     double a = 0.0, b = 0.0;
-    for (int w = 0; w < nt / 32; ++w) {
-      a += red[w];
-      b += red[8 + w];
+    for (int k = 0; k < nt / 32; ++k) {
+      a += red[k];
+      b += red[32 + k];
     }
     info[0] = s_fail;
     info[1] = sqrt(a) * sqrt(b);
@@ -374,7 +373,7 @@ extern "C" int lsspa_chol_factor(const double *G, int p, double *R_out, double *
   const int nt = gram_nt(p), nc = 8 * nt, ldr = gram_ldr(nt);
   const size_t smem = (size_t)2 * nc * nc * sizeof(double);
   LSSPA_CUDA_TRY(cudaFuncSetAttribute(chol_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  chol_factor_kernel<<<1, 256, smem, as_stream(stream)>>>(G, p + 1, nc, ldr, R_out, Rinv_out, info);
+  chol_factor_kernel<<<1, 1024, smem, as_stream(stream)>>>(G, p + 1, nc, ldr, R_out, Rinv_out, info);
   LSSPA_LAUNCH_CHECK();
   return LSSPA_OK;
 }
