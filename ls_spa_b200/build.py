@@ -70,6 +70,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
         raise RuntimeError("link failed")
+    for obj in objs:                 # only the shared library needs to travel
+        try:
+            os.remove(obj)
+        except OSError:
+            pass
     return LIB_PATH
 
 
