@@ -145,7 +145,10 @@ LSSPA_API int lsspa_lifts(int p, const double *R_tr_cm, const double *c_tr, cons
  *                      R' = R_tr D^-1 (the lifts do not change when train and test features are
  *                      scaled alike, and unit columns remove the conditioning that is only units):
  *                      gram_out[0 .. (p+1)^2)       = [R'|c_tr]^T [R'|c_tr],
- *                      gram_out[(p+1)^2 + 0]        = |R'|_F |R'^-1|_F  (>= cond_2, inf if singular),
+ *                      gram_out[(p+1)^2 + 0]        = a bound >= cond_2(R') (inf if singular): the smaller
+ *                                                     of [+2] = |R'|_F |R'^-1|_F and, for p <= 128,
+ *                                                     [+3] = sqrt(max row sum of |G|) *
+ *                                                     sqrt(|R'^-1|_1 |R'^-1|_inf),
  *                      gram_out[(p+1)^2 + 1]        = min|R'_kk| / max|R'_kk|,
  *                      gram_out[(p+1)^2 + 8 .. +8+p) = D; the rest is scratch.
  *   lsspa_lifts_chol   same outputs as lsspa_lifts, reading gram_out instead of R_tr / c_tr;
