@@ -190,7 +190,8 @@ __global__ void gram_sum_kernel(const double *parts, int count, int n2, double s
 
 // Cholesky G = R^T R (upper, G row-major nc x nc, leading q x q block used), then R^-1.
 // info[0] = 0 ok / 1 non-positive or tiny pivot (relative to the column's own norm),
-// info[1] = |R'|_F |R'^-1|_F (>= cond_2(R')) of the column-equilibrated factor R' = R D^-1,
+// info[1] = a bound >= cond_2(R') of the column-equilibrated factor R' = R D^-1 (the smaller of
+// |R'|_F |R'^-1|_F and sqrt(max row sum |G'|) sqrt(|R'^-1|_1 |R'^-1|_inf)),
 // D = diag(sqrt(G_jj)): the accuracy of a Cholesky factor is governed by the conditioning of the
 // equilibrated matrix (van der Sluis / Demmel), so units of the columns must not count.
 // R is written row-major q x q (slot layout of reduce.cu); Rinv row-major [nc][ldr], zero padded.
@@ -261,14 +262,40 @@ __global__ void __launch_bounds__(1024) chol_factor_kernel(const double *G, int 
     red[32 + w] = fi;
   }
   __syncthreads();
+  // second bound: sqrt(Gershgorin bound on the largest eigenvalue of the equilibrated Gram matrix)
+  // * sqrt(|R'^-1|_1 |R'^-1|_inf) with R'^-1 = D R^-1; thread t takes row / column t
+  __shared__ double b_g[128], b_c[128], b_r[128];
+  for (int t = tid; t < q; t += nt) {
+    const double dt = sqrt(fmax(G[(size_t)t * nc + t], 0.0));
+    double g = 0.0, cs = 0.0, rs = 0.0;
+    for (int k = 0; k < q; ++k) {
+      const double dk = sqrt(fmax(G[(size_t)k * nc + k], 0.0));
+      const double gij = (k >= t) ? G[(size_t)t * nc + k] : G[(size_t)k * nc + t];   // upper part of G
+      g += (dt > 0.0 && dk > 0.0) ? fabs(gij) / (dt * dk) : 0.0;
+      cs += fabs(Vi[(size_t)k * nc + t]) * dk;     // column t of D R^-1
+      rs += fabs(Vi[(size_t)t * nc + k]) * dt;     // row t
+    }
+    b_g[t] = g;
+    b_c[t] = cs;
+    b_r[t] = rs;
+  }
+  __syncthreads();
   if (tid == 0) {
-    double a = 0.0, b = 0.0;
+    double a = 0.0, b = 0.0, gm = 0.0, cm = 0.0, rm = 0.0;
     for (int k = 0; k < nt / 32; ++k) {
       a += red[k];
       b += red[32 + k];
     }
+    for (int t = 0; t < q; ++t) {
+      gm = fmax(gm, b_g[t]);
+      cm = fmax(cm, b_c[t]);
+      rm = fmax(rm, b_r[t]);
+    }
+    double frob = sqrt(a) * sqrt(b), sharp = sqrt(gm) * sqrt(cm * rm);
+    if (!(frob == frob)) frob = INFINITY;
+    if (!(sharp == sharp)) sharp = INFINITY;
     info[0] = s_fail;
-    info[1] = sqrt(a) * sqrt(b);
+    info[1] = fmin(frob, sharp);
   }
   for (int e = tid; e < q * q; e += nt) {
     const int i = e / q, j = e - i * q;
