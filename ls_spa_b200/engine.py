@@ -473,14 +473,13 @@ def run_samples(backend, coll: Collective, prob, source: PermutationSource, cfg:
         more = (not cur["dry"]) and (limit is None or pos + n_sb < limit)
         if cfg.estimate_errors:
             if W > 1:
-                ov = backend.zeros(per)
-                ft = backend.zeros(per, p)
+                both = backend.zeros(per, p + 1)          # one exchange: [overall | per-feature] per batch
                 if overall is not None:
-                    ov[: b1 - b0] = overall
-                    ft[: b1 - b0] = feat
-                ov_all, ft_all = coll.all_gather(ov), coll.all_gather(ft)
-                overall = torch.cat([ov_all[r, : b - a] for r, (a, b) in enumerate(runs)], 0)
-                feat = torch.cat([ft_all[r, : b - a] for r, (a, b) in enumerate(runs)], 0)
+                    both[: b1 - b0, 0] = overall
+                    both[: b1 - b0, 1:] = feat
+                both_all = coll.all_gather(both)
+                merged = torch.cat([both_all[r, : b - a] for r, (a, b) in enumerate(runs)], 0)
+                overall, feat = merged[:, 0].contiguous(), merged[:, 1:]
             if can_stop:
                 # The per-batch errors start their way to the host, the lifts of the NEXT super-batch
                 # are issued behind them, and only then does the host wait: the stop test (the only
