@@ -329,7 +329,7 @@ def run_gpu(args):
                              "overall_error": float(last["res"].overall_error)},
         }
         if world == 1 and not args.no_cpu:
-            out["cpu_baseline"] = cpu_baseline(sample_perms_per_core=256)
+            out["cpu_baseline"] = cpu_baseline(sample_perms_per_core=1024)
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -398,7 +398,7 @@ def run_reference(args):
     steps, warm = args.steps, args.warmup
     vals = []
     for i in range(warm + steps):
-        b = cpu_baseline(sample_perms_per_core=64)
+        b = cpu_baseline(sample_perms_per_core=256)
         if i >= warm:
             vals.append(b)
     v = float(np.mean([b["value"] for b in vals]))
