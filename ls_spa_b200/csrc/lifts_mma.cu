@@ -540,16 +540,16 @@ __global__ void __launch_bounds__(256, MINB) lifts_mma_kernel(LiftParams2 a) {
             if (q >= 2) P += up;
             const double ra = r_in - (P - sl) - t0;
             const double rb = r_in - P;
-            double d0 = ra * ra, d1 = rb * rb;
-#pragma unroll
-            for (int o = 4; o < 32; o <<= 1) {
-              d0 += __shfl_xor_sync(kFull, d0, o);
-              d1 += __shfl_xor_sync(kFull, d1, o);
-            }
-            if (c == 0) {
-              const int k0 = 8 * J + 2 * q;
-              if (k0 < p) wc[k0] += d0;          // wc[k] collects cost_{k+1}
-              if (k0 + 1 < p) wc[k0 + 1] += d1;
+            // row sums of both squares with three shuffles: the first round hands each value to one
+            // half of the lanes; even rows end up with the first column's total, odd rows with the second's
+            const double d0 = ra * ra, d1 = rb * rb;
+            const bool odd = (c & 1) != 0;
+            double tot = (odd ? d1 : d0) + __shfl_xor_sync(kFull, odd ? d0 : d1, 4);
+            tot += __shfl_xor_sync(kFull, tot, 8);
+            tot += __shfl_xor_sync(kFull, tot, 16);
+            if (c < 2) {
+              const int k0 = 8 * J + 2 * q + c;
+              if (k0 < p) wc[k0] += tot;          // wc[k] collects cost_{k+1}
             }
             r_in -= __shfl_sync(kFull, P, 3, 4);
             m0 = -m0;
