@@ -150,16 +150,14 @@ __device__ __forceinline__ void elim_step(double (&xr)[RT][2], double &r_in, dou
   double m0 = 0.0, m1 = 0.0;  // C layout (row, column 2q+e of the tile)
   dmma(m0, m1, xr[J][0], dv.x);
   dmma(m0, m1, xr[J][1], dv.y);
+  // residual of row c after each of the 8 columns of the tile as one more product:
+  // R[m][n] = r_in[m] - sum_{k <= n} M[m][k] c_k, i.e. M times the upper-triangular matrix whose
+  // row k holds c_k (B fragment: k = 2q + e, n = c); plain fp64 arithmetic would queue behind the
+  // DMMAs of the other warps operation by operation
   const double2 cv = *reinterpret_cast<const double2 *>(cvec + 8 * J + 2 * q);
-  const double t0 = m0 * cv.x, t1 = m1 * cv.y;
-  const double sl = t0 + t1;
-  double P = sl;
-  double up = __shfl_up_sync(kFull, P, 1, 4);
-  if (q >= 1) P += up;
-  up = __shfl_up_sync(kFull, P, 2, 4);
-  if (q >= 2) P += up;
-  const double ra = r_in - (P - sl) - t0;
-  const double rb = r_in - P;
+  double ra = r_in, rb = r_in;
+  dmma(ra, rb, -m0, (2 * q <= c) ? cv.x : 0.0);
+  dmma(ra, rb, -m1, (2 * q + 1 <= c) ? cv.y : 0.0);
   // sum of the squares over the 8 rows (lane bits 2..4) of both values with three shuffles: the
   // first round hands each value to one half of the lanes; even rows end up with the total of the
   // first column, odd rows with that of the second
@@ -172,7 +170,7 @@ __device__ __forceinline__ void elim_step(double (&xr)[RT][2], double &r_in, dou
     const int k0 = 8 * J + 2 * q + c;
     if (k0 < p) wc[k0] += tot;          // wc[k] collects cost_{k+1}
   }
-  r_in -= __shfl_sync(kFull, P, 3, 4);
+  r_in = __shfl_sync(kFull, rb, 3, 4);   // residual after the last column of the tile
   m0 = -m0;
   m1 = -m1;
 #pragma unroll
