@@ -530,16 +530,12 @@ __global__ void __launch_bounds__(256, MINB) lifts_mma_kernel(LiftParams2 a) {
             dmma(m0, m1, xr[J][0], dv.x);
             dmma(m0, m1, xr[J][1], dv.y);
             // running test residual of this row after each of the 8 columns of the panel
+            // residual of row c after each of the 8 columns of the panel as one more product with the
+            // upper-triangular matrix whose row k holds c_k (B fragment: k = 2q + e, n = c)
             const double2 cv = *reinterpret_cast<const double2 *>(cvec + 8 * J + 2 * q);
-            const double t0 = m0 * cv.x, t1 = m1 * cv.y;
-            const double sl = t0 + t1;
-            double P = sl;
-            double up = __shfl_up_sync(kFull, P, 1, 4);
-            if (q >= 1) P += up;
-            up = __shfl_up_sync(kFull, P, 2, 4);
-            if (q >= 2) P += up;
-            const double ra = r_in - (P - sl) - t0;
-            const double rb = r_in - P;
+            double ra = r_in, rb = r_in;
+            dmma(ra, rb, -m0, (2 * q <= c) ? cv.x : 0.0);
+            dmma(ra, rb, -m1, (2 * q + 1 <= c) ? cv.y : 0.0);
             // row sums of both squares with three shuffles: the first round hands each value to one
             // half of the lanes; even rows end up with the first column's total, odd rows with the second's
             const double d0 = ra * ra, d1 = rb * rb;
@@ -551,7 +547,7 @@ __global__ void __launch_bounds__(256, MINB) lifts_mma_kernel(LiftParams2 a) {
               const int k0 = 8 * J + 2 * q + c;
               if (k0 < p) wc[k0] += tot;          // wc[k] collects cost_{k+1}
             }
-            r_in -= __shfl_sync(kFull, P, 3, 4);
+            r_in = __shfl_sync(kFull, rb, 3, 4);   // residual after the last column of the panel
             m0 = -m0;
             m1 = -m1;
 #pragma unroll
