@@ -198,23 +198,27 @@ def lifts_one(R_tr, c_tr, R_te, c_te, ynsq, perm):
             for e in range(2):
                 M = mma(M, xr[J][:, e], dv[:, e])
             cv = np.stack([cvec[8 * J + 2 * Q_], cvec[8 * J + 2 * Q_ + 1]], 1)
-            t0, t1 = M[:, 0] * cv[:, 0], M[:, 1] * cv[:, 1]
-            sl = t0 + t1
-            P = np.zeros(32)                                     # inclusive prefix over the quad
-            for l in range(32):
-                P[l] = sl[(l & ~3):l + 1].sum()
-            ra = r_in - (P - sl) - t0
-            rb = r_in - P
-            d = np.stack([ra * ra, rb * rb], 1)
+            # residuals after each of the 8 columns as one more product: R = r_in 1^T - M Tc with
+            # Tc[k][n] = c_k for k <= n (B fragment of k-step e: k = 2q + e, n = c)
+            R = np.stack([r_in, r_in], 1)
             for e in range(2):
-                tot = np.zeros(32)
-                for l in range(32):                              # sum over the 8 rows (same q)
-                    tot[l] = d[(l & 3)::4, e].sum()
-                for qq in range(4):                              # lanes 0..3 write
-                    k = 8 * J + 2 * qq + e
+                bfrag = np.where(2 * Q_ + e <= C_, cv[:, e], 0.0)
+                R = mma(R, -M[:, e], bfrag)
+            d = R * R
+            # row sums of both squares with three shuffles: round 1 (xor 4) hands column e to the
+            # lanes with (c & 1) == e, rounds 2 and 3 (xor 8, 16) finish the sum over the 8 rows
+            odd = (C_ & 1) != 0
+            keep = np.where(odd, d[:, 1], d[:, 0])
+            send = np.where(odd, d[:, 0], d[:, 1])
+            tot = keep + send[LANES ^ 4]
+            tot = tot + tot[LANES ^ 8]
+            tot = tot + tot[LANES ^ 16]
+            for l in range(32):
+                if C_[l] < 2:                                    # lanes of rows 0 and 1 write
+                    k = 8 * J + 2 * Q_[l] + C_[l]
                     if k < p:
-                        cost[k + 1] += tot[qq]
-            r_in = r_in - np.array([P[(l & ~3) + 3] for l in range(32)])
+                        cost[k + 1] += tot[l]
+            r_in = R[(LANES & ~3) + 3, 1]                        # residual after the last column
             for L in range(J + 1, RT):
                 rt = ld_tile(A, 8 * J, 8 * L)
                 for e in range(2):

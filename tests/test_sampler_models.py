@@ -98,3 +98,22 @@ def test_permutohedron_model():
             perm, _ = dm.permutohedron_perm(p, sv, shift, eng.bits, k)
             bad += not np.array_equal(perm, g[key][k])
         assert bad == 0
+
+
+@pytest.mark.parametrize("p", [9, 20, 29])
+def test_lane_level_lift_model_matches_oracle(p):
+    """tests/lifts_v2_model.py mirrors the DMMA lift kernel lane by lane (fragments, tile accesses,
+    C->A reuse, the residual product with the triangular c matrix, the three-shuffle row sums);
+    it must reproduce the oracle's lifts."""
+    import lifts_v2_model as lm
+    from oracle import lsspa_oracle as lo
+    from oracle import samplers_oracle as so
+    rng = np.random.default_rng(p)
+    Xtr, Xte, ytr, yte, _, _ = so.gen_data(rng, p, 40 * p, 30 * p)
+    R_tr, R_te, c_tr, c_te = lo.reduce_data(Xtr, Xte, ytr, yte, 1e-3)
+    ynsq = float(yte @ yte)
+    for _ in range(2):
+        perm = rng.permutation(p)
+        got = lm.lifts_one(R_tr, c_tr, R_te, c_te, ynsq, perm)
+        want = lo.square_shapley(R_tr, R_te, c_tr, c_te, ynsq, perm)
+        assert np.max(np.abs(got - want)) < 1e-12 * max(np.max(np.abs(want)), 1e-300) + 1e-15
