@@ -1,13 +1,14 @@
 """Ground-truth experiment on the medium shape (the role of the reference's
 experiments/ground_truth_medium.py:74-119 and notebooks/medium_experiment.py:340-603, without the
-plots): data from the `gen_data` recipe, a ground truth from 2^19 antithetic pairs of the PCG64
-stream, then every sampler (random, permutohedron, argsort) with and without antithetic pairs
-for 2^13 evaluations, and the true error ||attribution_history[k] - ground truth||_2 against the
-number of samples next to the estimated error.  Everything runs through ls_spa_b200.ls_spa on the
-GPU; results go to experiments/data/ as .npy / .json.
+plots): correlated synthetic data drawn on the device after that recipe, a ground truth from 2^19
+antithetic pairs of the PCG64 stream, then every sampler (random, permutohedron, argsort) with and
+without antithetic pairs for 2^13 evaluations, and the true error
+||attribution_history[k] - ground truth||_2 against the number of samples next to the estimated
+error.  Everything runs through ls_spa_b200.ls_spa on the GPU; results go to experiments/data/ as
+.npy / .json.
 
-    python experiments/ground_truth_medium.py [--p 100] [--n 100000] [--m 100000] [--gt-log2 19]
-                                              [--samples-log2 13] [--data numpy|device]
+    python experiments/ground_truth_b200.py [--p 100] [--n 100000] [--m 100000] [--gt-log2 19]
+                                            [--samples-log2 13]
 """
 import argparse
 import json
@@ -26,30 +27,10 @@ STN_RATIO = 5.0
 CONDITIONING = 20.0
 
 
-def gen_data_numpy(rng, p, n, m):
-    """The reference recipe (experiments/ground_truth_medium.py:74-109), host numpy."""
-    A = rng.standard_normal((p, max(int(p / CONDITIONING), 1)))
-    cov = A @ A.T + np.eye(p)
-    v = np.sqrt(np.diag(cov))
-    cov = cov / np.outer(v, v)
-    Xtr = rng.multivariate_normal(np.zeros(p), cov, (n,), method="svd")
-    Xte = rng.multivariate_normal(np.zeros(p), cov, (m,), method="svd")
-    theta = np.zeros(p)
-    k = max((p + 1) // 10, 1)
-    theta[:k] = 2.0
-    theta = rng.permutation(theta)
-    std = np.sqrt(np.sum(np.diag(cov) * theta ** 2) / STN_RATIO)
-    ytr = Xtr @ theta + std * rng.standard_normal(n)
-    mu, ymu = Xtr.mean(0, keepdims=True), None
-    Xtr = Xtr - mu
-    ymu = ytr.mean()
-    ytr = ytr - ymu
-    yte = Xte @ theta + std * rng.standard_normal(m)
-    return Xtr, Xte - mu, ytr, yte - ymu
-
-
 def gen_data_device(seed, p, n, m, dev):
-    """The same recipe drawn on the device (torch generators): nothing crosses PCIe."""
+    """Factor-model covariance with unit diagonal, a tenth of the features relevant, signal-to-noise
+    ratio 5 (the reference's recipe), drawn on the device with torch generators: nothing crosses
+    PCIe."""
     g = torch.Generator(device=dev).manual_seed(seed)
     rn = lambda *s: torch.randn(*s, generator=g, device=dev, dtype=torch.float64)
     A = rn(p, max(int(p / CONDITIONING), 1))
@@ -69,17 +50,15 @@ def gen_data_device(seed, p, n, m, dev):
     return Xtr - mu, Xte - mu, ytr - ymu, yte - ymu
 
 
-def run(p, n, m, gt_log2, samples_log2, data, seed=42, out_dir=None, quiet=False):
+def run(p, n, m, gt_log2, samples_log2, seed=42, out_dir=None, quiet=False):
     dev = torch.device("cuda")
     rng = np.random.default_rng(seed)
     t0 = time.perf_counter()
-    if data == "numpy":
-        Xtr, Xte, ytr, yte = gen_data_numpy(rng, p, n, m)
-    else:
-        Xtr, Xte, ytr, yte = gen_data_device(seed, p, n, m, dev)
+    Xtr, Xte, ytr, yte = gen_data_device(seed, p, n, m, dev)
     t_data = time.perf_counter() - t0
 
-    # ground truth: the permutation stream continues the data generator, as in the reference script
+    # ground truth: the device continues the PCG64 stream of this numpy generator (the reference script
+    # draws its permutations from the generator that made the data)
     t0 = time.perf_counter()
     gt = L.ls_spa(Xtr, Xte, ytr, yte, max_samples=2 ** gt_log2, batch_size=2 ** 10, tolerance=0.0, seed=rng,
                   antithetical=True)
@@ -133,6 +112,5 @@ if __name__ == "__main__":
     ap.add_argument("--m", type=int, default=100_000)
     ap.add_argument("--gt-log2", type=int, default=19)
     ap.add_argument("--samples-log2", type=int, default=13)
-    ap.add_argument("--data", choices=("numpy", "device"), default="device")
     a = ap.parse_args()
-    run(a.p, a.n, a.m, a.gt_log2, a.samples_log2, a.data, out_dir=os.path.join(ROOT, "experiments", "data"))
+    run(a.p, a.n, a.m, a.gt_log2, a.samples_log2, out_dir=os.path.join(ROOT, "experiments", "data"))

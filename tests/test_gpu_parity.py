@@ -530,13 +530,13 @@ def test_generator_continuation(T, L):
 
 
 def test_ground_truth_experiment_script(T):
-    """experiments/ground_truth_medium.py on a small shape: the true error of every
+    """experiments/ground_truth_b200.py on a small shape: the true error of every
     sampler falls with the number of samples and the antithetic quasi-Monte-Carlo samplers beat
     plain Monte Carlo at equal cost."""
     import os, sys
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "experiments"))
-    import ground_truth_medium as gtm
-    out = gtm.run(p=20, n=4000, m=3000, gt_log2=14, samples_log2=10, data="device", quiet=True)
+    import ground_truth_b200 as gtm
+    out = gtm.run(p=20, n=4000, m=3000, gt_log2=14, samples_log2=10, quiet=True)
     assert out["ground_truth_error_estimate"] < 2e-3
     finals = {k: c["final_true_error"] for k, c in out["curves"].items()}
     for k, c in out["curves"].items():
