@@ -107,3 +107,22 @@ def test_explicit_source_on_cpu_tensors():
     assert np.array_equal(torch.cat([a, b]).numpy(), np.array(perms))
     src = ExplicitSource(6, np.array(perms), torch.device("cpu"))
     assert src.total == 7 and src.take(100).shape == (7, 6)
+
+
+def test_superbatch_plan():
+    """Jobs that can stop early ramp their super-batches up (2048 samples per rank, x4 per round);
+    jobs that cannot (tolerance 0 or no error estimates) start at full size; the plan is what the
+    split route prepares its factorisations against, so it must be a pure function of the config."""
+    from ls_spa_b200.engine import JobConfig, superbatch_geometry, target_samples
+    base = dict(p=100, batch_size=128, max_samples=65536, seed=1, antithetical=True, return_history=False)
+    full = target_samples(100)
+    limit, bs, size = superbatch_geometry(JobConfig(tolerance=1e-4, estimate_errors=True, **base), 1, None)
+    assert (limit, bs) == (65536, 128)
+    assert [size(i) for i in range(4)] == [2048, 8192, full, full]
+    assert [size(i) for i in range(3)] == [2048, 8192, full]          # calling it again changes nothing
+    _, _, size8 = superbatch_geometry(JobConfig(tolerance=1e-4, estimate_errors=True, **base), 8, None)
+    assert [size8(i) for i in range(3)] == [8 * 2048, 8 * 8192, 8 * full]
+    _, _, flat = superbatch_geometry(JobConfig(tolerance=0.0, estimate_errors=True, **base), 1, None)
+    assert flat(0) == flat(5) == full
+    limit, bs, nosplit = superbatch_geometry(JobConfig(tolerance=1e-2, estimate_errors=False, **base), 1, 5000)
+    assert limit == 5000 and bs == 1024 and nosplit(0) == full
