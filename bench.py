@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Benchmark of the LS-SPA hot path (BASELINE.json metric: permutations/sec at p=100, N=M=1e6).
+"""Benchmark of the LS-SPA hot path (BASELINE.json metric: permutations/sec and time-to-tolerance
+at p=100, N=M=1e6, 1/2/4/8 B200 vs host CPU).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
@@ -11,9 +12,19 @@ epilogue.  `value` = permutations evaluated by all ranks / max-over-ranks device
 inputs resident in HBM; `e2e` = the same job through ls_spa_b200.ls_spa() from pinned host
 buffers (host->device copies and the result read-back inside the timed region).
 
+`time_to_tolerance` (the second half of the metric) runs the same job with a sample budget large
+enough that the error estimate, not the budget, stops it, at tolerance 1e-2, 1e-3 and the
+configuration's 1e-4; under torchrun that job is STRONG-scaled (fixed tolerance, rows and samples
+sharded), and the CPU figure next to it is samples-needed / CPU rate + the CPU reduction.
+
 Multi-GPU: rows of the reduction are sharded (N=10^6 in total, fixed), permutations are
-weak-scaled (2^16 samples per GPU).  `--impl reference` times the numpy oracle port of the
-reference (same LAPACK calls as the reference) on all host cores, on a bounded sample.
+weak-scaled (2^16 samples per GPU).  Before timing, a small fixed job is compared on every rank
+with the numpy oracle (`result_check.multi_gpu_parity`).
+
+`--impl reference` / `cpu_baseline` time the numpy oracle port of the reference (the same LAPACK
+calls as the reference, which is pure Python and cannot travel to the GPU box) on the host cores,
+with BLAS threads pinned explicitly in child processes, so the numbers do not depend on the
+OMP_NUM_THREADS=1 that torchrun exports.
 """
 
 from __future__ import annotations
@@ -40,6 +51,8 @@ BATCHES_PER_GPU = 512          # 2^16 antithetic samples = 2^17 permutation eval
 TOL = 1e-4
 SEED = 42
 FLOP_PER_PERM = 7.0 / 3.0 * P ** 3   # 4/3 p^3 Householder + p^3 triangular solve
+TTT_BATCHES = 1 << 17          # sample budget of the time-to-tolerance jobs: 2^24 pairs (never reached)
+METRIC = "permutations/sec (LS-SPA, p=100, N=M=1e6 rows, reduction + permutohedron samples + estimator)"
 
 
 # --------------------------------------------------------------------------- helpers
@@ -53,17 +66,19 @@ def read_peaks():
     return peaks
 
 
-def lifts_dram_bytes_per_perm(route=None):
-    """DRAM bytes (read + write) per permutation evaluation of the lift kernel, from the committed
-    `ncu --set full` capture of the kernel of that route (profiles/r01_lifts*_ncu_summary.json);
-    None if absent."""
-    name = "r01_lifts_chol_ncu_summary.json" if route == "cholesky" else "r01_lifts_ncu_summary.json"
-    try:
-        with open(os.path.join(ROOT, "profiles", name)) as f:
-            d = json.load(f)
-        return float(d["dram_bytes_per_launch"]) / float(d["permutation_evaluations_per_launch"])
-    except Exception:
-        return None
+def ncu_capture(route):
+    """(dram bytes per permutation evaluation, file) of the lift kernel of that route from the newest
+    committed `ncu --set full` capture (profiles/r0*_lifts*_ncu_summary.json); (None, None) if absent."""
+    names = (["r02_lifts_chol_ncu_summary.json", "r01_lifts_chol_ncu_summary.json"] if route == "cholesky"
+             else ["r02_lifts_ncu_summary.json", "r01_lifts_ncu_summary.json"])
+    for name in names:
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                d = json.load(f)
+            return float(d["dram_bytes_per_launch"]) / float(d["permutation_evaluations_per_launch"]), name
+        except Exception:
+            continue
+    return None, None
 
 
 def fp64_peak_tflops():
@@ -145,27 +160,90 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- GPU arm
-def synth_on_device(torch, dev, rows_train, rows_test, seed):
+def synth_on_device(torch, dev, p, rows_train, rows_test, seed, dist=None, n_train_total=None):
     """Medium-experiment recipe (reference experiments/ground_truth_medium.py:74-106) drawn on
-    the device: unit-diagonal covariance A A^T + I with p/20 latent factors, (p+1)//10 active
-    coefficients equal to 2, SNR 5; centred with the train means."""
+    the device: unit-diagonal covariance A A^T + I with max(p/20, 1) latent factors, (p+1)//10 active
+    coefficients equal to 2, SNR 5; centred with the TRAIN means (of all ranks' rows when sharded)."""
     g = torch.Generator(device=dev).manual_seed(seed)
     rn = lambda *s: torch.randn(*s, generator=g, device=dev, dtype=torch.float64)
-    A = torch.randn(P, P // 20, generator=torch.Generator().manual_seed(1234), dtype=torch.float64).to(dev)
-    cov = A @ A.T + torch.eye(P, device=dev, dtype=torch.float64)
+    A = torch.randn(p, max(p // 20, 1), generator=torch.Generator().manual_seed(1234), dtype=torch.float64).to(dev)
+    cov = A @ A.T + torch.eye(p, device=dev, dtype=torch.float64)
     d = cov.diagonal().sqrt()
     cov = cov / d.outer(d)
     Lc = torch.linalg.cholesky(cov)
-    theta = torch.zeros(P, dtype=torch.float64, device=dev)
-    theta[torch.randperm(P, generator=torch.Generator().manual_seed(99))[: (P + 1) // 10].to(dev)] = 2.0
+    theta = torch.zeros(p, dtype=torch.float64, device=dev)
+    theta[torch.randperm(p, generator=torch.Generator().manual_seed(99))[: max((p + 1) // 10, 1)].to(dev)] = 2.0
     std = float(torch.sqrt((cov.diagonal() * theta ** 2).sum() / 5.0))
-    Xtr = rn(rows_train, P) @ Lc.T
+    Xtr = rn(rows_train, p) @ Lc.T
     ytr = Xtr @ theta + std * rn(rows_train)
-    Xte = rn(rows_test, P) @ Lc.T
+    Xte = rn(rows_test, p) @ Lc.T
     yte = Xte @ theta + std * rn(rows_test)
-    # the driver centres with the train means; a per-shard mean is close enough for a benchmark
-    mu, ymu = Xtr.mean(0, keepdim=True), ytr.mean()
+    sums = torch.cat([Xtr.sum(0), ytr.sum().reshape(1)])
+    total = float(rows_train)
+    if dist is not None:
+        dist.all_reduce(sums)
+        total = float(n_train_total)
+    mu, ymu = (sums[:p] / total).unsqueeze(0), sums[p] / total
     return Xtr - mu, Xte - mu, ytr - ymu, yte - ymu
+
+
+def multi_gpu_parity(L, torch, dist, dev):
+    """One small fixed job (p=40, 384 antithetic samples, tolerance 0) on every rank against the numpy
+    oracle on the same permutohedron stream: attribution, theta, r_squared, attribution history."""
+    from oracle import lsspa_oracle as lo
+    from oracle import samplers_oracle as so
+    Xtr, Xte, ytr, yte, _, _ = so.gen_data(np.random.default_rng(11), 40, 3000, 2500)
+    got = L.ls_spa(Xtr, Xte, ytr, yte, reg=1e-3, method="permutohedron", batch_size=16, num_batches=24,
+                   tolerance=0.0, seed=5, antithetical=True, return_history=True)
+    perms = so.perms_permutohedron(40, 384, 5)[0]
+    want = lo.ls_spa_reference_loop(Xtr, Xte, ytr, yte, reg=1e-3, perms=list(perms), tolerance=0.0, batch_size=16,
+                                    antithetical=True, return_attribution_history=True)
+    sc = lambda a, b: float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / np.max(np.abs(np.asarray(b))))
+    errs = [sc(got.attribution, want.attribution), sc(got.theta, want.theta),
+            abs(float(got.r_squared) - float(want.r_squared)), sc(got.attribution_history, want.attribution_history)]
+    shapes_ok = got.error_history.shape == want.error_history.shape
+    worst = torch.tensor([max(errs), 0.0 if shapes_ok else 1.0], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+    # every rank must hold bit-identical results (replicated estimator state)
+    same = torch.from_numpy(np.ascontiguousarray(got.attribution)).to(dev)
+    lo_, hi_ = same.clone(), same.clone()
+    if dist is not None:
+        dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+    return {"job": "p=40, N=3000, M=2500, reg=1e-3, permutohedron, 24 batches x 16 antithetic samples, tolerance 0",
+            "checked": "attribution, theta, r_squared, attribution_history vs the numpy oracle on every rank",
+            "max_scaled_err_over_ranks": float(worst[0].item()), "tolerance": 1e-9,
+            "error_history_shape_ok": bool(worst[1].item() == 0.0),
+            "ranks_bit_identical": bool(torch.equal(lo_, hi_)),
+            "ok": bool(worst[0].item() < 1e-9 and worst[1].item() == 0.0 and torch.equal(lo_, hi_))}
+
+
+def side_configs(L, torch, dev):
+    """Throughput of the other BASELINE.json configurations on one GPU (device-resident synthetic
+    inputs, wall clock around ls_spa() after one warm-up call); parity of each is a -m gpu test."""
+    out = {}
+
+    def run(tag, note, p, n, perms, **kw):
+        Xtr, Xte, ytr, yte = synth_on_device(torch, dev, p, n, n, 77)
+        L.ls_spa(Xtr, Xte, ytr, yte, **kw)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        r = L.ls_spa(Xtr, Xte, ytr, yte, **kw)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        out[tag] = {"workload": note, "seconds": dt, "permutations": perms, "permutations_per_s": perms / dt,
+                    "sum_attribution_minus_r2": float(abs(r.attribution.sum() - r.r_squared)),
+                    "overall_error": float(r.overall_error)}
+        del Xtr, Xte, ytr, yte
+        torch.cuda.empty_cache()
+
+    run("C2", "p=10, N=M=1e5, method=exact (all 10! = 3628800 permutations)", 10, 100_000, 3_628_800, method="exact")
+    run("C3", "p=100, N=M=1e5, method=argsort, 2^7 x 2^7 samples, no antithetic pairs", 100, 100_000, 1 << 14,
+        method="argsort", batch_size=128, num_batches=128, tolerance=0.0, antithetical=False)
+    run("C5_reduced", "p=1000, N=M=1e5 (C5 has 1e6 rows on 8 GPUs), method=random, 2^10 permutations, no antithetic pairs",
+        1000, 100_000, 1 << 10, method="random", batch_size=128, num_batches=8, tolerance=0.0, antithetical=False)
+    return out
 
 
 def run_gpu(args):
@@ -193,9 +271,12 @@ def run_gpu(args):
     import ls_spa_b200 as L
     from ls_spa_b200 import engine, ops
 
+    parity = multi_gpu_parity(L, torch, dist if world > 1 else None, dev) if world > 1 else None
+
     rows_tr = N_ROWS // world + (1 if rank < N_ROWS % world else 0)
     rows_te = M_ROWS // world + (1 if rank < M_ROWS % world else 0)
-    Xtr, Xte, ytr, yte = synth_on_device(torch, dev, rows_tr, rows_te, 1000 + rank)
+    Xtr, Xte, ytr, yte = synth_on_device(torch, dev, P, rows_tr, rows_te, 1000 + rank,
+                                         dist if world > 1 else None, N_ROWS)
     num_batches = BATCHES_PER_GPU * world
     perms_per_step = 2 * BATCH * num_batches          # antithetic pair = 2 evaluations
     kw = dict(reg=REG, method="permutohedron", batch_size=BATCH, num_batches=num_batches, tolerance=TOL,
@@ -242,11 +323,13 @@ def run_gpu(args):
     ms_step = ms_total / args.steps
     value = perms_per_step / (ms_step * 1e-3)
 
-    # stand-alone pass over the reduction (HBM-bound stage) for its own roofline line
+    # stand-alone pass over the reduction for its own roofline line (this rank's rows, collectives included)
     backend, coll = engine.CudaBackend(dev), engine.Collective(None)
-    red_ms = timed(lambda: engine.reduce_problem(backend, coll, Xtr, Xte, ytr, yte, REG, P,
-                                                 n_train_global=N_ROWS), 3) / 3
+    red_fn = lambda: engine.reduce_problem(backend, coll, Xtr, Xte, ytr, yte, REG, P, n_train_global=N_ROWS)
+    red_fn()
+    red_ms = timed(red_fn, 5) / 5
     red_bytes = 8.0 * (rows_tr + rows_te) * (P + 1)
+    red_flop = float(rows_tr + rows_te) * (P + 1) ** 2          # symmetric Gram count
 
     # end to end: pinned host buffers -> ls_spa() -> host results
     host = [t.cpu().pin_memory() for t in (Xtr, Xte, ytr, yte)]
@@ -268,21 +351,35 @@ def run_gpu(args):
     e2e_val = perms_per_step / float(e2e_s.item())
     r = last["e2e"]
     d2h = 8 * (r.attribution.size + r.theta.size + r.attribution_errors.size + r.error_history.size + 2)
+    # the link alone: the same pinned buffers copied once more (reported next to e2e)
+    dst = torch.empty_like(Xtr)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    dst.copy_(host[0], non_blocking=True)
+    torch.cuda.synchronize()
+    h2d_gbs = host[0].numel() * 8 / (time.perf_counter() - t0) / 1e9
+    del dst, host
 
     # time to tolerance (the second half of BASELINE.json's metric): the same job, device-resident
-    # inputs, stopped by the error estimate at the reference's default tolerance 1e-2 and at 2e-3
-    # (outside the timed region; every rank runs it, the stop decision is collective)
+    # inputs, a sample budget that is never reached (2^24 pairs), stopped by the error estimate.
+    # Strong-scaled under torchrun: the tolerance is fixed, every rank takes 1/world of each round.
     ttt = []
-    for tol in (1e-2, 2e-3):
-        kw_t = dict(kw, tolerance=tol)
+    for tol in (1e-2, 1e-3, TOL):
+        kw_t = dict(kw, tolerance=tol, num_batches=TTT_BATCHES)
         L.ls_spa(Xtr, Xte, ytr, yte, **kw_t)
         barrier()
         t0 = time.perf_counter()
         rt = L.ls_spa(Xtr, Xte, ytr, yte, **kw_t)
         barrier()
-        ttt.append({"tolerance": tol, "seconds": time.perf_counter() - t0,
-                    "estimated_error_at_stop": float(rt.overall_error),
-                    "batches": int(rt.error_history.size), "pairs": int(rt.error_history.size) * BATCH})
+        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        nb = int(rt.error_history.size)
+        ttt.append({"tolerance": tol, "seconds": float(dt.item()), "estimated_error_at_stop": float(rt.overall_error),
+                    "batches": nb, "pairs": nb * BATCH, "permutation_evaluations": 2 * nb * BATCH,
+                    "stopped_by": "tolerance" if nb < TTT_BATCHES else "budget",
+                    "scaling": "strong (fixed tolerance, rows and samples sharded over the ranks)",
+                    "timer": "wall clock around ls_spa() with device-resident inputs, max over ranks"})
 
     if rank == 0:
         peaks = read_peaks()
@@ -292,10 +389,12 @@ def run_gpu(args):
         # solve).  The Cholesky route executes 1/3 p^3 + p^3; frac_executed rates the pipe on that.
         chol = ops.LIFT_ROUTE == "cholesky"
         exec_flop = (4.0 / 3.0 if chol else 7.0 / 3.0) * P ** 3
-        bpp = lifts_dram_bytes_per_perm(ops.LIFT_ROUTE)
+        bpp, cap_file = ncu_capture(ops.LIFT_ROUTE)
         traffic = bpp * lift_perms / max(len(trace), 1) if bpp is not None else None
+        red_gbs = red_bytes / (red_ms * 1e-3) / 1e9
+        red_tf = red_flop / (red_ms * 1e-3) / 1e12
         out = {
-            "metric": "permutations/sec (LS-SPA, p=100, N=M=1e6 rows, reduction + permutohedron samples + estimator)",
+            "metric": METRIC,
             "value": value, "unit": "permutations/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -305,7 +404,9 @@ def run_gpu(args):
                        "permutations_per_step": perms_per_step, "rows_per_gpu": rows_tr,
                        "l2": "inputs (2 x 808 MB / n_gpus) larger than L2; no explicit flush"},
             "e2e": {"value": e2e_val, "unit": "permutations/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "timer": "wall clock around ls_spa() incl. H2D/D2H, max over ranks"},
+                    "d2h_bytes_per_step": d2h, "timer": "wall clock around ls_spa() incl. H2D/D2H, max over ranks",
+                    "h2d_link_gbs_measured": h2d_gbs,
+                    "link_floor_permutations_per_s": perms_per_step / (h2d / (h2d_gbs * 1e9))},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "pipe": "fp64 (DFMA/DMMA share one pipe; tcgen05 has no fp64)",
                          "kernel": "lifts_chol_kernel" if chol else "lifts_mma_kernel",
@@ -314,28 +415,48 @@ def run_gpu(args):
                          "executed_flop_per_permutation": exec_flop,
                          "frac_executed": (ach * exec_flop / FLOP_PER_PERM) / fp64_peak if fp64_peak else None,
                          "traffic": traffic,
-                         "traffic_note": "dram read+write bytes per launch from the committed ncu --set full capture, "
-                                         "scaled to this launch size; algorithmic HBM bytes/launch = 1200 B x evaluations / 2",
+                         "traffic_note": f"dram read+write bytes per launch from the committed ncu --set full capture "
+                                         f"profiles/{cap_file}, scaled to this launch size (not re-measured in this run); "
+                                         f"algorithmic HBM bytes/launch = 1200 B x evaluations / 2",
                          "peak_source": fp64_src, "kernel_ms_per_step": lift_ms / args.steps,
                          "kernel_share_of_step": lift_ms / ms_total,
                          "algorithmic_flop_per_permutation": FLOP_PER_PERM},
-            "roofline_reduce": {"bound": "hbm", "kernel": "gram_rows_kernel (CholeskyQR, second pass only when cond > 1e3) + chol_factor_kernel",
-                                "achieved": red_bytes / (red_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
-                                "unit": "GB/s", "frac": red_bytes / (red_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                                "peak_source": peaks["which"], "ms": red_ms, "algorithmic_bytes": red_bytes},
+            # intensity (p+1)/8 = 12.6 flop/B is above the FP64 ridge (~5.7 flop/B), so the
+            # binding roof of the reduction at p=100 is the FP64 pipe; both fractions are reported
+            "roofline_reduce": {"bound": "tensor", "binding": "fp64 pipe (12.6 flop/B > ridge 5.7 flop/B)",
+                                "kernel": "gram_tma_kernel (CholeskyQR Gram pass, DMMA) + gram_tail_kernel",
+                                "ms": red_ms, "algorithmic_bytes": red_bytes, "algorithmic_flop": red_flop,
+                                "achieved": red_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                                "frac": red_tf / fp64_peak if fp64_peak else None,
+                                "achieved_gbs": red_gbs, "peak_gbs": peaks["hbm_gbs"], "frac_hbm": red_gbs / peaks["hbm_gbs"],
+                                "peak_source": f"fp64: {fp64_src}; hbm: MEASURED_PEAKS.json ({peaks['which']})",
+                                "rows_this_rank": rows_tr + rows_te},
             "clocks": clocks,
             "time_to_tolerance": ttt,
             "result_check": {"sum_attribution_minus_r2": float(abs(last["res"].attribution.sum() - last["res"].r_squared)),
-                             "overall_error": float(last["res"].overall_error)},
+                             "overall_error": float(last["res"].overall_error),
+                             "multi_gpu_parity": parity},
         }
         if world == 1 and not args.no_cpu:
-            out["cpu_baseline"] = cpu_baseline(sample_perms_per_core=1024)
+            try:
+                out["configs"] = side_configs(L, torch, dev)
+            except Exception as exc:      # a side line must never cost the headline
+                out["configs"] = {"error": repr(exc)}
+            out["cpu_baseline"] = cpu_baseline(sample_perms_per_core=1024, full=True)
+            cb = out["cpu_baseline"]
+            for t in ttt:
+                t["cpu_seconds_extrapolated"] = (cb["reduce_data_s"] + t["permutation_evaluations"]
+                                                 / cb["loop_only_permutations_per_s"])
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
 # --------------------------------------------------------------------------- CPU arm
+def host_cores():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
 def _cpu_worker(job):
     from threadpoolctl import threadpool_limits
     from oracle import lsspa_oracle as lo
@@ -346,48 +467,125 @@ def _cpu_worker(job):
         return time.perf_counter() - t0
 
 
-_CPU_CACHE = {}
+def cheap_data(rows, seed=SEED):
+    """The medium-experiment recipe without its SVD-based multivariate_normal (too slow at 10^6 rows):
+    X = Z chol(cov)^T.  Same distribution, used only for timing the CPU path."""
+    rng = np.random.default_rng(seed)
+    a = rng.standard_normal((P, P // 20))
+    cov = a @ a.T + np.eye(P)
+    v = np.sqrt(np.diag(cov))
+    Lc = np.linalg.cholesky(cov / np.outer(v, v))
+    theta = np.zeros(P)
+    theta[rng.permutation(P)[: (P + 1) // 10]] = 2.0
+    std = np.sqrt(np.sum(theta ** 2) / 5.0)
+    out = []
+    for _ in range(2):
+        X = rng.standard_normal((rows, P)) @ Lc.T
+        out.append((X, X @ theta + std * rng.standard_normal(rows)))
+    (Xtr, ytr), (Xte, yte) = out
+    mu, ymu = Xtr.mean(0, keepdims=True), ytr.mean()
+    return Xtr - mu, Xte - mu, ytr - ymu, yte - ymu
 
 
-def cpu_data(rows):
-    if rows not in _CPU_CACHE:
-        from oracle import samplers_oracle as so
-        rng = np.random.default_rng(SEED)
-        _CPU_CACHE[rows] = so.gen_data(rng, P, rows, rows)[:4]
-    return _CPU_CACHE[rows]
-
-
-def cpu_baseline(sample_perms_per_core=256):
-    """Oracle port (same LAPACK calls as the reference) on all host cores: P worker processes x 1
-    BLAS thread over slices of the same permutohedron stream; reduce_data timed on a row sample
-    with default BLAS threads and scaled linearly to 10^6 rows."""
-    import multiprocessing as mp
+def child_main(args):
+    """Body of the child processes of the CPU arm (BLAS threads were pinned through the environment
+    before numpy was imported).  Prints one JSON line."""
     from oracle import lsspa_oracle as lo
     from oracle import samplers_oracle as so
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    sample_rows = 100_000
-    Xtr, Xte, ytr, yte = cpu_data(sample_rows)
+    what, rows, count = args.child, args.child_rows, args.child_count
+    Xtr, Xte, ytr, yte = cheap_data(rows)
     t0 = time.perf_counter()
     fac = lo.reduce_data(Xtr, Xte, ytr, yte, REG)
     t_red = time.perf_counter() - t0
-    ynsq = float(yte @ yte)
+    out = {"what": what, "rows": rows, "reduce_data_s": t_red,
+           "blas_threads": os.environ.get("OPENBLAS_NUM_THREADS")}
+    if what == "loop":
+        # the reference's loop as shipped (ls_spa/ls_spa.py:196-236: square_shapley x 2, merge_sample_cov,
+        # merge_sample_mean, error_estimates every batch), explicit permutohedron stream
+        perms = so.perms_permutohedron(P, count, SEED)[0]
+        t0 = time.perf_counter()
+        res = lo.ls_spa_reference_loop(Xtr, Xte, ytr, yte, reg=REG, perms=list(perms), tolerance=0.0,
+                                       batch_size=BATCH, antithetical=True)
+        t_all = time.perf_counter() - t0
+        out.update(pairs=count, total_s=t_all, loop_s=max(t_all - t_red, 1e-9),
+                   permutations_per_s=2 * count / max(t_all - t_red, 1e-9), r_squared=float(res.r_squared))
+    elif what == "factors":
+        np.savez(args.child_out, R_tr=fac[0], R_te=fac[1], c_tr=fac[2], c_te=fac[3], ynsq=float(yte @ yte))
+    print(json.dumps(out), flush=True)
+
+
+def run_child(what, rows, count, threads, out=None, timeout=900):
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads), OPENBLAS_NUM_THREADS=str(threads),
+               MKL_NUM_THREADS=str(threads), PYTHONDONTWRITEBYTECODE="1")
+    cmd = [sys.executable, os.path.abspath(__file__), "--child", what, "--child-rows", str(rows),
+           "--child-count", str(count)] + (["--child-out", out] if out else [])
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+    if res.returncode != 0:
+        raise RuntimeError(f"cpu child {what} failed: {res.stderr[-500:]}")
+    return json.loads(res.stdout.strip().splitlines()[-1])
+
+
+_REDUCE_CACHE = {}
+
+
+def cpu_reduce(rows, cores):
+    """reduce_data of the oracle (np.linalg.qr x 2, as the reference) on `rows` train and test rows with
+    `cores` BLAS threads, in a child process; also leaves the reduced factors for the loop workers."""
+    key = (rows, cores)
+    if key not in _REDUCE_CACHE:
+        path = os.path.join("/tmp", f"lsspa_bench_factors_{os.getpid()}_{rows}.npz")
+        info = run_child("factors", rows, 0, cores, out=path)
+        z = np.load(path)
+        os.remove(path)
+        _REDUCE_CACHE[key] = (info["reduce_data_s"], tuple(z[k] for k in ("R_tr", "R_te", "c_tr", "c_te")) + (float(z["ynsq"]),))
+    return _REDUCE_CACHE[key]
+
+
+def cpu_baseline(sample_perms_per_core=256, full=True):
+    """Oracle port (same LAPACK calls as the reference) on all host cores: P worker processes x 1
+    BLAS thread over slices of the same permutohedron stream (BASELINE.md section 3, variant 3);
+    reduce_data timed ONCE at the full N=M=10^6 with all cores as BLAS threads.  With full=True also the
+    reference's loop as shipped (variants 1 and 2: default BLAS threads / 1 thread) on a short stream."""
+    import multiprocessing as mp
+    from oracle import samplers_oracle as so
+    cores = host_cores()
+    t_red, fac = cpu_reduce(N_ROWS, cores)
     perms = so.perms_permutohedron(P, sample_perms_per_core * cores, SEED)[0]
-    jobs = [(fac[0], fac[1], fac[2], fac[3], ynsq, perms[i::cores]) for i in range(cores)]
+    jobs = [fac + (perms[i::cores],) for i in range(cores)]
     with mp.get_context("fork").Pool(cores) as pool:
-        pool.map(_cpu_worker, jobs[:cores])          # spin the workers up (imports, page-in)
+        pool.map(_cpu_worker, [fac + (perms[:8],)] * cores)      # spin the workers up (imports, page-in)
         t0 = time.perf_counter()
         pool.map(_cpu_worker, jobs)
         t_loop = time.perf_counter() - t0
     evals = 2 * len(perms)                         # antithetic pairs
     loop_rate = evals / t_loop
     job_perms = 2 * BATCH * BATCHES_PER_GPU
-    t_red_full = t_red * (N_ROWS / sample_rows)
-    whole_job = job_perms / (t_red_full + job_perms / loop_rate)
-    return {"value": whole_job, "unit": "permutations/s", "cores": cores, "kind": "port",
-            "loop_only_permutations_per_s": loop_rate, "reduce_data_s_extrapolated_1e6_rows": t_red_full,
-            "sample": f"{evals} permutation evaluations (p=100, {len(perms)} antithetic permutohedron samples) "
-                      f"split over {cores} processes x 1 BLAS thread; reduce_data timed on N=M={sample_rows} rows "
-                      f"(default BLAS threads) and scaled x{N_ROWS // sample_rows}; value = 2^17 / (reduce + 2^17 / loop rate)"}
+    whole_job = job_perms / (t_red + job_perms / loop_rate)
+    out = {"value": whole_job, "unit": "permutations/s", "cores": cores, "kind": "port",
+           "loop_only_permutations_per_s": loop_rate, "reduce_data_s": t_red,
+           "reduce_data_rows": N_ROWS, "reduce_data_blas_threads": cores,
+           "host": {"cpu_count": os.cpu_count(), "affinity": cores, "numpy": np.__version__},
+           "sample": f"{evals} permutation evaluations (p=100, {len(perms)} antithetic permutohedron samples) "
+                     f"split over {cores} processes x 1 BLAS thread; reduce_data timed once at the full N=M={N_ROWS} rows "
+                     f"with {cores} BLAS threads (child process, threads pinned by environment); "
+                     f"value = 2^17 / (reduce + 2^17 / loop rate)"}
+    if full:
+        try:
+            one = run_child("loop", 10_000, 256, 1)
+            dflt = run_child("loop", 10_000, 32, cores)
+            out["as_shipped"] = {
+                "what": "the reference's own loop (square_shapley x 2 per pair, merge_sample_cov, merge_sample_mean, "
+                        "error_estimates per batch; oracle restatement of ls_spa/ls_spa.py:196-236), one process, "
+                        "N=M=10^4 rows (the loop does not depend on N)",
+                "one_blas_thread": {"permutations_per_s": one["permutations_per_s"], "pairs": one["pairs"]},
+                "default_blas_threads": {"permutations_per_s": dflt["permutations_per_s"], "pairs": dflt["pairs"],
+                                         "threads": cores},
+                "whole_job_one_thread_permutations_per_s": job_perms / (t_red + job_perms / one["permutations_per_s"]),
+                "whole_job_default_threads_permutations_per_s": job_perms / (t_red + job_perms / dflt["permutations_per_s"]),
+            }
+        except Exception as exc:
+            out["as_shipped"] = {"error": repr(exc)}
+    return out
 
 
 def run_reference(args):
@@ -398,18 +596,19 @@ def run_reference(args):
     steps, warm = args.steps, args.warmup
     vals = []
     for i in range(warm + steps):
-        b = cpu_baseline(sample_perms_per_core=256)
+        b = cpu_baseline(sample_perms_per_core=128, full=(i == warm + steps - 1))
         if i >= warm:
             vals.append(b)
     v = float(np.mean([b["value"] for b in vals]))
     b = vals[-1]
     b["value"] = v
-    out = {"impl": "reference", "metric": "permutations/sec (LS-SPA, p=100, N=M=1e6 rows, reduction + permutohedron samples + estimator)",
+    out = {"impl": "reference", "metric": METRIC,
            "value": v, "unit": "permutations/s", "n_gpus": world, "steps": steps, "warmup": warm,
            "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
            "data": "synthetic",
            "config": {"workload": "C4: p=100, N=M=10^6, reg=1e-2, permutohedron, antithetic, 2^17 permutation "
-                                  "evaluations per step (bounded sample, extrapolated; see cpu_baseline.sample)"},
+                                  "evaluations per step (each step a bounded sample of the loop; reduce_data timed once "
+                                  "at full size; see cpu_baseline.sample)"},
            "cpu_baseline": b,
            "e2e": {"value": v, "unit": "permutations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
@@ -421,9 +620,15 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline and side-configuration legs")
+    ap.add_argument("--child", default=None, help=argparse.SUPPRESS)
+    ap.add_argument("--child-rows", type=int, default=0, help=argparse.SUPPRESS)
+    ap.add_argument("--child-count", type=int, default=0, help=argparse.SUPPRESS)
+    ap.add_argument("--child-out", default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.child:
+        child_main(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_gpu(args)

@@ -122,6 +122,12 @@ LSSPA_API int lsspa_perms_sobol_argsort(int p, const uint32_t *sv, const uint32_
 LSSPA_API int lsspa_perms_permutohedron(int p, const uint32_t *sv, const uint32_t *shift, int bits,
                               uint64_t first_index, int64_t count, int32_t *perms_out, void *stream);
 
+/* Caller-supplied permutations (perms=, ls_spa/ls_spa.py:165-167,176-177: the reference does not
+ * validate them and numpy raises IndexError on a bad index): every row must be a bijection of
+ * {0..p-1}.  bad_flag (device int, zero-initialised by the caller) receives 1 + index of an
+ * offending row, 0 if all rows are valid. */
+LSSPA_API int lsspa_perms_validate(int p, const int32_t *perms, int64_t count, int *bad_flag, void *stream);
+
 /* ------------------------------------------------------------------------
  * 3. Per-permutation core             replaces square_shapley, ls_spa/ls_spa.py:256-287
  *    and the antithetic pair average, :205-208.
@@ -216,6 +222,13 @@ LSSPA_API int lsspa_estimator_quantiles(int p, double *zsq, int nown, double *ov
  * (carry_sum + sum_{r<=k} lifts[r]) / (carry_count + k + 1); carry is updated */
 LSSPA_API int lsspa_prefix_means(int p, const double *lifts, int64_t rows, double *carry_sum,
                        double carry_count, double *hist_out, void *stream);
+/* error_estimates(rng, cov) as a standalone call (ls_spa/ls_spa.py:321-341): 1024 draws of N(0, cov) for a
+ * caller-supplied positive semi-definite cov (p x p row-major) through a Cholesky factorisation that
+ * skips vanishing pivots (cov = L L^T also when cov is singular), Gaussians from the counter-based
+ * device stream keyed by `seed`.  zsq [p+1][1024] receives the squared draws (input of
+ * lsspa_estimator_quantiles with nown = 1); workspace: p*p doubles. */
+LSSPA_API int lsspa_error_draws(int p, const double *cov, uint64_t seed, double *zsq, double *workspace,
+                                void *stream);
 /* standalone merge, the device twin of merge_sample_mean / merge_sample_cov */
 LSSPA_API int lsspa_merge_moments(int p, double *mean, double *cov, double old_n, const double *new_mean,
                         const double *new_cov_or_null, double new_n, void *stream);

@@ -39,6 +39,7 @@ SIGNATURES = {
     "lsspa_perms_pcg64": (c_i32, [c_i32, vp, c_i64, vp, vp, sz, vp, vp]),
     "lsspa_perms_sobol_argsort": (c_i32, [c_i32, vp, vp, c_i32, c_u64, c_i64, vp, vp]),
     "lsspa_perms_permutohedron": (c_i32, [c_i32, vp, vp, c_i32, c_u64, c_i64, vp, vp]),
+    "lsspa_perms_validate": (c_i32, [c_i32, vp, c_i64, vp, vp]),
     "lsspa_lifts_workspace_bytes": (sz, [c_i32, c_i64]),
     "lsspa_lifts": (c_i32, [c_i32, vp, vp, vp, vp, c_f64, vp, c_i64, c_i32, vp, vp, sz, vp]),
     "lsspa_lifts_chol_supported": (c_i32, [c_i32]),
@@ -54,6 +55,7 @@ SIGNATURES = {
     "lsspa_estimator_partials": (c_i32, [c_i32, vp, vp, c_i32, c_u64, c_i32, vp, vp]),
     "lsspa_estimator_absorb": (c_i32, [vp, c_i32, c_i32, c_f64, vp, vp, c_i32, c_i32, c_i32, vp, c_i32, vp]),
     "lsspa_estimator_quantiles": (c_i32, [c_i32, vp, c_i32, vp, vp, vp]),
+    "lsspa_error_draws": (c_i32, [c_i32, vp, c_u64, vp, vp, vp]),
     "lsspa_prefix_means": (c_i32, [c_i32, vp, c_i64, vp, c_f64, vp, vp]),
     "lsspa_merge_moments": (c_i32, [c_i32, vp, vp, c_f64, vp, vp, c_f64, vp]),
     "lsspa_theta_r2_workspace_bytes": (sz, [c_i32]),

@@ -275,6 +275,9 @@ def square_shapley(X_train, X_test, y_train, y_test, y_norm_sq, perm):
     prob = ops.ReducedProblem(_to_dev(X_train, device), _to_dev(y_train, device), _to_dev(X_test, device),
                               _to_dev(y_test, device), float(y_norm_sq))
     pt = torch.as_tensor(np.asarray(perm).astype(np.int32)).reshape(1, -1).to(device)
+    if pt.shape[1] != prob.p:
+        raise ValueError("perm must have p entries")
+    ops.perms_validate(pt)
     return ops.lifts(prob, pt, False)[0].cpu().numpy()
 
 
@@ -299,23 +302,11 @@ def error_estimates(rng, cov):
     """Device twin of reference error_estimates (ls_spa/ls_spa.py:321-341): 0.95 quantiles of
     |z| per feature and of |z|_2 over 1024 draws z ~ N(0, cov).
 
-    The draws come from the device's counter-based Gaussian stream (seeded from ``rng``), and
-    cov is factorised by an eigen-decomposition on the device (it may be singular), so the
-    values agree with the reference statistically, not bit for bit."""
+    cov is factorised on the device by a Cholesky that skips vanishing pivots (it may be singular:
+    the reference falls back from Cholesky to SVD there) and the draws come from the device's
+    counter-based Gaussian stream, keyed by one integer taken from ``rng``: the values agree with the
+    reference statistically, not bit for bit."""
     device = ops.require_cuda()
-    c = _to_dev(cov, device)
-    p = c.shape[0]
     seed = int(rng.integers(0, 2 ** 63 - 1)) if hasattr(rng, "integers") else int(rng)
-    # symmetric square root rows as "samples": cov = sum_k a_k a_k^T with a_k = sqrt(w_k) v_k;
-    # feeding the p vectors a_k * sqrt(p-1) (mean 0 by pairing +/-) through the estimator
-    # reproduces N(0, cov) draws with the same kernels the main loop uses.
-    w, v = torch.linalg.eigh(c)
-    a = (v * torch.sqrt(torch.clamp(w, min=0.0))).t().contiguous()        # rows a_k
-    n = 2 * p
-    rows = torch.cat([a, -a], 0) * np.sqrt((n - 1) / 2.0)                 # mean 0, unbiased cov/n... = cov/n*n
-    est = ops.Estimator(p, seed, True, device)
-    part = est.partials(rows, [(0, n, 0)])
-    overall, feat = est.absorb(part, [0], [n], own=(0, 1), emit=True)
-    out = {"attribution_errors": feat[0].cpu().numpy(), "overall_error": float(overall[0].item())}
-    scale = np.sqrt(n)        # the estimator reports draws of N(0, unbiased_cov / n)
-    return out["attribution_errors"] * scale, out["overall_error"] * scale
+    feat, overall = ops.error_draws_quantiles(_to_dev(cov, device), seed)
+    return feat.cpu().numpy(), float(overall.item())

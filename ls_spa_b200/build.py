@@ -22,7 +22,7 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
     "--expt-relaxed-constexpr",
-]
+] + os.environ.get("LSSPA_EXTRA_NVCC_FLAGS", "").split()
 
 
 def find_nvcc() -> str:

@@ -14,6 +14,14 @@
 
 #define LSSPA_LAUNCH_CHECK() LSSPA_CUDA_TRY(cudaGetLastError())
 
+// Cycle probes of the lift kernels (tools/lifts_cycles.py): compiled in only with
+// -DLSSPA_LIFTS_TIMING (LSSPA_EXTRA_NVCC_FLAGS); the shipped library carries none.
+#ifdef LSSPA_LIFTS_TIMING
+#define LSSPA_CLOCK() clock64()
+#else
+#define LSSPA_CLOCK() 0LL
+#endif
+
 namespace lsspa {
 
 constexpr int kWarp = 32;

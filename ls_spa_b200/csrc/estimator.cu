@@ -509,6 +509,12 @@ __global__ void __launch_bounds__(256) est_quantile_kernel(int p, int nown, cons
   double v[kPerLane];
 #pragma unroll
   for (int i = 0; i < kPerLane; ++i) v[i] = zb[32 * i + lane];
+  // a NaN draw (an estimate after a single sample: 0 / sqrt(n (n-1)), the reference returns nan there
+  // too) makes the whole quantile NaN, so that it can never pass the `< tolerance` stop test
+  bool nan_row = false;
+#pragma unroll
+  for (int i = 0; i < kPerLane; ++i) nan_row |= !(v[i] == v[i]);
+  nan_row = __any_sync(kFull, nan_row);
   unsigned long long key[kPerLane];
 #pragma unroll
   for (int i = 0; i < kPerLane; ++i) key[i] = (unsigned long long)__double_as_longlong(v[i] > 0.0 ? v[i] : 0.0);
@@ -538,10 +544,54 @@ __global__ void __launch_bounds__(256) est_quantile_kernel(int p, int nown, cons
     const unsigned long long khi = (n_gt >= kDraws - lo - 1) ? above : klo;
     const double t = pos - (double)lo;
     const double a = sqrt(__longlong_as_double((long long)klo)), c = sqrt(__longlong_as_double((long long)khi));
-    const double q = c - (c - a) * (1.0 - t);
+    const double q = nan_row ? __longlong_as_double(0x7ff8000000000000LL) : c - (c - a) * (1.0 - t);
     if (f < p) feat_out[(size_t)b * p + f] = q;
     else overall_out[b] = q;
   }
+}
+
+// ---------------------------------------------------------------- standalone error_estimates
+// L L^T = cov for a positive semi-definite cov (one CTA, right-looking, L row-major in `L`): a pivot
+// that is not above 1e-13 of the largest diagonal entry is round-off of a singular direction -- its
+// column is set to zero, exactly what a factorisation of a PSD matrix of that rank leaves there.
+__global__ void __launch_bounds__(1024) psd_factor_kernel(int p, const double *cov, double *L) {
+  __shared__ double s_piv;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  double dmax = 0.0;
+  for (int i = 0; i < p; ++i) dmax = fmax(dmax, cov[(size_t)i * p + i]);
+  for (int e = tid; e < p * p; e += nt) {
+    const int i = e / p, j = e - i * p;
+    L[e] = (j <= i) ? cov[e] : 0.0;
+  }
+  __syncthreads();
+  for (int k = 0; k < p; ++k) {
+    if (tid == 0) {
+      const double d = L[(size_t)k * p + k];
+      s_piv = (d > 1e-13 * dmax && d > 0.0) ? 1.0 / sqrt(d) : 0.0;
+    }
+    __syncthreads();
+    const double ri = s_piv;
+    for (int i = k + tid; i < p; i += nt) L[(size_t)i * p + k] *= ri;     // column k (incl. the diagonal: d / sqrt(d))
+    __syncthreads();
+    const int m = p - k - 1;
+    for (int e = tid; e < m * m; e += nt) {
+      const int i = k + 1 + e / m, j = k + 1 + e % m;
+      if (j <= i) L[(size_t)i * p + j] = fma(-L[(size_t)i * p + k], L[(size_t)j * p + k], L[(size_t)i * p + j]);
+    }
+    __syncthreads();
+  }
+}
+
+// zsq[f][s] = (sum_k L[f][k] g[s][k])^2: block f, thread s
+__global__ void __launch_bounds__(kDraws) err_draws_kernel(int p, const double *L, uint64_t seed, double *zsq) {
+  const int f = blockIdx.x, s = threadIdx.x;
+  double z = 0.0;
+  for (int k = 0; k <= f; ++k) {
+    float g0, g1;
+    gauss_pair(seed, (uint64_t)k, (uint32_t)s >> 1, g0, g1);   // column k, draws 2 (s/2) and 2 (s/2) + 1
+    z = fma(L[(size_t)f * p + k], (double)((s & 1) ? g1 : g0), z);
+  }
+  zsq[(size_t)f * kDraws + s] = z * z;
 }
 
 // ---------------------------------------------------------------- history / merge / epilogue
@@ -840,6 +890,17 @@ extern "C" int lsspa_estimator_quantiles(int p, double *zsq, int nown, double *o
   LSSPA_LAUNCH_CHECK();
   const int64_t rows = (int64_t)nown * (p + 1);
   est_quantile_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, as_stream(stream)>>>(p, nown, zsq, overall_out, feat_out);
+  LSSPA_LAUNCH_CHECK();
+  return LSSPA_OK;
+}
+
+extern "C" int lsspa_error_draws(int p, const double *cov, uint64_t seed, double *zsq, double *workspace,
+                                 void *stream) {
+  if (p < 1 || !cov || !zsq || !workspace) return LSSPA_E_BADARG;
+  cudaStream_t st = as_stream(stream);
+  psd_factor_kernel<<<1, 1024, 0, st>>>(p, cov, workspace);
+  LSSPA_LAUNCH_CHECK();
+  err_draws_kernel<<<p, kDraws, 0, st>>>(p, workspace, seed, zsq);
   LSSPA_LAUNCH_CHECK();
   return LSSPA_OK;
 }

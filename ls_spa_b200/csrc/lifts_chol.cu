@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(256, MINB) lifts_chol_kernel(CholParams a) {
       for (int k = tid; k <= p; k += 256)
         perm_s[k] = (k == p) ? p : a.perms[sidx * p + (h == 0 ? k : p - 1 - k)];
       __syncthreads();
-      const long long t_a = clock64();
+      const long long t_a = LSSPA_CLOCK();
       constexpr int64_t FD = chol_fact_doubles(RT, PT);
       const int64_t eval = sidx * halves + h;
       if constexpr (MODE == 2) {
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(256, MINB) lifts_chol_kernel(CholParams a) {
       }
       __syncthreads();
 
-      const long long t_b = clock64();
+      const long long t_b = LSSPA_CLOCK();
       long long t_acc = 0, t_diag = 0, t_wait = 0;
       // ---- phase 1: left-looking blocked Cholesky, software-pipelined around the serial part.
       // The 8x8 diagonal blocks form a chain (factor s needs row block s - 1), so warp 0 does
@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(256, MINB) lifts_chol_kernel(CholParams a) {
         }
         for (int s = 0; s < RT; ++s) {
           const int nf = (p - 8 * s < 8) ? p - 8 * s : 8;
-          const long long u0 = clock64();
+          const long long u0 = LSSPA_CLOCK();
           double2 tvn[NSL];
           if (warp == 0) {
             double2 t = ld_tile(A, ld, 8 * s, 8 * s, c, q);
@@ -428,10 +428,10 @@ __global__ void __launch_bounds__(256, MINB) lifts_chol_kernel(CholParams a) {
               st_tile(A, ld, 8 * (s + 1), 8 * (s + 1), c, q, make_double2(g.x - z.x, g.y - z.y));
             }
           }
-          const long long u1 = clock64();
+          const long long u1 = LSSPA_CLOCK();
           t_acc += u1 - u0;
           __syncthreads();
-          const long long u2 = clock64();
+          const long long u2 = LSSPA_CLOCK();
           t_wait += u2 - u1;
           if (warp != 0) {
             const double2 dv = ld_tile(Dbuf + s * 64, 8, 0, 0, c, q);
@@ -464,11 +464,11 @@ __global__ void __launch_bounds__(256, MINB) lifts_chol_kernel(CholParams a) {
             }
           }
           if (fused) elim_dispatch<RT, ld>(s, xr, r_in, wc, A, Dbuf, cvec, p, c, q);
-          t_diag += clock64() - u2;
+          t_diag += LSSPA_CLOCK() - u2;
         }
       }
 
-      const long long t_c = clock64();
+      const long long t_c = LSSPA_CLOCK();
       if constexpr (MODE == 1) {
         // ---- split route: R (upper tiles, with c) and the diagonal inverses go to global memory
         double2 *dst = reinterpret_cast<double2 *>(a.fact + eval * FD);
@@ -500,8 +500,9 @@ __global__ void __launch_bounds__(256, MINB) lifts_chol_kernel(CholParams a) {
         load_x<RT>(xr, r_in, a, perm_s, it, p, c, q);
         elim_all<RT, ld>(xr, r_in, wc, A, Dbuf, cvec, p, c, q);
       }
-      const long long t_d = clock64();
+      const long long t_d = LSSPA_CLOCK();
       __syncthreads();
+#ifdef LSSPA_LIFTS_TIMING
       if (a.dbg != nullptr && blockIdx.x == 0 && lane == 0 && sidx == blockIdx.x && h == 0) {
         long long *d = a.dbg + warp * 8;
         d[0] = t_b - t_a;   // gather
@@ -511,6 +512,9 @@ __global__ void __launch_bounds__(256, MINB) lifts_chol_kernel(CholParams a) {
         d[4] = t_c - t_b;   // whole phase 1
         d[5] = t_d - t_c;   // phase 2 (this warp)
       }
+#else
+      (void)t_a; (void)t_b; (void)t_c; (void)t_d; (void)t_acc; (void)t_diag; (void)t_wait;
+#endif
       for (int k = tid; k < p; k += 256) {
         double sacc = 0.0;
 #pragma unroll

@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(256, MINB) lifts_mma_kernel(LiftParams2 a) {
       __syncthreads();
       for (int k = tid; k < p; k += 256) perm_s[k] = a.perms[sidx * p + (h == 0 ? k : p - 1 - k)];
       __syncthreads();
-      long long t_a = clock64();
+      long long t_a = LSSPA_CLOCK();
       // ---- phase 0: gather A = [R_tr[:, perm] | c_tr], zero padding
       {
         const int half = NR / 2, tot = NC * half;
@@ -446,31 +446,31 @@ __global__ void __launch_bounds__(256, MINB) lifts_mma_kernel(LiftParams2 a) {
       // ---- phase 1: blocked Householder with one panel of look-ahead.  In step s warp 0 first
       // brings column tile s+1 up to date and factors it (into the other V/T buffer) while
       // warps 1..7 apply panel s to the remaining tiles: one barrier per panel.
-      long long t_b = clock64(), t_pan = 0, t_trc = 0, t_wait = 0;
+      long long t_b = LSSPA_CLOCK(), t_pan = 0, t_trc = 0, t_wait = 0;
       if (warp < kPW) panel_coop<KL>(A, V0, Tb, px, ld, p, RT, 0, lane, warp);
-      t_pan += clock64() - t_b;
+      t_pan += LSSPA_CLOCK() - t_b;
       __syncthreads();
       for (int s = 0; s < RT; ++s) {
         const double *Vc = (s & 1) ? V1 : V0;
         double *Vn = (s & 1) ? V0 : V1;
         const double *Tc = Tb + 64 * (s & 1);
         double *Tn = Tb + 64 * ((s + 1) & 1);
-        long long t0 = clock64();
+        long long t0 = LSSPA_CLOCK();
         if (warp < kPW) {
           if (s + 1 < PT) trailing_coop<KL>(A, Vc, Tc, px, ld, RT, s, s + 1, lane, warp);
-          long long t1 = clock64();
+          long long t1 = LSSPA_CLOCK();
           t_trc += t1 - t0;
           if (s + 1 < RT) panel_coop<KL>(A, Vn, Tn, px, ld, p, RT, s + 1, lane, warp);
-          t_pan += clock64() - t1;
+          t_pan += LSSPA_CLOCK() - t1;
         } else {
           for (int j = s + 2 + (warp - kPW); j < PT; j += 8 - kPW) trailing_tile(A, Vc, Tc, ld, RT, s, j, lane);
-          t_trc += clock64() - t0;
+          t_trc += LSSPA_CLOCK() - t0;
         }
-        long long t2 = clock64();
+        long long t2 = LSSPA_CLOCK();
         __syncthreads();
-        t_wait += clock64() - t2;
+        t_wait += LSSPA_CLOCK() - t2;
       }
-      long long t_c = clock64();
+      long long t_c = LSSPA_CLOCK();
 
       // ---- phase 1.5: inverses of the 8x8 diagonal blocks of R (column-major 8x8 each), zero the
       //      per-warp cost partials (both overlay the V buffers)
@@ -561,8 +561,9 @@ __global__ void __launch_bounds__(256, MINB) lifts_mma_kernel(LiftParams2 a) {
           }
         }
       }
-      long long t_d = clock64();
+      long long t_d = LSSPA_CLOCK();
       __syncthreads();
+#ifdef LSSPA_LIFTS_TIMING
       if (a.dbg != nullptr && blockIdx.x == 0 && lane == 0 && sidx == blockIdx.x && h == 0) {
         long long *d = a.dbg + warp * 8;
         d[0] = t_b - t_a;      // gather
@@ -572,6 +573,9 @@ __global__ void __launch_bounds__(256, MINB) lifts_mma_kernel(LiftParams2 a) {
         d[4] = t_c - t_b;      // whole phase 1
         d[5] = t_d - t_c;      // phase 1.5 + phase 2 (this warp)
       }
+#else
+      (void)t_a; (void)t_b; (void)t_c; (void)t_d; (void)t_pan; (void)t_trc; (void)t_wait;
+#endif
       for (int k = tid; k < p; k += 256) {
         double sacc = 0.0;
 #pragma unroll
@@ -652,7 +656,10 @@ int lifts_mma_launch(int p, const double *R_tr_cm, const double *c_tr, const dou
 
 }  // namespace lsspa
 
-// development aid, not part of include/lsspa.h: 64 device long longs receiving block 0's cycle counters
+#ifdef LSSPA_LIFTS_TIMING
+// development aid (tools/lifts_cycles.py), only in builds with -DLSSPA_LIFTS_TIMING and therefore not
+// part of include/lsspa.h: 64 device long longs receiving block 0's cycle counters
 extern "C" __attribute__((visibility("default"))) void lsspa_debug_set_lifts_counters(long long *dev_ptr) {
   lsspa::g_lifts_dbg = dev_ptr;
 }
+#endif

@@ -514,6 +514,42 @@ extern "C" int lsspa_perms_pcg64(int p, uint64_t *gen_state, int64_t count, int3
   return LSSPA_OK;
 }
 
+namespace lsspa {
+// One warp per row: every entry in [0, p) and every value hit exactly once (bitmap in shared memory).
+// bad_flag (device int, never cleared here) receives 1 + the first offending row seen by some warp.
+__global__ void __launch_bounds__(256) perms_validate_kernel(int p, const int32_t *perms, int64_t count, int *bad_flag) {
+  extern __shared__ unsigned int bm_all[];
+  const int words = (p + 31) / 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned int *bm = bm_all + (size_t)warp * words;
+  for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < count; row += (int64_t)gridDim.x * 8) {
+    for (int w = lane; w < words; w += 32) bm[w] = 0u;
+    __syncwarp();
+    bool bad = false;
+    for (int k = lane; k < p; k += 32) {
+      const int v = perms[row * p + k];
+      if (v < 0 || v >= p) bad = true;
+      else if (atomicOr(&bm[v >> 5], 1u << (v & 31)) & (1u << (v & 31))) bad = true;   // seen before
+    }
+    __syncwarp();
+    if (__any_sync(kFull, bad) && lane == 0) atomicCAS(bad_flag, 0, (int)(row < 0x7ffffffe ? row + 1 : 0x7fffffff));
+    __syncwarp();
+  }
+}
+}  // namespace lsspa
+
+extern "C" int lsspa_perms_validate(int p, const int32_t *perms, int64_t count, int *bad_flag, void *stream) {
+  if (p < 1 || count < 0 || !bad_flag || (count > 0 && !perms)) return LSSPA_E_BADARG;
+  if (count == 0) return LSSPA_OK;
+  const size_t smem = (size_t)8 * ((p + 31) / 32) * sizeof(unsigned int);
+  if (smem > 48 * 1024) return LSSPA_E_UNSUPPORTED;
+  int64_t grid = lsspa::ceil_div(count, 8);
+  if (grid > 148 * 8) grid = 148 * 8;
+  lsspa::perms_validate_kernel<<<(unsigned)grid, 256, smem, lsspa::as_stream(stream)>>>(p, perms, count, bad_flag);
+  LSSPA_LAUNCH_CHECK();
+  return LSSPA_OK;
+}
+
 extern "C" int lsspa_perms_sobol_argsort(int p, const uint32_t *sv, const uint32_t *shift, int bits,
                                          uint64_t first_index, int64_t count, int32_t *perms_out,
                                          void *stream) {

@@ -116,8 +116,13 @@ class CudaBackend:
         staging buffers (single-pass consumers); keep=True lands the chunks in one resident device
         array (the CholeskyQR2 reduction reads the rows twice)."""
         if isinstance(X, torch.Tensor) and X.is_cuda:
-            yv = y if (isinstance(y, torch.Tensor) and y.is_cuda) else torch.as_tensor(y).to(self.device)
-            yield X[lo:hi], yv[lo:hi].contiguous(), None
+            # device-resident inputs: the kernels read raw float64 storage on THIS device, so any other
+            # dtype (torch's default is float32) or device is converted here (a no-op for float64 rows)
+            Xv = X[lo:hi].to(device=self.device, dtype=torch.float64)
+            yv = torch.as_tensor(y)[lo:hi].to(device=self.device, dtype=torch.float64).contiguous()
+            if Xv.stride(1) != 1:
+                Xv = Xv.contiguous()
+            yield Xv, yv, None
             return
         Xh = X if isinstance(X, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(X))
         yh = y if isinstance(y, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(y))
@@ -323,7 +328,11 @@ class Prefactor:
             return train
         per_sample = 2 if cfg.antithetical else 1
         fd = int(_ops._lib().lsspa_lifts_chol_factor_doubles(p))
-        budget = min(self.MAX_BYTES // (8 * fd), int(self.FACTOR_RATE * self.test_bytes / self.LINK_RATE))
+        max_bytes = self.MAX_BYTES
+        if torch.cuda.is_available():
+            # the test rows (staged before this runs) and the sample loop need room too
+            max_bytes = min(max_bytes, torch.cuda.mem_get_info()[0] // 2)
+        budget = min(max_bytes // (8 * fd), int(self.FACTOR_RATE * self.test_bytes / self.LINK_RATE))
         pos, index, evals = 0, 0, 0
         while pos < limit:
             want = min(sb_size(index), limit - pos)
@@ -339,9 +348,22 @@ class Prefactor:
         return train
 
 
-def superbatch_geometry(cfg: JobConfig, world: int, source_total):
+def batch_cap(p: int, estimate_errors: bool, free_bytes: int | None = None) -> int:
+    """Most batches one super-batch may hold per rank.  Every batch costs one partial-moment block
+    ((8 + p + p^2 + 1024 + 1024 p) doubles) and, with error estimates, (p + 1) x 1024 squared draws;
+    without a cap that memory grows like 1 / batch_size (the reference's own tests use batch_size=2).
+    Budget: 2 GB, or a quarter of the free device memory when that is less."""
+    per_batch = 8 * (8 + p + p * p + 1024 + 1024 * p) + (8 * (p + 1) * 1024 if estimate_errors else 0)
+    budget = 2 << 30
+    if free_bytes is not None:
+        budget = min(budget, free_bytes // 4)
+    return max(1, int(budget // per_batch))
+
+
+def superbatch_geometry(cfg: JobConfig, world: int, source_total, max_batches: int | None = None):
     """-> (limit, effective batch size, size(index)): how many samples super-batch `index` asks for
-    (before clipping to the limit).  Deterministic, so that work can be prepared ahead of the loop."""
+    (before clipping to the limit).  Deterministic, so that work can be prepared ahead of the loop.
+    max_batches caps the batches of one super-batch per rank (default: batch_cap without a device)."""
     limit = cfg.max_samples
     if source_total is not None:
         limit = source_total if limit is None else min(limit, source_total)
@@ -349,7 +371,8 @@ def superbatch_geometry(cfg: JobConfig, world: int, source_total):
     # without error estimates batch boundaries are irrelevant: cut the super-batch into 1024-sample
     # batches so that the per-batch moment kernels run in parallel
     bs_eff = cfg.batch_size if cfg.estimate_errors else min(tgt, 1024)
-    g_local = max(1, -(-tgt // bs_eff))
+    cap = max_batches if max_batches is not None else batch_cap(cfg.p, cfg.estimate_errors)
+    g_local = max(1, min(-(-tgt // bs_eff), cap))
     # When the job can stop early the super-batches ramp up (2048 samples per rank, then 4x per
     # round up to the full size): a loose tolerance is then reached after little more than the work
     # it needs instead of after one full super-batch, at the price of two extra (pipelined) rounds.

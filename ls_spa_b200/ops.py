@@ -142,6 +142,10 @@ class CholQR2:
     def add_chunk(self, Xc: torch.Tensor, yc: torch.Tensor) -> None:
         if Xc.shape[0] == 0:
             return
+        # the kernels read raw float64 storage through these pointers
+        Xc, yc = _dev_f64(Xc, "X"), _dev_f64(yc, "y").contiguous()
+        if Xc.device != yc.device or Xc.dim() != 2 or yc.dim() != 1 or Xc.shape[0] != yc.shape[0]:
+            raise LsSpaCudaError("CholQR2.add_chunk: X must be (n, p), y (n,), on one device")
         if Xc.stride(1) != 1:
             Xc = Xc.contiguous()
         self.chunks.append((Xc, yc))
@@ -243,6 +247,21 @@ def perms_permutohedron(p, sv, shift, bits, first_index, count) -> torch.Tensor:
                                            out.data_ptr(), _stream()), "lsspa_perms_permutohedron")
     _count(1)
     return out
+
+
+def perms_validate(perms: torch.Tensor) -> None:
+    """Raise ValueError unless every row of the int32 CUDA tensor `perms` is a bijection of {0..p-1}
+    (the lift kernels index shared memory with these values).  One launch + one flag read."""
+    if perms.numel() == 0:
+        return
+    perms = perms.contiguous()
+    count, p = perms.shape
+    flag = torch.zeros(1, dtype=torch.int32, device=perms.device)
+    check(_lib().lsspa_perms_validate(p, perms.data_ptr(), count, flag.data_ptr(), _stream()), "lsspa_perms_validate")
+    _count(1)
+    bad = int(flag.item())
+    if bad:
+        raise ValueError(f"perms: row {bad - 1} is not a permutation of range({p})")
 
 
 # ---------------------------------------------------------------------------
@@ -518,6 +537,26 @@ class Estimator:
             off = 2 * p + 2 * ERR_DRAWS
             res["cov"] = self.state[off:off + p * p].reshape(p, p).cpu().numpy().copy()
         return res
+
+
+def error_draws_quantiles(cov: torch.Tensor, seed: int):
+    """error_estimates (ls_spa/ls_spa.py:321-341) for an explicit covariance: (per-feature, overall)
+    0.95 quantiles over 1024 device draws of N(0, cov)."""
+    cov = _dev_f64(cov, "cov").contiguous()
+    p = int(cov.shape[0])
+    if cov.dim() != 2 or cov.shape[1] != p:
+        raise LsSpaCudaError("cov must be square")
+    zsq = torch.empty((1, p + 1, ERR_DRAWS), dtype=torch.float64, device=cov.device)
+    ws = torch.empty(p * p, dtype=torch.float64, device=cov.device)
+    lib = _lib()
+    check(lib.lsspa_error_draws(p, cov.data_ptr(), int(seed) & ((1 << 64) - 1), zsq.data_ptr(), ws.data_ptr(),
+                                _stream()), "lsspa_error_draws")
+    overall = torch.empty(1, dtype=torch.float64, device=cov.device)
+    feat = torch.empty((1, p), dtype=torch.float64, device=cov.device)
+    check(lib.lsspa_estimator_quantiles(p, zsq.data_ptr(), 1, overall.data_ptr(), feat.data_ptr(), _stream()),
+          "lsspa_estimator_quantiles")
+    _count(4)
+    return feat[0], overall[0]
 
 
 def prefix_means(lift_rows: torch.Tensor, carry_sum: torch.Tensor, carry_count: int, out: torch.Tensor) -> None:

@@ -181,6 +181,8 @@ class ExplicitSource(PermutationSource):
             self._tensor = t.to(device=device, dtype=torch.int32)
             total = t.shape[0]
         elif isinstance(perms, np.ndarray) and perms.ndim == 2:
+            if perms.size and (perms.min() < 0 or perms.max() >= p):
+                raise ValueError(f"perms: entries must lie in range({p})")
             self._tensor = torch.from_numpy(np.ascontiguousarray(perms).astype(np.int32)).to(device)
             total = perms.shape[0]
         else:
@@ -192,11 +194,22 @@ class ExplicitSource(PermutationSource):
         super().__init__(p, total)
         self.exhausted = False
 
+    @staticmethod
+    def _validate(out):
+        # the product path always runs on a CUDA device (ops.require_cuda); CPU tensors only occur in the
+        # host-logic unit tests, whose oracle-backed stand-in indexes with numpy (IndexError on bad input)
+        if out.is_cuda:
+            ops.perms_validate(out)
+
     def take(self, count):
+        """Every chunk handed out was checked on the device to consist of bijections of range(p):
+        the reference leaves that to numpy's IndexError (ls_spa/ls_spa.py:165-167), here a bad
+        index would address shared memory out of bounds."""
         if self._tensor is not None:
             count = self._clip(count)
             out = self._tensor[self.position:self.position + count]
             self.position += count
+            self._validate(out)
             return out
         rows = list(itertools.islice(self._iter, count))
         if len(rows) < count:
@@ -209,7 +222,11 @@ class ExplicitSource(PermutationSource):
         if arr.shape[1] != self.p:
             raise LsSpaCudaError("explicit permutations must have p entries each")
         self.position += len(rows)
-        return torch.from_numpy(arr.astype(np.int32)).to(self.device)
+        if arr.size and (arr.min() < 0 or arr.max() >= self.p):      # before the cast to int32 can wrap
+            raise ValueError(f"perms: entries must lie in range({self.p})")
+        out = torch.from_numpy(arr.astype(np.int32)).to(self.device)
+        self._validate(out)
+        return out
 
 
 def make_source(method, p, seed, total, device, perms=None) -> PermutationSource:

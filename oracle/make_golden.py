@@ -132,8 +132,61 @@ def streams():
     print("streams", {k: v.shape for k, v in out.items()})
 
 
+from oracle.samplers_oracle import WIDTHS, width_problem  # noqa: E402
+
+
+def widths():
+    """square_shapley of the reference at every tile count of the Cholesky lift kernel (p = 17..152);
+    only the lifts are stored, the inputs come from width_problem()."""
+    out = {}
+    for p in WIDTHS:
+        R_tr, R_te, c_tr, c_te, ynsq, perms = width_problem(p)
+        cond = np.linalg.cond(R_tr / np.linalg.norm(R_tr, axis=0))
+        assert cond < 300, (p, cond)
+        out[f"lifts_p{p}"] = np.array([ref_mod.square_shapley(R_tr, R_te, c_tr, c_te, ynsq, pm) for pm in perms])
+        out[f"cond_p{p}"] = np.float64(cond)
+    np.savez_compressed(os.path.join(OUT, "widths.npz"), **out)
+    print("widths", {k: float(v) for k, v in out.items() if k.startswith("cond")})
+
+
+def ill_conditioned(tag="ill_p64", p=64, n=400, m=300, k=12, cond=1e5):
+    """Train/test features with singular values spread over `cond` in random directions (column
+    equilibration cannot repair that): the route the condition guard sends to the Householder kernels."""
+    rng = np.random.default_rng(64)
+    V = np.linalg.qr(rng.standard_normal((p, p)))[0]
+    s = np.geomspace(1.0, 1.0 / cond, p)
+    Xtr = np.linalg.qr(rng.standard_normal((n, p)))[0] * s @ V.T * np.sqrt(n)
+    Xte = np.linalg.qr(rng.standard_normal((m, p)))[0] * s @ V.T * np.sqrt(m)
+    theta = V @ (rng.standard_normal(p) / np.sqrt(s))
+    ytr = Xtr @ theta + 0.05 * rng.standard_normal(n)
+    yte = Xte @ theta + 0.05 * rng.standard_normal(m)
+    Xtr, Xte, ytr, yte = f32_exact(Xtr, Xte, ytr, yte)
+    R_tr, R_te, c_tr, c_te = ref_mod.reduce_data(Xtr, Xte, ytr, yte, 0.0)
+    ynsq = np.linalg.norm(yte) ** 2
+    out = dict(p=p, n=n, m=m, reg=0.0, X_train=Xtr.astype(np.float32), X_test=Xte.astype(np.float32),
+               y_train=ytr.astype(np.float32), y_test=yte.astype(np.float32),
+               R_tr=R_tr, R_te=R_te, c_tr=c_tr, c_te=c_te, y_norm_sq=ynsq,
+               cond_equilibrated=np.linalg.cond(R_tr / np.linalg.norm(R_tr, axis=0)), cond=np.linalg.cond(R_tr))
+    perms = so.perms_random(p, k, 5)
+    out["perms_random"] = perms.astype(np.int16)
+    out["lifts_random"] = np.array([ref_mod.square_shapley(R_tr, R_te, c_tr, c_te, ynsq, pm) for pm in perms])
+    for anti in (False, True):
+        res = ref_pkg.ls_spa(Xtr, Xte, ytr, yte, reg=0.0, perms=list(perms), tolerance=0.0, batch_size=4,
+                             antithetical=anti, return_attribution_history=True)
+        out.update(results_dict(res, f"random_anti{int(anti)}_"))
+    np.savez_compressed(os.path.join(OUT, f"{tag}.npz"), **out)
+    print(tag, "cond", out["cond"], "equilibrated", out["cond_equilibrated"], "r2", out["random_anti0_r_squared"],
+          "max|lift|", np.abs(out["lifts_random"]).max())
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1:          # only the named fixtures, e.g. `make_golden.py widths ill_conditioned`
+        for name in sys.argv[1:]:
+            globals()[name]()
+        sys.exit(0)
+    widths()
+    ill_conditioned()
     toy()
     exact_p7()
     synthetic("syn_p10", p=10, n=500, m=400, reg=0.0, k=48, exact_small=True)

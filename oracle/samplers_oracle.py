@@ -93,3 +93,17 @@ def gen_data(rng, p, n_train, n_test, stn_ratio=5.0, conditioning=20.0):
     X_test = X_test - x_mean                                               # :103
     y_test = y_test - y_mean                                               # :104
     return X_train, X_test, y_train, y_test, theta_true, cov
+
+
+WIDTHS = (17, 24, 31, 40, 48, 56, 64, 65, 80, 88, 96, 104, 105, 120, 128, 129, 144, 152)
+
+
+def width_problem(p):
+    """Reduced problem of width p built WITHOUT LAPACK (seeded numpy draws only), so that the test
+    regenerates it bit for bit on any host: well-conditioned upper-triangular factors."""
+    rng = np.random.default_rng(1000 + p)
+    R_tr = np.triu(np.eye(p) + 0.6 * rng.standard_normal((p, p)) / np.sqrt(p))
+    R_te = np.triu(1.5 * np.eye(p) + 0.9 * rng.standard_normal((p, p)) / np.sqrt(p))
+    c_tr, c_te = rng.standard_normal(p), rng.standard_normal(p)
+    perms = np.array([rng.permutation(p) for _ in range(4)])
+    return R_tr, R_te, c_tr, c_te, float(c_te @ c_te) * 1.3, perms

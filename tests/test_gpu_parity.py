@@ -19,7 +19,8 @@ SYN = ["syn_p10", "syn_p33", "syn_p100", "syn_p100_reg", "syn_p160"]
 @pytest.fixture(scope="module")
 def T():
     import torch
-    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    if not torch.cuda.is_available():
+        pytest.skip("gpu tests need a CUDA device")
     return torch
 
 

@@ -126,3 +126,26 @@ def test_superbatch_plan():
     assert flat(0) == flat(5) == full
     limit, bs, nosplit = superbatch_geometry(JobConfig(tolerance=1e-2, estimate_errors=False, **base), 1, 5000)
     assert limit == 5000 and bs == 1024 and nosplit(0) == full
+
+
+def test_superbatch_memory_cap():
+    """Tiny batches (the reference's tests use batch_size=2) must not blow the per-batch partial blocks
+    up: the batches of one super-batch are capped by a byte budget."""
+    from ls_spa_b200.engine import JobConfig, batch_cap, superbatch_geometry, target_samples
+    cap = batch_cap(100, True)
+    per_batch = 8 * (8 + 100 + 100 * 100 + 1024 + 1024 * 100) + 8 * 101 * 1024
+    assert cap * per_batch <= 2 << 30 < (cap + 1) * per_batch
+    assert batch_cap(100, True, free_bytes=1 << 30) == (1 << 28) // per_batch
+    assert batch_cap(5000, True) == 1                       # never zero
+    cfg = JobConfig(p=100, batch_size=2, max_samples=1 << 20, tolerance=0.0, seed=1, antithetical=True,
+                    estimate_errors=True, return_history=False)
+    _, bs, size = superbatch_geometry(cfg, 1, None)
+    assert bs == 2 and size(0) == 2 * cap < target_samples(100)
+    _, _, size4 = superbatch_geometry(cfg, 4, None)
+    assert size4(0) == 4 * 2 * cap                          # per rank
+    _, _, small = superbatch_geometry(cfg, 1, None, max_batches=7)
+    assert small(0) == 14
+    cfg10 = JobConfig(p=10, batch_size=1, max_samples=None, tolerance=0.0, seed=1, antithetical=False,
+                      estimate_errors=True, return_history=False)
+    _, _, s10 = superbatch_geometry(cfg10, 1, None)
+    assert s10(0) == min(target_samples(10), batch_cap(10, True))

@@ -1,4 +1,5 @@
-"""Cycle counters of one CTA of the DMMA lift kernel (development aid)."""
+"""Cycle counters of one CTA of the DMMA lift kernel (development aid).
+Needs a library built with the probes: LSSPA_EXTRA_NVCC_FLAGS=-DLSSPA_LIFTS_TIMING python -m ls_spa_b200.build --force"""
 import ctypes, sys, torch
 sys.path.insert(0, "."); sys.path.insert(0, "tools")
 from quick_bench import synth_problem
