@@ -136,7 +136,7 @@ def test_superbatch_memory_cap():
     per_batch = 8 * (8 + 100 + 100 * 100 + 1024 + 1024 * 100) + 8 * 101 * 1024
     assert cap * per_batch <= 2 << 30 < (cap + 1) * per_batch
     assert batch_cap(100, True, free_bytes=1 << 30) == (1 << 28) // per_batch
-    assert batch_cap(5000, True) == 1                       # never zero
+    assert batch_cap(30000, True) == 1                      # never zero
     cfg = JobConfig(p=100, batch_size=2, max_samples=1 << 20, tolerance=0.0, seed=1, antithetical=True,
                     estimate_errors=True, return_history=False)
     _, bs, size = superbatch_geometry(cfg, 1, None)
