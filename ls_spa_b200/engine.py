@@ -330,8 +330,11 @@ class Prefactor:
         fd = int(_ops._lib().lsspa_lifts_chol_factor_doubles(p))
         max_bytes = self.MAX_BYTES
         if torch.cuda.is_available():
-            # the test rows (staged before this runs) and the sample loop need room too
-            max_bytes = min(max_bytes, torch.cuda.mem_get_info()[0] // 2)
+            # the test rows (staged before this runs) and the sample loop need room too.  Not
+            # cudaMemGetInfo: it synchronises the device, and the host must keep running ahead here.
+            dev = self.backend.device
+            room = torch.cuda.get_device_properties(dev).total_memory - torch.cuda.memory_reserved(dev)
+            max_bytes = min(max_bytes, max(room, 0) // 2)
         budget = min(max_bytes // (8 * fd), int(self.FACTOR_RATE * self.test_bytes / self.LINK_RATE))
         pos, index, evals = 0, 0, 0
         while pos < limit:
