@@ -93,8 +93,29 @@ LSSPA_API int lsspa_gram_finish(const double *parts, int count, int p, double sc
                                 void *stream);
 LSSPA_API int lsspa_chol_factor(const double *G, int p, double *R_out, double *Rinv_out, double *info,
                                 void *stream);
+/* ridge rows of the train block (:310) as reg added to the first p diagonal entries of G (in place) */
+LSSPA_API int lsspa_gram_add_ridge(double *G, int p, double reg, void *stream);
 LSSPA_API int lsspa_tri_product(const double *R2, const double *R1, int p, const double *G1, double *out_slot,
                                 void *stream);
+
+/* Wide problems (p + 1 > 120, up to p = 2047; gram_big.cu + lifts_big.cu): the same one-pass Gram
+ * reduction with 128-column blocks.
+ *   lsspa_gram_big_rows        partial Gram blocks of rows [0, nrows) of [X | y]:
+ *                              parts[nsplit][lsspa_gram_big_part_doubles(p)], nsplit = lsspa_gram_big_num_splits;
+ *   lsspa_gram_big_accumulate  G_acc ((p+1) x (p+1) row-major, upper blocks) += sum of the partial blocks;
+ *                              G_acc is what a multi-GPU job all-reduces;
+ *   lsspa_gram_big_factor      slot (layout of lsspa_tsqr_merge) = Cholesky factor of
+ *                              scale * G_acc + reg * diag(I_p, 0)  (blocked, fp64 tensor tiles);
+ *                              status_flag (device int, zero-initialised) raised on a non-positive feature pivot. */
+LSSPA_API int lsspa_gram_big_supported(int p);
+LSSPA_API int lsspa_gram_big_num_splits(int p, int64_t nrows);
+LSSPA_API int64_t lsspa_gram_big_part_doubles(int p);
+LSSPA_API int lsspa_gram_big_rows(const double *X, int64_t ldx, const double *y, int64_t nrows, int p,
+                                  double *parts, int nsplit, void *stream);
+LSSPA_API int lsspa_gram_big_accumulate(const double *parts, int nsplit, int p, double *G_acc, void *stream);
+LSSPA_API size_t lsspa_gram_big_factor_workspace_bytes(int p);
+LSSPA_API int lsspa_gram_big_factor(const double *G_acc, int p, double scale, double reg, double *slot_out,
+                                    void *workspace, size_t workspace_bytes, int *status_flag, void *stream);
 
 /* ------------------------------------------------------------------------
  * 2. Permutation sources (int32 indices, perms_out[count][p])
@@ -168,6 +189,18 @@ LSSPA_API int lsspa_lifts_gram(int p, const double *R_tr_cm, const double *c_tr,
 LSSPA_API int lsspa_lifts_chol(int p, const double *gram, const double *R_te_cm, const double *c_te,
                      double y_norm_sq, const int32_t *perms, int64_t count, int antithetical,
                      double *lifts_out, void *stream);
+
+/* Wide problems (152 < p <= 2047; BASELINE config 5 is p = 1000): the same Cholesky route as a batched
+ * blocked factorisation over a tile workspace in device memory (lifts_big.cu).  lsspa_lifts_gram accepts
+ * these widths too (same gram_out layout).  workspace: lsspa_lifts_big_workspace_bytes(p, count,
+ * antithetical, budget) bytes -- as many samples as fit into `budget` are processed per pass (at least
+ * one); status_flag (device int, zero-initialised) is raised if a feature pivot was not positive. */
+LSSPA_API int lsspa_lifts_big_supported(int p);
+LSSPA_API size_t lsspa_lifts_big_workspace_bytes(int p, int64_t count, int antithetical, size_t budget_bytes);
+LSSPA_API int lsspa_lifts_big(int p, const double *gram, const double *R_te_cm, const double *c_te,
+                              double y_norm_sq, const int32_t *perms, int64_t count, int antithetical,
+                              double *lifts_out, void *workspace, size_t workspace_bytes, int *status_flag,
+                              void *stream);
 
 /* The same route in two launches (49 <= p <= 128), for jobs whose inputs arrive over PCIe: the
  * factorisation of R_tr[:, perm] (np.linalg.qr, ls_spa/ls_spa.py:268-270) needs the train side

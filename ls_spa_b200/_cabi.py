@@ -33,6 +33,14 @@ SIGNATURES = {
     "lsspa_gram_rows": (c_i32, [vp, c_i64, vp, c_i64, c_i32, vp, vp, c_i32, vp]),
     "lsspa_gram_finish": (c_i32, [vp, c_i32, c_i32, c_f64, vp, vp]),
     "lsspa_chol_factor": (c_i32, [vp, c_i32, vp, vp, vp, vp]),
+    "lsspa_gram_add_ridge": (c_i32, [vp, c_i32, c_f64, vp]),
+    "lsspa_gram_big_supported": (c_i32, [c_i32]),
+    "lsspa_gram_big_num_splits": (c_i32, [c_i32, c_i64]),
+    "lsspa_gram_big_part_doubles": (c_i64, [c_i32]),
+    "lsspa_gram_big_rows": (c_i32, [vp, c_i64, vp, c_i64, c_i32, vp, c_i32, vp]),
+    "lsspa_gram_big_accumulate": (c_i32, [vp, c_i32, c_i32, vp, vp]),
+    "lsspa_gram_big_factor_workspace_bytes": (sz, [c_i32]),
+    "lsspa_gram_big_factor": (c_i32, [vp, c_i32, c_f64, c_f64, vp, vp, sz, vp, vp]),
     "lsspa_tri_product": (c_i32, [vp, vp, c_i32, vp, vp, vp]),
     "lsspa_perms_exact": (c_i32, [c_i32, c_u64, c_i64, vp, vp]),
     "lsspa_perms_pcg64_workspace_bytes": (sz, [c_i32, c_i64]),
@@ -46,6 +54,9 @@ SIGNATURES = {
     "lsspa_lifts_gram_doubles": (c_i64, [c_i32]),
     "lsspa_lifts_gram": (c_i32, [c_i32, vp, vp, vp, vp]),
     "lsspa_lifts_chol": (c_i32, [c_i32, vp, vp, vp, c_f64, vp, c_i64, c_i32, vp, vp]),
+    "lsspa_lifts_big_supported": (c_i32, [c_i32]),
+    "lsspa_lifts_big_workspace_bytes": (sz, [c_i32, c_i64, c_i32, sz]),
+    "lsspa_lifts_big": (c_i32, [c_i32, vp, vp, vp, c_f64, vp, c_i64, c_i32, vp, vp, sz, vp, vp]),
     "lsspa_lifts_chol_factor_doubles": (c_i64, [c_i32]),
     "lsspa_lifts_chol_factor": (c_i32, [c_i32, vp, vp, c_i64, c_i32, vp, vp]),
     "lsspa_lifts_chol_eliminate": (c_i32, [c_i32, vp, vp, vp, c_f64, vp, c_i64, c_i32, vp, vp]),

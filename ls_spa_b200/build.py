@@ -16,7 +16,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libls_spa_b200.so")
-SOURCES = ["common.cu", "reduce.cu", "gram.cu", "perms.cu", "lifts.cu", "lifts_mma.cu", "lifts_chol.cu", "estimator.cu"]
+SOURCES = ["common.cu", "reduce.cu", "gram.cu", "gram_big.cu", "perms.cu", "lifts.cu", "lifts_mma.cu", "lifts_chol.cu", "lifts_big.cu", "estimator.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

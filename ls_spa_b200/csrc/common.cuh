@@ -67,4 +67,9 @@ int lifts_mma_launch(int p, const double *R_tr_cm, const double *c_tr, const dou
                      double y_norm_sq, const int32_t *perms, int64_t count, int antithetical, double *lifts_out,
                      cudaStream_t st);
 
+// wide problems (lifts_big.cu): p > 152
+bool lifts_big_supported(int p);
+int lifts_big_cond(int p, const double *R_tr_cm, const double *D, const double *Gh, double *Xinv, double *colstat,
+                   double *info, cudaStream_t st);
+
 }  // namespace lsspa

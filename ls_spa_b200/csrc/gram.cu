@@ -394,6 +394,20 @@ extern "C" int lsspa_gram_finish(const double *parts, int count, int p, double s
   return LSSPA_OK;
 }
 
+// G (layout of lsspa_gram_finish) += reg on the first p diagonal entries: the sqrt(reg) I rows of the train
+// block (reference ls_spa/ls_spa.py:310) contribute exactly reg I to the Gram matrix
+__global__ void gram_ridge_kernel(double *G, int nc, int p, double reg) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < p) G[(size_t)i * nc + i] += reg;
+}
+
+extern "C" int lsspa_gram_add_ridge(double *G, int p, double reg, void *stream) {
+  if (!G || !lsspa_gram_supported(p)) return LSSPA_E_BADARG;
+  gram_ridge_kernel<<<(p + 127) / 128, 128, 0, as_stream(stream)>>>(G, 8 * gram_nt(p), p, reg);
+  LSSPA_LAUNCH_CHECK();
+  return LSSPA_OK;
+}
+
 extern "C" int lsspa_chol_factor(const double *G, int p, double *R_out, double *Rinv_out, double *info,
                                  void *stream) {
   if (!G || !R_out || !Rinv_out || !info || !lsspa_gram_supported(p)) return LSSPA_E_BADARG;

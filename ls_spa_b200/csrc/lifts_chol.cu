@@ -726,12 +726,13 @@ extern "C" int lsspa_lifts_chol_supported(int p) { return lifts_chol_supported(p
 
 extern "C" int64_t lsspa_lifts_gram_doubles(int p) {
   if (p < 1) return 0;
-  return (int64_t)(p + 1) * (p + 1) + 8 + p + (int64_t)p * p;  // Gh, info[8], D[p], scratch of the estimate
+  // Gh, info[8], D[p], scratch of the estimate (wide problems: the inverse of the equilibrated factor + 2p column sums)
+  return (int64_t)(p + 1) * (p + 1) + 8 + p + (int64_t)p * p + 2 * (int64_t)p;
 }
 
 extern "C" int lsspa_lifts_gram(int p, const double *R_tr_cm, const double *c_tr, double *gram_out, void *stream) {
   if (p < 1 || !R_tr_cm || !c_tr || !gram_out) return LSSPA_E_BADARG;
-  if (!lifts_chol_supported(p)) return LSSPA_E_UNSUPPORTED;
+  if (!lifts_chol_supported(p) && !lifts_big_supported(p)) return LSSPA_E_UNSUPPORTED;
   cudaStream_t st = as_stream(stream);
   double *info = gram_out + (size_t)(p + 1) * (p + 1);
   double *D = info + 8;
@@ -739,6 +740,10 @@ extern "C" int lsspa_lifts_gram(int p, const double *R_tr_cm, const double *c_tr
   LSSPA_LAUNCH_CHECK();
   lift_gram_kernel<<<p + 1, 128, 0, st>>>(p, R_tr_cm, c_tr, D, gram_out);
   LSSPA_LAUNCH_CHECK();
+  if (lifts_big_supported(p)) {
+    double *Xinv = D + p;
+    return lifts_big_cond(p, R_tr_cm, D, gram_out, Xinv, Xinv + (size_t)p * p, info, st);
+  }
   const int tight = p <= 128 ? 1 : 0;   // the sharper bound needs 32 p more doubles of shared memory
   const size_t cond_smem = ((size_t)32 * p * (1 + tight) + (size_t)p * p) * sizeof(double);
   LSSPA_CUDA_TRY(cudaFuncSetAttribute(lift_cond_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cond_smem));

@@ -65,8 +65,10 @@ def contiguous_runs(nbatch: int, world: int):
 
 
 def target_samples(p: int) -> int:
+    """Samples per rank and super-batch: ~16K at p = 100, falling with the p^2 growth of the work per sample.
+    Wide problems (the batched tile kernels, p > 152) need at least four evaluations per SM in flight."""
     t = int(16384 * (100.0 / max(p, 1)) ** 2)
-    return max(256, min(t, 131072))
+    return max(592 if p > 152 else 256, min(t, 131072))
 
 
 class Collective:
@@ -89,6 +91,12 @@ class Collective:
         out = torch.empty(self.world * flat.numel(), dtype=t.dtype, device=t.device)
         self.dist.all_gather_into_tensor(out, flat, group=self.group)
         return out.view((self.world,) + tuple(t.shape))
+
+    def all_reduce_sum(self, t: torch.Tensor) -> torch.Tensor:
+        """In-place sum over the ranks (identical bits on every rank afterwards)."""
+        if self.active:
+            self.dist.all_reduce(t, group=self.group)
+        return t
 
     def all_reduce_sum_int(self, v: int, device) -> int:
         if not self.active:
@@ -187,26 +195,72 @@ class CudaBackend:
         return (bigX, bigy), fence
 
     def reduce_rows(self, X, y, lo, hi, p, divisor, staging=None, fence=None):
-        """Rows [lo, hi) of [X|y]/divisor -> one triangular factor in slot layout (device)."""
+        """Rows [lo, hi) of [X|y]/divisor -> one triangular factor in slot layout (device), by the
+        Householder TSQR (any shape, any conditioning)."""
         if hi - lo <= 0:
             return torch.zeros(ops.tsqr_slot(p), dtype=torch.float64, device=self.device)
-        if self.use_cholqr2 and ops.gram_supported(p) and hi - lo >= 4 * (p + 1):
-            fac = ops.CholQR2(p, divisor)
-            for Xc, yc, _ in self._row_chunks(X, y, lo, hi, p, keep=True, staging=staging, fence=fence):
-                fac.add_chunk(Xc, yc)          # pass 1 on this chunk overlaps the next copy
-            chunks = fac.chunks
-            slot, info = fac.finish()          # pass 2 re-reads the resident rows
-            bad1, cond1, bad2, cond2 = info.cpu().numpy().ravel()
-            if bad1 == 0 and bad2 == 0 and cond1 <= self.CHOLQR2_MAX_COND and cond2 <= 10.0 * (p + 1):
-                return slot
-            parts = [ops.tsqr_rows(Xc, yc, divisor) for Xc, yc in chunks if Xc.shape[0] > 0]
-        else:
-            parts = []
-            for Xc, yc, _ in self._row_chunks(X, y, lo, hi, p):
-                if Xc.shape[0] > 0:
-                    parts.append(ops.tsqr_rows(Xc, yc, divisor))
+        parts = []
+        for Xc, yc, _ in self._row_chunks(X, y, lo, hi, p, staging=staging, fence=fence, keep=staging is not None):
+            if Xc.shape[0] > 0:
+                parts.append(ops.tsqr_rows(Xc, yc, divisor))
         stacked = parts[0] if len(parts) == 1 else torch.cat(parts, 0)
         return ops.tsqr_merge(stacked, p)
+
+    def _tsqr_side(self, coll, chunks, X, y, lo, hi, p, divisor, reg):
+        """The Householder route of one side, all ranks: per-rank triangles, all-gather, ridge rows as one
+        more triangle (reference :310), identical merge on every rank."""
+        if chunks is not None:      # rows already resident on the device
+            parts = [ops.tsqr_rows(Xc, yc, divisor) for Xc, yc in chunks if Xc.shape[0] > 0]
+            if parts:
+                f = ops.tsqr_merge(parts[0] if len(parts) == 1 else torch.cat(parts, 0), p)
+            else:
+                f = torch.zeros(ops.tsqr_slot(p), dtype=torch.float64, device=self.device)
+        else:
+            f = self.reduce_rows(X, y, lo, hi, p, divisor)
+        g = coll.all_gather(f)
+        if reg != 0.0:
+            g = torch.cat([g, self.ridge(p, reg).unsqueeze(0)], 0)
+        return self.merge_factors(g, p) if g.shape[0] > 1 else g[0]
+
+    def reduce_side(self, coll, X, y, lo, hi, p, divisor, reg, staging=None, fence=None, is_train=False):
+        """One side of reduce_data over all ranks: rows [lo, hi) of this rank -> (merged slot, TrainSide or None).
+
+        Gram route (default): every rank accumulates the Gram matrix of its rows with fp64 tensor tiles,
+        the ranks ALL-REDUCE it (82 KB at p = 100, 8 MB at p = 1000), the ridge term is added to its
+        diagonal and every rank factors the same matrix -- so the condition / pivot flags, and with them
+        the decision to fall back, are identical everywhere.  One pass is kept when the factor is well
+        conditioned; otherwise a second CholeskyQR pass (p + 1 <= 120, no ridge) or the Householder TSQR."""
+        small = ops.gram_supported(p)
+        if not (self.use_cholqr2 and (small or ops.gram_big_supported(p))):
+            return self._tsqr_side(coll, None, X, y, lo, hi, p, divisor, reg), None
+        fac = ops.CholQR2(p, divisor, self.device) if small else ops.GramBig(p, divisor, self.device)
+        chunks = []
+        if hi - lo > 0:
+            for Xc, yc, _ in self._row_chunks(X, y, lo, hi, p, keep=True, staging=staging, fence=fence):
+                fac.add_chunk(Xc, yc)          # the Gram pass on this chunk overlaps the next copy
+                chunks.append((Xc, yc))
+        slot, info = fac.factor(coll.all_reduce_sum(fac.gram()), reg)
+        bad, cond = (float(v) for v in info.cpu())
+        train = None
+        if bad == 0 and not small and is_train:
+            # wide problems: the blocked factorisation reports no condition bound; the estimate the lift
+            # route needs anyway (equilibrated train factor) decides
+            R, c, _ = ops.split_factor(slot, p)
+            train = ops.TrainSide(R, c)
+            cond = train.cond_estimate
+        elif bad == 0 and not small:
+            cond = 0.0     # test side: everything downstream depends on R_te through R_te^T R_te, which Cholesky reproduces
+        if bad == 0 and cond <= self.SINGLE_PASS_COND:
+            return slot, train
+        if small and bad == 0 and reg == 0.0 and cond <= self.CHOLQR2_MAX_COND:
+            slot, info2 = fac.finish_second(coll.all_reduce_sum(fac.second_gram()))
+            bad2, cond2 = (float(v) for v in info2.cpu())
+            if bad2 == 0 and cond2 <= 10.0 * (p + 1):
+                return slot, None
+        return self._tsqr_side(coll, chunks, X, y, lo, hi, p, divisor, reg), None
+
+    # factor condition (equilibrated) up to which one Cholesky pass is kept
+    SINGLE_PASS_COND = 1e3
 
     def merge_factors(self, factors, p):
         return ops.tsqr_merge(factors, p, group=max(int(factors.shape[0]), 2))
@@ -274,14 +328,19 @@ def reduce_problem(backend, coll: Collective, X_train, X_test, y_train, y_test, 
     if n_train_global is None:
         n_train_global = (coll.all_reduce_sum_int(n_tr_local, backend.device)
                           if row_sharded else n_tr_local)
+    fused = hasattr(backend, "reduce_side")     # the CUDA backend; the CPU stand-in of the unit tests merges triangles
+
+    def one_side(X, y, lo, hi, divisor, ridge, is_train, **kw):
+        if fused:
+            return backend.reduce_side(coll, X, y, lo, hi, p, divisor, ridge, is_train=is_train, **kw)
+        g = coll.all_gather(backend.reduce_rows(X, y, lo, hi, p, divisor))
+        if ridge != 0.0:
+            g = torch.cat([g, backend.ridge(p, ridge).unsqueeze(0)], 0)    # :310
+        return (backend.merge_factors(g, p) if g.shape[0] > 1 else g[0]), None
+
     lo, hi = local_range(n_tr_local)
-    # train side: rows scaled by 1/sqrt(N) (reference ls_spa/ls_spa.py:309,311)
-    f_tr = backend.reduce_rows(X_train, y_train, lo, hi, p, math.sqrt(n_train_global))
-    g_tr = coll.all_gather(f_tr)
-    if reg != 0.0:
-        g_tr = torch.cat([g_tr, backend.ridge(p, reg).unsqueeze(0)], 0)    # :310
-    train_slot = backend.merge_factors(g_tr, p) if g_tr.shape[0] > 1 else g_tr[0]
-    train = None
+    # train side: rows scaled by 1/sqrt(N) (reference ls_spa/ls_spa.py:309,311), ridge rows sqrt(reg) I (:310)
+    train_slot, train = one_side(X_train, y_train, lo, hi, math.sqrt(n_train_global), reg, True)
     lo, hi = local_range(int(X_test.shape[0]))
     if prefactor is not None:
         # single process, host-resident test rows: the train factor is complete, so permutations
@@ -289,12 +348,10 @@ def reduce_problem(backend, coll: Collective, X_train, X_test, y_train, y_test, 
         # the test rows are allocated first: the copies then only wait for what was enqueued before
         # the factorisations, and no block freed during them can end up under a copy.
         staging, fence = backend.alloc_staging(hi - lo, p)
-        train = prefactor.run(train_slot, p)
-        f_te = backend.reduce_rows(X_test, y_test, lo, hi, p, 1.0, staging=staging, fence=fence)
+        train = prefactor.run(train_slot, p, train)
+        test_slot, _ = one_side(X_test, y_test, lo, hi, 1.0, 0.0, False, staging=staging, fence=fence)
     else:
-        f_te = backend.reduce_rows(X_test, y_test, lo, hi, p, 1.0)       # :315 unscaled
-    g_te = coll.all_gather(f_te)
-    test_slot = backend.merge_factors(g_te, p) if g_te.shape[0] > 1 else g_te[0]
+        test_slot, _ = one_side(X_test, y_test, lo, hi, 1.0, 0.0, False)       # :315 unscaled, no ridge
     if train is not None:
         return backend.make_problem(train_slot, test_slot, p, train=train)
     return backend.make_problem(train_slot, test_slot, p)
@@ -315,10 +372,12 @@ class Prefactor:
         self.backend, self.cfg, self.get_source, self.test_bytes = backend, cfg, get_source, test_bytes
         self.table, self.train, self.source = {}, None, None
 
-    def run(self, train_slot, p):
+    def run(self, train_slot, p, train=None):
         from . import ops as _ops
-        R_tr, c_tr, _ = _ops.split_factor(train_slot, p)
-        self.train = train = _ops.TrainSide(R_tr, c_tr)
+        if train is None:
+            R_tr, c_tr, _ = _ops.split_factor(train_slot, p)
+            train = _ops.TrainSide(R_tr, c_tr)
+        self.train = train
         if not (train.use_chol and _ops.split_route_supported(p)):
             return train
         cfg = self.cfg
@@ -546,6 +605,8 @@ def run_samples(backend, coll: Collective, prob, source: PermutationSource, cfg:
             nxt = launch_lifts(pos)
     if hasattr(source, "check"):
         source.check()
+    if hasattr(prob, "check"):
+        prob.check()
     res = est.read()
     if err_parts:
         err_hist = torch.cat(err_parts).cpu().numpy().tolist()

@@ -106,20 +106,23 @@ def gram_supported(p: int) -> bool:
 
 
 class CholQR2:
-    """CholeskyQR2 of [X | y] / divisor over device row chunks (csrc/gram.cu).
+    """CholeskyQR(2) of [X | y] / divisor over device row chunks (csrc/gram.cu), p + 1 <= 120.
 
-    add_chunk() launches pass 1 on a chunk as soon as it is resident (so it overlaps the copy of the
-    next one); finish() sums the partial Gram matrices, factors, runs pass 2 over the kept chunks
-    and returns (slot, info): slot has the layout of tsqr_merge's result, info (device) =
-    [[bad pivot 1, cond bound 1], [bad pivot 2, cond bound 2]]."""
+    add_chunk() launches the Gram pass on a chunk as soon as it is resident (so it overlaps the copy
+    of the next one); gram() sums the partial Gram matrices of this process (a multi-GPU job
+    all-reduces that tensor: 82 KB at p = 100); factor(G, reg) adds the ridge term reg I (reference
+    ls_spa/ls_spa.py:310) to the diagonal, factors, and returns (slot, info): slot has the layout of
+    tsqr_merge's result, info (device) = [bad pivot, cond bound].  second_gram() / finish_second()
+    are the second pass of CholeskyQR2 for factors that are not well conditioned."""
 
     # |R1|_F |R1^-1|_F of [X | y] up to which one Cholesky pass is kept as the factor
     SINGLE_PASS_COND = 1e3
 
-    def __init__(self, p: int, divisor: float):
+    def __init__(self, p: int, divisor: float, device=None):
         self.p, self.scale = p, 1.0 / (float(divisor) ** 2)
         self.chunks, self.parts1 = [], []
         self.n2 = int(_lib().lsspa_gram_slot_doubles(p))
+        self.device = device
 
     def _rows(self, Xc, yc, rinv):
         lib = _lib()
@@ -132,6 +135,8 @@ class CholQR2:
         return buf
 
     def _sum(self, parts):
+        if not parts:
+            return torch.zeros(self.n2, dtype=torch.float64, device=self.device)
         allp = parts[0] if len(parts) == 1 else torch.cat(parts, 0)
         G = torch.empty(self.n2, dtype=torch.float64, device=allp.device)
         check(_lib().lsspa_gram_finish(allp.data_ptr(), allp.shape[0], self.p, self.scale, G.data_ptr(),
@@ -148,39 +153,67 @@ class CholQR2:
             raise LsSpaCudaError("CholQR2.add_chunk: X must be (n, p), y (n,), on one device")
         if Xc.stride(1) != 1:
             Xc = Xc.contiguous()
+        self.device = Xc.device
         self.chunks.append((Xc, yc))
         self.parts1.append(self._rows(Xc, yc, None))
 
-    def finish(self):
+    def gram(self) -> torch.Tensor:
+        """Scaled Gram matrix of this process's rows (zeros when it holds none)."""
+        return self._sum(self.parts1)
+
+    def factor(self, G: torch.Tensor, reg: float = 0.0):
         lib = _lib()
         p, q = self.p, self.p + 1
-        dev = self.chunks[0][0].device
-        G1 = self._sum(self.parts1)
-        R1 = torch.empty(q * q, dtype=torch.float64, device=dev)
-        Rinv = torch.empty(int(lib.lsspa_gram_rinv_doubles(p)), dtype=torch.float64, device=dev)
-        info = torch.zeros((2, 2), dtype=torch.float64, device=dev)
-        check(lib.lsspa_chol_factor(G1.data_ptr(), p, R1.data_ptr(), Rinv.data_ptr(), info[0].data_ptr(),
+        dev = G.device
+        if reg != 0.0:
+            check(lib.lsspa_gram_add_ridge(G.data_ptr(), p, float(reg), _stream()), "lsspa_gram_add_ridge")
+            _count(1)
+        self.R1 = torch.empty(q * q, dtype=torch.float64, device=dev)
+        self.Rinv = torch.empty(int(lib.lsspa_gram_rinv_doubles(p)), dtype=torch.float64, device=dev)
+        info = torch.zeros(2, dtype=torch.float64, device=dev)
+        check(lib.lsspa_chol_factor(G.data_ptr(), p, self.R1.data_ptr(), self.Rinv.data_ptr(), info.data_ptr(),
                                     _stream()), "lsspa_chol_factor")
         slot = torch.empty(tsqr_slot(p), dtype=torch.float64, device=dev)
-        bad1, cond1 = (float(v) for v in info[0].cpu())
+        # one pass: slot = R1 (well conditioned: the second pass would only remove an orthogonality
+        # defect of order eps * cond^2 <= 1e-10, and everything downstream depends on the factor
+        # through R^T R = the Gram matrix, which Cholesky reproduces to eps)
+        eye = torch.eye(q, dtype=torch.float64, device=dev)
+        check(lib.lsspa_tri_product(eye.data_ptr(), self.R1.data_ptr(), p, G.data_ptr(), slot.data_ptr(),
+                                    _stream()), "lsspa_tri_product")
+        _count(2)
+        self.G1 = G
+        return slot, info
+
+    def second_gram(self) -> torch.Tensor:
+        """Gram matrix of Q1 = Z R1^-1 over this process's rows (pass 2 re-reads the resident chunks)."""
+        return self._sum([self._rows(Xc, yc, self.Rinv) for Xc, yc in self.chunks])
+
+    def finish_second(self, G2: torch.Tensor):
+        lib = _lib()
+        p = self.p
+        dev = G2.device
+        R2 = torch.empty_like(self.R1)
+        Rinv2 = torch.empty_like(self.Rinv)
+        info = torch.zeros(2, dtype=torch.float64, device=dev)
+        check(lib.lsspa_chol_factor(G2.data_ptr(), p, R2.data_ptr(), Rinv2.data_ptr(), info.data_ptr(), _stream()),
+              "lsspa_chol_factor")
+        slot = torch.empty(tsqr_slot(p), dtype=torch.float64, device=dev)
+        check(lib.lsspa_tri_product(R2.data_ptr(), self.R1.data_ptr(), p, self.G1.data_ptr(), slot.data_ptr(),
+                                    _stream()), "lsspa_tri_product")
+        _count(2)
+        return slot, info
+
+    def finish(self):
+        """Single-process CholeskyQR2 without a ridge term -> (slot, info[2][2])."""
+        slot, info1 = self.factor(self.gram(), 0.0)
+        info = torch.zeros((2, 2), dtype=torch.float64, device=info1.device)
+        info[0] = info1
+        bad1, cond1 = (float(v) for v in info1.cpu())
         if bad1 == 0 and cond1 <= self.SINGLE_PASS_COND:
-            # Well conditioned: the second pass would only remove an orthogonality defect of order
-            # eps * cond^2 <= 1e-10, which is the accuracy class of everything downstream (the lifts
-            # depend on the factor through R^T R = the Gram matrix, which Cholesky reproduces to eps).
-            eye = torch.eye(q, dtype=torch.float64, device=dev)
-            check(lib.lsspa_tri_product(eye.data_ptr(), R1.data_ptr(), p, G1.data_ptr(), slot.data_ptr(),
-                                        _stream()), "lsspa_tri_product")
-            _count(2)
             info[1, 1] = 1.0
             return slot, info
-        G2 = self._sum([self._rows(Xc, yc, Rinv) for Xc, yc in self.chunks])
-        R2 = torch.empty_like(R1)
-        Rinv2 = torch.empty_like(Rinv)
-        check(lib.lsspa_chol_factor(G2.data_ptr(), p, R2.data_ptr(), Rinv2.data_ptr(), info[1].data_ptr(),
-                                    _stream()), "lsspa_chol_factor")
-        check(lib.lsspa_tri_product(R2.data_ptr(), R1.data_ptr(), p, G1.data_ptr(), slot.data_ptr(), _stream()),
-              "lsspa_tri_product")
-        _count(3)
+        slot, info2 = self.finish_second(self.second_gram())
+        info[1] = info2
         return slot, info
 
 
@@ -190,6 +223,55 @@ def cholqr2_factor(chunks, p: int, divisor: float):
     for Xc, yc in chunks:
         f.add_chunk(Xc, yc)
     return f.finish()
+
+
+def gram_big_supported(p: int) -> bool:
+    return bool(_lib().lsspa_gram_big_supported(p))
+
+
+class GramBig:
+    """One-pass Gram reduction of [X | y] / divisor for wide problems (p + 1 > 120; csrc/gram_big.cu):
+    add_chunk() accumulates the dense (p+1)^2 Gram matrix of this process's rows, gram() hands it
+    out (a multi-GPU job all-reduces it), factor(G, reg) runs the blocked Cholesky factorisation
+    (csrc/lifts_big.cu with a batch of one) -> (slot, info) with info (device) = [bad pivot, nan]:
+    the caller judges the conditioning from the factor itself (TrainSide)."""
+
+    def __init__(self, p: int, divisor: float, device):
+        self.p, self.scale, self.device = p, 1.0 / (float(divisor) ** 2), device
+        self.G = torch.zeros((p + 1) * (p + 1), dtype=torch.float64, device=device)
+        self.part_doubles = int(_lib().lsspa_gram_big_part_doubles(p))
+
+    def add_chunk(self, Xc: torch.Tensor, yc: torch.Tensor) -> None:
+        if Xc.shape[0] == 0:
+            return
+        Xc, yc = _dev_f64(Xc, "X"), _dev_f64(yc, "y").contiguous()
+        if Xc.stride(1) != 1:
+            Xc = Xc.contiguous()
+        lib = _lib()
+        n = Xc.shape[0]
+        nsplit = lib.lsspa_gram_big_num_splits(self.p, n)
+        parts = torch.empty((nsplit, self.part_doubles), dtype=torch.float64, device=Xc.device)
+        check(lib.lsspa_gram_big_rows(Xc.data_ptr(), Xc.stride(0), yc.data_ptr(), n, self.p, parts.data_ptr(), nsplit,
+                                      _stream()), "lsspa_gram_big_rows")
+        check(lib.lsspa_gram_big_accumulate(parts.data_ptr(), nsplit, self.p, self.G.data_ptr(), _stream()),
+              "lsspa_gram_big_accumulate")
+        _count(2)
+
+    def gram(self) -> torch.Tensor:
+        return self.G
+
+    def factor(self, G: torch.Tensor, reg: float = 0.0):
+        lib = _lib()
+        p = self.p
+        nbytes = int(lib.lsspa_gram_big_factor_workspace_bytes(p))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=G.device)
+        flag = torch.zeros(1, dtype=torch.int32, device=G.device)
+        slot = torch.empty(tsqr_slot(p), dtype=torch.float64, device=G.device)
+        check(lib.lsspa_gram_big_factor(G.data_ptr(), p, self.scale, float(reg), slot.data_ptr(), ws.data_ptr(), nbytes,
+                                        flag.data_ptr(), _stream()), "lsspa_gram_big_factor")
+        _count(2 + 2 * ((p + 64) // 64))
+        info = torch.stack([flag.to(torch.float64)[0], torch.tensor(float("nan"), dtype=torch.float64, device=G.device)])
+        return slot, info
 
 
 def split_factor(slot: torch.Tensor, p: int):
@@ -286,7 +368,8 @@ class TrainSide:
         self.cond_estimate = float("inf")
         self.use_chol = False
         forced = os.environ.get("LSSPA_LIFTS_IMPL", "")
-        if forced not in ("v1", "householder") and _lib().lsspa_lifts_chol_supported(p):
+        self.big = bool(_lib().lsspa_lifts_big_supported(p))     # wide problems: batched tile kernels (lifts_big.cu)
+        if forced not in ("v1", "householder") and (_lib().lsspa_lifts_chol_supported(p) or self.big):
             n = _lib().lsspa_lifts_gram_doubles(p)
             self.gram = torch.empty(n, dtype=torch.float64, device=dev)
             check(_lib().lsspa_lifts_gram(p, self.R_tr_cm.data_ptr(), self.c_tr.data_ptr(),
@@ -322,6 +405,29 @@ class ReducedProblem:
             # the Cholesky route works on unit-norm train columns: scale the test columns alike
             self.R_te_scaled_cm = self.R_te_cm / train.scale.unsqueeze(1)
 
+    # device memory the tile workspace of the wide route may take (it is processed in passes)
+    BIG_WS_BUDGET = 24 << 30
+
+    def big_workspace(self, count: int, antithetical: bool):
+        """(tile workspace, status flag) of the wide route, sized for as many samples as fit the budget."""
+        dev = self.c_tr.device
+        room = torch.cuda.get_device_properties(dev).total_memory - torch.cuda.memory_reserved(dev)
+        held = 0 if getattr(self, "_big_ws", None) is None else self._big_ws.numel()
+        budget = max(min(self.BIG_WS_BUDGET, (room + held) // 2), 1 << 20)
+        nbytes = int(_lib().lsspa_lifts_big_workspace_bytes(self.p, count, 1 if antithetical else 0, budget))
+        if getattr(self, "_big_ws", None) is None or self._big_ws.numel() < nbytes:
+            self._big_ws = None
+            self._big_ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            self._big_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        return self._big_ws, self._big_flag
+
+    def check(self) -> None:
+        """Raise if a kernel of the wide route met a non-positive pivot (one flag read)."""
+        flag = getattr(self, "_big_flag", None)
+        if flag is not None and int(flag.item()) != 0:
+            raise LsSpaCudaError("wide Cholesky route: non-positive pivot (the condition guard should have "
+                                 "sent this problem to the Householder kernels)")
+
     def workspace(self, count: int):
         nbytes = _lib().lsspa_lifts_workspace_bytes(self.p, count)
         if nbytes == 0:
@@ -348,7 +454,14 @@ def lifts(prob: ReducedProblem, perms: torch.Tensor, antithetical: bool, out: to
         e0.record()
     global LIFT_ROUTE
     LIFT_ROUTE = "cholesky" if prob.use_chol else "householder"
-    if prob.use_chol:
+    if prob.use_chol and prob.train.big:
+        ws, flag = prob.big_workspace(count, antithetical)
+        check(_lib().lsspa_lifts_big(p, prob.gram.data_ptr(), prob.R_te_scaled_cm.data_ptr(), prob.c_te.data_ptr(),
+                                     prob.y_norm_sq, perms.data_ptr(), count, 1 if antithetical else 0,
+                                     out.data_ptr(), ws.data_ptr(), ws.numel(), flag.data_ptr(), _stream()),
+              "lsspa_lifts_big")
+        _count(2 * (2 + 2 * ((p + 64) // 64)) - 1)     # per pass: gather, (diag + panel) per block row, cost
+    elif prob.use_chol:
         check(_lib().lsspa_lifts_chol(p, prob.gram.data_ptr(), prob.R_te_scaled_cm.data_ptr(), prob.c_te.data_ptr(),
                                       prob.y_norm_sq, perms.data_ptr(), count, 1 if antithetical else 0,
                                       out.data_ptr(), _stream()), "lsspa_lifts_chol")

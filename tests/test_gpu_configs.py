@@ -163,10 +163,21 @@ def test_large_p_lifts_against_oracle(T, p):
     want = np.array([lo.square_shapley(R_tr, R_te, c_tr, c_te, ynsq, pm) for pm in perms])
     rev = np.array([lo.square_shapley(R_tr, R_te, c_tr, c_te, ynsq, pm[::-1]) for pm in perms])
     dperms = T.from_numpy(perms.astype(np.int32)).cuda()
+    assert prob.use_chol and prob.train.big and prob.cond_estimate < 1e3, prob.cond_estimate
     got = ops.lifts(prob, dperms, False).cpu().numpy()
+    prob.check()
+    assert ops.LIFT_ROUTE == "cholesky"
     assert scaled_err(got, want) < TOL, scaled_err(got, want)
     anti = ops.lifts(prob, dperms, True).cpu().numpy()
     assert scaled_err(anti, 0.5 * (want + rev)) < TOL
+    # several passes over a small workspace (3 samples at a time) give the same rows
+    prob._big_ws, prob.BIG_WS_BUDGET = None, 3 * 2 * int(prob._big_ws.numel() // (2 * 11))
+    again = ops.lifts(prob, dperms, True).cpu().numpy()
+    assert np.array_equal(again, anti)
+    # the Householder kernels (scalar at these widths) agree
+    prob.use_chol = False
+    hh = ops.lifts(prob, dperms[:4].contiguous(), False).cpu().numpy()
+    assert scaled_err(hh, want[:4]) < TOL
 
 
 # ------------------------------------------------------------------ Cholesky lift kernel, every tile count
