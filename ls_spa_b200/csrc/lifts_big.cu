@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(256) big_diag_kernel(BigParams a) {
   }
   for (int k = 0; k < j; ++k) {
     const double *t = tile_ptr(a, ev, k, j);
-#pragma unroll 2
+#pragma unroll 4
     for (int kk = 0; kk < 8; ++kk) {
       const double2 av = *reinterpret_cast<const double2 *>(t + (size_t)(kk * 8 + mi) * 64 + 2 * lane);
       double2 bv[8];
@@ -238,14 +238,22 @@ __global__ void __launch_bounds__(256) big_diag_kernel(BigParams a) {
     }
     __syncthreads();
   }
-  // inverse of the upper-triangular U, one column per thread (zero pivots give zero rows / columns)
-  if (tid < kNB) {
-    const int n = tid;
-    for (int i = n; i >= 0; --i) {
-      double s = (i == n) ? 1.0 : 0.0;
-      for (int k = i + 1; k <= n; ++k) s = fma(-S[i][k], V[k][n], s);
-      const double d = S[i][i];
-      V[i][n] = (d != 0.0) ? s / d : 0.0;
+  // inverse of the upper-triangular U: column n by back substitution, four lanes per column (they split
+  // the dot product of each step and combine with two shuffles; a column only ever touches its own
+  // entries of V, so warp-level synchronisation suffices).  Zero pivots give zero rows / columns.
+  {
+    const int n = tid >> 2, part = tid & 3;
+    for (int i = kNB - 1; i >= 0; --i) {          // uniform trip count: columns n < i idle through the step
+      double s = 0.0;
+      if (i <= n)
+        for (int k = i + 1 + part; k <= n; k += 4) s = fma(-S[i][k], V[k][n], s);
+      s += __shfl_xor_sync(kFull, s, 1);
+      s += __shfl_xor_sync(kFull, s, 2);
+      if (i <= n && part == 0) {
+        const double d = S[i][i];
+        V[i][n] = (d != 0.0) ? (s + ((i == n) ? 1.0 : 0.0)) / d : 0.0;
+      }
+      __syncwarp();
     }
   }
   __syncthreads();
@@ -527,14 +535,17 @@ __device__ double power_sigma(int p, const double *__restrict__ A, const double 
     for (int j = tid; j < p; j += 1024) xs[j] = x[j] / nx / (scale ? scale[j] : 1.0);
     __syncthreads();
     for (int i = tid; i < p; i += 1024) {          // y = A x: row i, columns j >= i (coalesced over i)
-      double s0 = 0.0, s1 = 0.0;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
       int j = i;
-      for (; j + 1 < p; j += 2) {
+#pragma unroll 2
+      for (; j + 3 < p; j += 4) {
         s0 = fma(A[(size_t)j * p + i], xs[j], s0);
         s1 = fma(A[(size_t)(j + 1) * p + i], xs[j + 1], s1);
+        s2 = fma(A[(size_t)(j + 2) * p + i], xs[j + 2], s2);
+        s3 = fma(A[(size_t)(j + 3) * p + i], xs[j + 3], s3);
       }
-      if (j < p) s0 = fma(A[(size_t)j * p + i], xs[j], s0);
-      y[i] = s0 + s1;
+      for (; j < p; ++j) s0 = fma(A[(size_t)j * p + i], xs[j], s0);
+      y[i] = (s0 + s1) + (s2 + s3);
     }
     __syncthreads();
     sigma = block_norm(y);
@@ -552,16 +563,16 @@ __device__ double power_sigma(int p, const double *__restrict__ A, const double 
 
 // info[2] = |R'|_F |R'^-1|_F and info[3] = sqrt(max_i sum_j |Gh_ij|) sqrt(|R'^-1|_1 |R'^-1|_inf) are rigorous
 // bounds >= cond_2(R') but over-state it by sqrt(p)-like factors at these widths (24x at p = 1000 on the
-// benchmark data), so info[4] = sigma_max(R') sigma_max(R'^-1) by 40 power iterations each (converges from
-// below; within 1 % here) is used with a safety factor: info[0] = min(info[2], info[3], 1.25 info[4]).
+// benchmark data), so info[4] = sigma_max(R') sigma_max(R'^-1) by 24 power iterations each (converges from
+// below; within 4 % here) is used with a safety factor: info[0] = min(info[2], info[3], 1.25 info[4]).
 // info[1] = min|R'_kk| / max|R'_kk|.
 __global__ void __launch_bounds__(1024) big_cond_kernel(int p, const double *__restrict__ R, const double *__restrict__ D,
                                                         const double *__restrict__ Gh, const double *__restrict__ Xinv,
                                                         const double *__restrict__ colstat, double *__restrict__ info) {
   extern __shared__ double pw[];   // 3 p
   __shared__ double red[6][32];
-  const double s_r = power_sigma(p, R, D, pw, pw + p, pw + 2 * p, &red[0][0], 40);
-  const double s_i = power_sigma(p, Xinv, nullptr, pw, pw + p, pw + 2 * p, &red[0][0], 40);
+  const double s_r = power_sigma(p, R, D, pw, pw + p, pw + 2 * p, &red[0][0], 24);
+  const double s_i = power_sigma(p, Xinv, nullptr, pw, pw + p, pw + 2 * p, &red[0][0], 24);
   __syncthreads();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double fr = 0.0, fi = 0.0, cm = 0.0, rm = 0.0, gs = 0.0, dmin = 1e300, dmax = 0.0;

@@ -19,6 +19,8 @@
 
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace lsspa {
 namespace {
 
@@ -535,6 +537,375 @@ __global__ void __launch_bounds__(256, MINB) lifts_chol_kernel(CholParams a) {
   }
 }
 
+
+// =====================================================================================================
+// Packed variant of the fused kernel (MODE 0): four warps per CTA and only the UPPER tiles of the
+// permuted Gram matrix in shared memory, so that four independent factorisations are resident per SM
+// at p = 100 (one serial diagonal chain per SM sub-partition instead of two per SM) -- 55 KB per CTA
+// instead of 102 KB.  Column tile L (8 columns) is stored column-major with its own leading dimension
+// ld(L) = 8 (L + 1) rounded up to 8 mod 16 (conflict-free tile accesses) at offset off(L).  The inverse
+// of diagonal block s overwrites the diagonal tile (s, s), which nothing reads once it is factored --
+// except in the last row block, whose diagonal tile may hold entries of c~ (column p): that one keeps U
+// and its inverse goes to a 64-double side buffer.  The chain warp rotates with blockIdx so that the
+// chains of co-resident CTAs issue on different sub-partitions.
+__host__ __device__ constexpr int pk_rows(int L, int RT) { return 8 * ((L < RT ? L : RT - 1) + 1); }
+__host__ __device__ constexpr int pk_ld(int L, int RT) { return (pk_rows(L, RT) % 16 == 8) ? pk_rows(L, RT) : pk_rows(L, RT) + 8; }
+__host__ __device__ constexpr int pk_off(int L, int RT) {
+  int o = 0;
+  for (int l = 0; l < L; ++l) o += 8 * pk_ld(l, RT);
+  return o;
+}
+// run-time forms (L <= RT): ld = 8 (L' + 1) + 8 (L' & 1) with L' = min(L, RT - 1); off = 64 (L (L + 1) / 2 + L / 2)
+template <int RT>
+__device__ __forceinline__ int pk_ld_rt(int L) {
+  const int l = L < RT ? L : RT - 1;
+  return 8 * (l + 1) + 8 * (l & 1);
+}
+template <int RT>
+__device__ __forceinline__ int pk_off_rt(int L) {
+  // columns before tile L: tiles 0..L-1, all with index < RT (L <= RT)
+  return 32 * L * (L + 1) + 64 * (L >> 1);
+}
+// tile (k, L) of the packed array: rows 8k.., column tile L
+template <int RT>
+__device__ __forceinline__ double2 ldp(const double *A, int k, int L, int c, int q) {
+  return *reinterpret_cast<const double2 *>(A + pk_off_rt<RT>(L) + c * pk_ld_rt<RT>(L) + 8 * k + 2 * q);
+}
+template <int RT>
+__device__ __forceinline__ void stp(double *A, int k, int L, int c, int q, double2 v) {
+  *reinterpret_cast<double2 *>(A + pk_off_rt<RT>(L) + c * pk_ld_rt<RT>(L) + 8 * k + 2 * q) = v;
+}
+// inverse of diagonal block J (see above): tile (J, J) for J < RT - 1, the side buffer for the last block
+template <int RT>
+__device__ __forceinline__ double2 ld_dinv(const double *A, const double *Dlast, int J, int c, int q) {
+  if (J < RT - 1) return ldp<RT>(A, J, J, c, q);
+  return *reinterpret_cast<const double2 *>(Dlast + c * 8 + 2 * q);
+}
+
+// Elimination step J of one 8-row tile of X on the packed array (see elim_step)
+template <int RT, int J>
+__device__ __forceinline__ void elim_step4(double (&xr)[RT][2], double &r_in, double *wc, const double *A,
+                                           const double *Dlast, const double *cvec, int p, int c, int q) {
+  const double2 dv = ld_dinv<RT>(A, Dlast, J, c, q);
+  double m0 = 0.0, m1 = 0.0;
+  dmma(m0, m1, xr[J][0], dv.x);
+  dmma(m0, m1, xr[J][1], dv.y);
+  const double2 cv = *reinterpret_cast<const double2 *>(cvec + 8 * J + 2 * q);
+  double ra = r_in, rb = r_in;
+  dmma(ra, rb, -m0, (2 * q <= c) ? cv.x : 0.0);
+  dmma(ra, rb, -m1, (2 * q + 1 <= c) ? cv.y : 0.0);
+  const double d0 = ra * ra, d1 = rb * rb;
+  const bool odd = (c & 1) != 0;
+  double tot = (odd ? d1 : d0) + __shfl_xor_sync(kFull, odd ? d0 : d1, 4);
+  tot += __shfl_xor_sync(kFull, tot, 8);
+  tot += __shfl_xor_sync(kFull, tot, 16);
+  if (c < 2) {
+    const int k0 = 8 * J + 2 * q + c;
+    if (k0 < p) wc[k0] += tot;
+  }
+  r_in = __shfl_sync(kFull, rb, 3, 4);
+  m0 = -m0;
+  m1 = -m1;
+#pragma unroll
+  for (int L = J + 1; L < RT; ++L) {
+    const double2 rt = *reinterpret_cast<const double2 *>(A + pk_off(L, RT) + c * pk_ld(L, RT) + 8 * J + 2 * q);
+    dmma(xr[L][0], xr[L][1], m0, rt.x);
+    dmma(xr[L][0], xr[L][1], m1, rt.y);
+  }
+}
+template <int RT, int J = 0>
+__device__ __forceinline__ void elim_all4(double (&xr)[RT][2], double &r_in, double *wc, const double *A,
+                                          const double *Dlast, const double *cvec, int p, int c, int q) {
+  if constexpr (J < RT) {
+    elim_step4<RT, J>(xr, r_in, wc, A, Dlast, cvec, p, c, q);
+    elim_all4<RT, J + 1>(xr, r_in, wc, A, Dlast, cvec, p, c, q);
+  }
+}
+
+// sum_{k < kend} R(k, L)^T R(k, S), packed array, four independent chains
+template <int RT>
+__device__ __forceinline__ double2 acc_tile4(const double *A, int kend, int L, int S, int c, int q) {
+  const double *pl = A + pk_off_rt<RT>(L) + c * pk_ld_rt<RT>(L) + 2 * q;
+  const double *ps = A + pk_off_rt<RT>(S) + c * pk_ld_rt<RT>(S) + 2 * q;
+  double p0 = 0.0, p1 = 0.0, r0 = 0.0, r1 = 0.0, e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0;
+  int k = 0;
+  for (; k + 1 < kend; k += 2) {
+    const double2 xa = *reinterpret_cast<const double2 *>(pl + 8 * k);
+    const double2 xb = *reinterpret_cast<const double2 *>(ps + 8 * k);
+    const double2 ya = *reinterpret_cast<const double2 *>(pl + 8 * k + 8);
+    const double2 yb = *reinterpret_cast<const double2 *>(ps + 8 * k + 8);
+    dmma(p0, p1, xa.x, xb.x);
+    dmma(r0, r1, ya.x, yb.x);
+    dmma(e0, e1, xa.y, xb.y);
+    dmma(f0, f1, ya.y, yb.y);
+  }
+  if (k < kend) {
+    const double2 xa = *reinterpret_cast<const double2 *>(pl + 8 * k);
+    const double2 xb = *reinterpret_cast<const double2 *>(ps + 8 * k);
+    dmma(p0, p1, xa.x, xb.x);
+    dmma(e0, e1, xa.y, xb.y);
+  }
+  return make_double2((p0 + r0) + (e0 + f0), (p1 + r1) + (e1 + f1));
+}
+
+constexpr int kC4Threads = 128;
+
+template <int RT, int PT, int MINB>
+__global__ void __launch_bounds__(kC4Threads, MINB) lifts_chol4_kernel(CholParams a, int sms) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int p = a.p;
+  constexpr int NR = 8 * RT;
+  constexpr int TOT = pk_off(PT, RT);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c = lane >> 2, q = lane & 3;
+  // role 0 = diagonal chain, roles 1..3 = workers; rotated so that co-resident CTAs (blockIdx differing by
+  // multiples of the SM count on a full grid) run their chains on different SM sub-partitions
+  const int role = (warp - (int)((blockIdx.x / (unsigned)sms) & 3u)) & 3;
+
+  double *A = reinterpret_cast<double *>(smem_raw);   // packed upper tiles
+  double *Dlast = A + TOT;                            // 64: inverse of the last diagonal block
+  double *wcost = Dlast + 64;                         // 4 x NR per-warp cost partials
+  double *cost = wcost + (size_t)4 * NR;              // p + 2
+  double *acc = cost + (p + 2);                       // p
+  int *perm_s = reinterpret_cast<int *>(acc + p + (p & 1));  // p + 1
+
+  const int halves = a.anti ? 2 : 1;
+  const double weight = a.anti ? 0.5 : 1.0;
+  const int ldg = p + 1;
+  constexpr int LP = PT - 1;                          // column tile holding column p (c~)
+  const double *cvec = A + pk_off(LP, RT) + (p - 8 * LP) * pk_ld(LP, RT);
+
+  for (int64_t sidx = blockIdx.x; sidx < a.count; sidx += gridDim.x) {
+    for (int h = 0; h < halves; ++h) {
+      __syncthreads();
+      for (int k = tid; k <= p; k += kC4Threads)
+        perm_s[k] = (k == p) ? p : a.perms[sidx * p + (h == 0 ? k : p - 1 - k)];
+      __syncthreads();
+      const long long t_a = LSSPA_CLOCK();
+      // ---- phase 0: gather the upper tiles of Gh[pi^, pi^] with 8-byte cp.async (zero-fill where masked):
+      // warp w takes the columns l = w + 4 g, lane the rows 2 lane, 2 lane + 1 (+ 64); every copy of the
+      // evaluation is in flight before the first one is awaited
+      {
+        constexpr int NRR = (NR + 63) / 64;
+        int pr[NRR][2];
+        bool pv[NRR][2];
+#pragma unroll
+        for (int r = 0; r < NRR; ++r) {
+          const int i0 = 2 * lane + 64 * r;
+          pv[r][0] = i0 < p;
+          pv[r][1] = i0 + 1 < p;
+          pr[r][0] = pv[r][0] ? perm_s[i0] : 0;
+          pr[r][1] = pv[r][1] ? perm_s[i0 + 1] : 0;
+        }
+#pragma unroll 2
+        for (int g = 0; g < 2 * PT; ++g) {
+          const int l = warp + 4 * g;
+          const int L = l >> 3, cc = l & 7;
+          const bool colv = l <= p;
+          const double *src = a.Gh + (size_t)perm_s[colv ? l : p] * ldg;
+          const int rows = 8 * ((L < RT ? L : RT - 1) + 1);
+          double *dst = A + pk_off_rt<RT>(L) + cc * pk_ld_rt<RT>(L);
+#pragma unroll
+          for (int r = 0; r < NRR; ++r) {
+            const int i0 = 2 * lane + 64 * r;
+            if (i0 < rows) {
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const unsigned dsta = (unsigned)__cvta_generic_to_shared(dst + i0 + e);
+                const int nbytes = (colv && pv[r][e]) ? 8 : 0;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dsta), "l"(src + pr[r][e]), "r"(nbytes)
+                             : "memory");
+              }
+            }
+          }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+      if (warp == 3) {
+        double s0 = 0.0;
+        for (int i = lane; i < p; i += 32) s0 = fma(a.cte[i], a.cte[i], s0);
+        s0 = warp_sum(s0);
+        if (lane == 0) cost[0] = s0;
+      }
+      for (int e = tid; e < 4 * NR; e += kC4Threads) wcost[e] = 0.0;
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+      const long long t_b = LSSPA_CLOCK();
+      long long t_work = 0, t_w1 = 0, t_w2 = 0, t_sf = 0;
+
+      // ---- phase 1: left-looking blocked Cholesky around the serial diagonal chain (see lifts_chol_kernel).
+      // Tile (r, L), L > r, belongs to worker (L - r - 1) % 3; the diagonal tile of row r is pre-accumulated in
+      // place by worker r % 3.
+      constexpr int NSL = (PT - 1 + 2) / 3;
+      double *wc = wcost + (size_t)warp * NR;
+      {
+        double2 tv[NSL];
+#pragma unroll
+        for (int sl = 0; sl < NSL; ++sl) {
+          const int L = role + 3 * sl;  // row block 0
+          tv[sl] = make_double2(0.0, 0.0);
+          if (role != 0 && L < PT) tv[sl] = ldp<RT>(A, 0, L, c, q);
+        }
+        for (int s = 0; s < RT; ++s) {
+          const int nf = (p - 8 * s < 8) ? p - 8 * s : 8;
+          double2 tvn[NSL];
+          const long long u0 = LSSPA_CLOCK();
+          if (role == 0) {
+            double2 t = ldp<RT>(A, s, s, c, q);
+            if (s > 0) {
+              const double2 xa = ldp<RT>(A, s - 1, s, c, q);
+              double p0 = 0.0, p1 = 0.0, e0 = 0.0, e1 = 0.0;
+              dmma(p0, p1, xa.x, xa.x);
+              dmma(e0, e1, xa.y, xa.y);
+              t.x -= p0 + e0;
+              t.y -= p1 + e1;
+            }
+            double y0, y1;
+            diag_factor(t.x, t.y, y0, y1, nf, lane);
+            if (s < RT - 1) {
+              stp<RT>(A, s, s, c, q, make_double2(y0, y1));       // inverse over the (dead) diagonal tile
+            } else {
+              stp<RT>(A, s, s, c, q, t);                          // last block: U stays (it may hold c~)
+              *reinterpret_cast<double2 *>(Dlast + c * 8 + 2 * q) = make_double2(y0, y1);
+            }
+          } else if (s + 1 < RT) {
+#pragma unroll
+            for (int sl = 0; sl < NSL; ++sl) {
+              const int L = s + 1 + role + 3 * sl;
+              tvn[sl] = make_double2(0.0, 0.0);
+              if (L < PT) {
+                const double2 g = ldp<RT>(A, s + 1, L, c, q);
+                const double2 z = acc_tile4<RT>(A, s, L, s + 1, c, q);
+                tvn[sl] = make_double2(g.x - z.x, g.y - z.y);
+              }
+            }
+            if (role == 1 + (s + 1) % 3 && s > 0) {
+              const double2 g = ldp<RT>(A, s + 1, s + 1, c, q);
+              const double2 z = acc_tile4<RT>(A, s, s + 1, s + 1, c, q);
+              stp<RT>(A, s + 1, s + 1, c, q, make_double2(g.x - z.x, g.y - z.y));
+            }
+          }
+          const long long u1 = LSSPA_CLOCK();
+          __syncthreads();
+          const long long u2 = LSSPA_CLOCK();
+          t_work += u1 - u0;
+          t_w1 += u2 - u1;
+          if (role != 0) {
+            const double2 dv = ld_dinv<RT>(A, Dlast, s, c, q);
+#pragma unroll
+            for (int sl = 0; sl < NSL; ++sl) {
+              const int L = s + role + 3 * sl;
+              if (L < PT) {
+                double r0 = 0.0, r1 = 0.0;
+                dmma(r0, r1, tv[sl].x, dv.x);
+                dmma(r0, r1, tv[sl].y, dv.y);
+                stp<RT>(A, s, L, c, q, make_double2(r0, r1));
+              }
+            }
+          }
+          const long long u3 = LSSPA_CLOCK();
+          __syncthreads();
+          const long long u4 = LSSPA_CLOCK();
+          t_sf += u3 - u2;
+          t_w2 += u4 - u3;
+          if (role != 0 && s + 1 < RT) {
+#pragma unroll
+            for (int sl = 0; sl < NSL; ++sl) {
+              const int L = s + 1 + role + 3 * sl;
+              tv[sl] = tvn[sl];
+              if (L < PT) {
+                const double2 xa = ldp<RT>(A, s, L, c, q);
+                const double2 xb = ldp<RT>(A, s, s + 1, c, q);
+                double p0 = 0.0, p1 = 0.0, e0 = 0.0, e1 = 0.0;
+                dmma(p0, p1, xa.x, xb.x);
+                dmma(e0, e1, xa.y, xb.y);
+                tv[sl].x -= p0 + e0;
+                tv[sl].y -= p1 + e1;
+              }
+            }
+          }
+          t_sf += LSSPA_CLOCK() - u4;
+        }
+      }
+      const long long t_c = LSSPA_CLOCK();
+      // ---- phase 2: elimination of X = R_te[:, perm], row tiles warp, warp + 4, ...
+      {
+        double xr[RT][2];
+        double r_in = 0.0;
+        for (int it = warp; it < RT; it += 4) {
+          load_x<RT>(xr, r_in, a, perm_s, it, p, c, q);
+          elim_all4<RT>(xr, r_in, wc, A, Dlast, cvec, p, c, q);
+        }
+      }
+      const long long t_d = LSSPA_CLOCK();
+      __syncthreads();
+#ifdef LSSPA_LIFTS_TIMING
+      if (a.dbg != nullptr && blockIdx.x == 0 && lane == 0 && sidx == blockIdx.x && h == 0) {
+        long long *d = a.dbg + warp * 8;
+        d[0] = t_b - t_a;   // gather
+        d[1] = t_work;      // chain: diagonal blocks / workers: pre-accumulation
+        d[2] = t_w1;        // wait at barrier 1
+        d[3] = t_sf;        // scale + finish phases
+        d[4] = t_w2;        // wait at barrier 2
+        d[5] = t_c - t_b;   // whole phase 1
+        d[6] = t_d - t_c;   // phase 2 (this warp)
+        d[7] = LSSPA_CLOCK() - t_d;   // wait for the slowest warp of phase 2
+      }
+#else
+      (void)t_a; (void)t_b; (void)t_c; (void)t_d; (void)t_work; (void)t_w1; (void)t_w2; (void)t_sf;
+#endif
+      for (int k = tid; k < p; k += kC4Threads) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) sacc += wcost[(size_t)w * NR + k];
+        cost[k + 1] = sacc;
+      }
+      __syncthreads();
+      for (int k = tid; k < p; k += kC4Threads) {
+        const double lift = (cost[k] - cost[k + 1]) * a.inv_ynsq;
+        const int f = perm_s[k];
+        acc[f] = (h == 0 ? 0.0 : acc[f]) + weight * lift;
+      }
+    }
+    __syncthreads();
+    for (int f = tid; f < p; f += kC4Threads) a.out[sidx * p + f] = acc[f];
+  }
+}
+
+template <int RT>
+size_t chol4_smem_bytes(int p, int pt) {
+  const int tot = (pt == RT) ? pk_off(RT, RT) : pk_off(RT + 1, RT);
+  const size_t d = (size_t)tot + 64 + (size_t)4 * 8 * RT + (size_t)(p + 2) + (size_t)(p + 1);
+  return d * sizeof(double) + (size_t)(p + 1) * sizeof(int) + 16;
+}
+
+template <int RT, int PT, int MINB>
+int launch_chol4(const CholParams &a, int grid, size_t smem, int sms, cudaStream_t st) {
+  LSSPA_CUDA_TRY(cudaFuncSetAttribute(lifts_chol4_kernel<RT, PT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+  LSSPA_CUDA_TRY(cudaFuncSetAttribute(lifts_chol4_kernel<RT, PT, MINB>,
+                                      cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  lifts_chol4_kernel<RT, PT, MINB><<<grid, kC4Threads, smem, st>>>(a, sms);
+  LSSPA_LAUNCH_CHECK();
+  return LSSPA_OK;
+}
+
+// p = 49 .. 128 (RT = 7 .. 16): CTAs per SM from the packed footprint
+template <int RT>
+int run_chol4(const CholParams &a, int64_t count, cudaStream_t st) {
+  const DeviceInfo &d = device_info();
+  const int sms = d.sm_count > 0 ? d.sm_count : 148;
+  const size_t smem = chol4_smem_bytes<RT>(a.p, a.pt);
+  int per_sm = (int)((size_t)(228 * 1024) / (smem + 1024));
+  if (per_sm > 4) per_sm = 4;
+  if (per_sm < 1) per_sm = 1;
+  int64_t grid = (int64_t)per_sm * sms;
+  if (grid > count) grid = count;
+  constexpr int MINB = RT <= 13 ? 4 : (RT <= 16 ? 2 : 1);
+  return (a.pt == RT) ? launch_chol4<RT, RT, MINB>(a, (int)grid, smem, sms, st)
+                      : launch_chol4<RT, RT + 1, MINB>(a, (int)grid, smem, sms, st);
+}
+
 size_t chol_smem_bytes(int p) {
   const int rt = (p + 7) / 8, pt = (p + 8) / 8;
   const int ld = chol_ld(rt);
@@ -788,6 +1159,25 @@ static int chol_run(int mode, int p, const double *gram, const double *R_te_cm, 
   int64_t grid = (int64_t)per_sm * sms;
   if (grid > count) grid = count;
   cudaStream_t st = as_stream(stream);
+  static const bool packed = [] {
+    const char *e = getenv("LSSPA_CHOL_PACKED");     // 0: the eight-warp kernel everywhere (A/B timing)
+    return !(e && e[0] == '0');
+  }();
+  if (mode == 0 && packed) {
+    switch (a.rt) {
+      case 7: return run_chol4<7>(a, count, st);
+      case 8: return run_chol4<8>(a, count, st);
+      case 9: return run_chol4<9>(a, count, st);
+      case 10: return run_chol4<10>(a, count, st);
+      case 11: return run_chol4<11>(a, count, st);
+      case 12: return run_chol4<12>(a, count, st);
+      case 13: return run_chol4<13>(a, count, st);
+      case 14: return run_chol4<14>(a, count, st);
+      case 15: return run_chol4<15>(a, count, st);
+      case 16: return run_chol4<16>(a, count, st);
+      default: break;
+    }
+  }
   switch (a.rt) {
     case 3: return launch_chol_rt<3>(a, (int)grid, smem, mode, st);
     case 4: return launch_chol_rt<4>(a, (int)grid, smem, mode, st);

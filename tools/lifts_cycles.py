@@ -20,6 +20,6 @@ ops.lifts(prob, perms, True)
 torch.cuda.synchronize()
 lib.lsspa_debug_set_lifts_counters(None)
 d = buf.cpu().numpy().reshape(8, 8).copy()
-print("warp  gather   panel|diag  trailing|accumulate  barrier-wait  phase1  phase1.5+2")
+print("warp  gather   panel|diag  trailing|accumulate  barrier-wait  phase1  phase1.5+2   (packed kernel: gather, work, wait1, scale+finish, wait2, phase1, phase2, tail-wait)")
 for w in range(8):
     print(w, d[w, :8])
