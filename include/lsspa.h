@@ -93,6 +93,13 @@ LSSPA_API int lsspa_gram_finish(const double *parts, int count, int p, double sc
                                 void *stream);
 LSSPA_API int lsspa_chol_factor(const double *G, int p, double *R_out, double *Rinv_out, double *info,
                                 void *stream);
+/* lsspa_chol_factor that also leaves, in gram_out (layout of lsspa_lifts_gram, may be NULL), what the
+ * Cholesky lift route needs from the TRAIN factor -- the Gram matrix with unit feature diagonal, the column
+ * scales and the condition bound of the equilibrated leading p x p block -- straight from G (= R^T R),
+ * so that a job does not run lsspa_lifts_gram on the factor it has just computed */
+LSSPA_API int lsspa_chol_factor_gram(const double *G, int p, double *R_out, double *Rinv_out, double *info,
+                                     double *gram_out_or_null, void *stream);
+
 /* ridge rows of the train block (:310) as reg added to the first p diagonal entries of G (in place) */
 LSSPA_API int lsspa_gram_add_ridge(double *G, int p, double reg, void *stream);
 LSSPA_API int lsspa_tri_product(const double *R2, const double *R1, int p, const double *G1, double *out_slot,

@@ -41,6 +41,7 @@ SIGNATURES = {
     "lsspa_gram_big_accumulate": (c_i32, [vp, c_i32, c_i32, vp, vp]),
     "lsspa_gram_big_factor_workspace_bytes": (sz, [c_i32]),
     "lsspa_gram_big_factor": (c_i32, [vp, c_i32, c_f64, c_f64, vp, vp, sz, vp, vp]),
+    "lsspa_chol_factor_gram": (c_i32, [vp, c_i32, vp, vp, vp, vp, vp]),
     "lsspa_tri_product": (c_i32, [vp, vp, c_i32, vp, vp, vp]),
     "lsspa_perms_exact": (c_i32, [c_i32, c_u64, c_i64, vp, vp]),
     "lsspa_perms_pcg64_workspace_bytes": (sz, [c_i32, c_i64]),

@@ -901,7 +901,7 @@ int run_chol4(const CholParams &a, int64_t count, cudaStream_t st) {
   if (per_sm < 1) per_sm = 1;
   int64_t grid = (int64_t)per_sm * sms;
   if (grid > count) grid = count;
-  constexpr int MINB = RT <= 13 ? 4 : (RT <= 16 ? 2 : 1);
+  constexpr int MINB = RT <= 13 ? 4 : (RT <= 15 ? 3 : 2);   // resident CTAs the register budget is cut for
   return (a.pt == RT) ? launch_chol4<RT, RT, MINB>(a, (int)grid, smem, sms, st)
                       : launch_chol4<RT, RT + 1, MINB>(a, (int)grid, smem, sms, st);
 }

@@ -239,9 +239,20 @@ class CudaBackend:
             for Xc, yc, _ in self._row_chunks(X, y, lo, hi, p, keep=True, staging=staging, fence=fence):
                 fac.add_chunk(Xc, yc)          # the Gram pass on this chunk overlaps the next copy
                 chunks.append((Xc, yc))
-        slot, info = fac.factor(coll.all_reduce_sum(fac.gram()), reg)
-        bad, cond = (float(v) for v in info.cpu())
+        if small:
+            slot, info = fac.factor(coll.all_reduce_sum(fac.gram()), reg, want_gram=is_train)
+        else:
+            slot, info = fac.factor(coll.all_reduce_sum(fac.gram()), reg)
         train = None
+        if small and is_train and fac.lift_gram is not None:
+            # one read: pivot flag and condition bound of the factor, condition bound of its leading block
+            base = (p + 1) * (p + 1)
+            bad, cond, lift_cond = (float(v) for v in torch.cat([info, fac.lift_gram[base:base + 1]]).cpu())
+            if bad == 0 and cond <= self.SINGLE_PASS_COND:
+                R, c, _ = ops.split_factor(slot, p)
+                train = ops.TrainSide(R, c, gram=fac.lift_gram, cond=lift_cond)
+        else:
+            bad, cond = (float(v) for v in info.cpu())
         if bad == 0 and not small and is_train:
             # wide problems: the blocked factorisation reports no condition bound; the estimate the lift
             # route needs anyway (equilibrated train factor) decides

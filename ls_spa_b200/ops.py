@@ -161,7 +161,9 @@ class CholQR2:
         """Scaled Gram matrix of this process's rows (zeros when it holds none)."""
         return self._sum(self.parts1)
 
-    def factor(self, G: torch.Tensor, reg: float = 0.0):
+    def factor(self, G: torch.Tensor, reg: float = 0.0, want_gram: bool = False):
+        """want_gram: also leave the record of lsspa_lifts_gram (equilibrated Gram matrix, column scales,
+        condition bound of the leading p x p block) in self.lift_gram -- the train side of a job."""
         lib = _lib()
         p, q = self.p, self.p + 1
         dev = G.device
@@ -171,8 +173,11 @@ class CholQR2:
         self.R1 = torch.empty(q * q, dtype=torch.float64, device=dev)
         self.Rinv = torch.empty(int(lib.lsspa_gram_rinv_doubles(p)), dtype=torch.float64, device=dev)
         info = torch.zeros(2, dtype=torch.float64, device=dev)
-        check(lib.lsspa_chol_factor(G.data_ptr(), p, self.R1.data_ptr(), self.Rinv.data_ptr(), info.data_ptr(),
-                                    _stream()), "lsspa_chol_factor")
+        self.lift_gram = None
+        if want_gram and lib.lsspa_lifts_chol_supported(p):
+            self.lift_gram = torch.empty(int(lib.lsspa_lifts_gram_doubles(p)), dtype=torch.float64, device=dev)
+        check(lib.lsspa_chol_factor_gram(G.data_ptr(), p, self.R1.data_ptr(), self.Rinv.data_ptr(), info.data_ptr(),
+                                         _ptr(self.lift_gram), _stream()), "lsspa_chol_factor_gram")
         slot = torch.empty(tsqr_slot(p), dtype=torch.float64, device=dev)
         # one pass: slot = R1 (well conditioned: the second pass would only remove an orthogonality
         # defect of order eps * cond^2 <= 1e-10, and everything downstream depends on the factor
@@ -355,7 +360,9 @@ class TrainSide:
     It needs no test data, so a host-resident job builds it (and pre-factors permutations with it)
     while the test rows are still crossing PCIe."""
 
-    def __init__(self, R_tr, c_tr):
+    def __init__(self, R_tr, c_tr, gram=None, cond=None):
+        """gram / cond: the record lsspa_chol_factor_gram left behind and its condition bound, when the
+        reduction has already produced them (no kernel, no host synchronisation here then)."""
         dev = R_tr.device
         self.p = p = int(R_tr.shape[0])
         # row-major (p,p) -> column-major storage == contiguous transpose
@@ -369,7 +376,12 @@ class TrainSide:
         self.use_chol = False
         forced = os.environ.get("LSSPA_LIFTS_IMPL", "")
         self.big = bool(_lib().lsspa_lifts_big_supported(p))     # wide problems: batched tile kernels (lifts_big.cu)
-        if forced not in ("v1", "householder") and (_lib().lsspa_lifts_chol_supported(p) or self.big):
+        if gram is not None and cond is not None and forced not in ("v1", "householder"):
+            base = (p + 1) * (p + 1)
+            self.gram, self.cond_estimate = gram, float(cond)
+            self.use_chol = forced == "chol" or self.cond_estimate <= CHOL_COND_LIMIT
+            self.scale = gram[base + 8:base + 8 + p]
+        elif forced not in ("v1", "householder") and (_lib().lsspa_lifts_chol_supported(p) or self.big):
             n = _lib().lsspa_lifts_gram_doubles(p)
             self.gram = torch.empty(n, dtype=torch.float64, device=dev)
             check(_lib().lsspa_lifts_gram(p, self.R_tr_cm.data_ptr(), self.c_tr.data_ptr(),
