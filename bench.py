@@ -241,8 +241,12 @@ def side_configs(L, torch, dev):
     run("C2", "p=10, N=M=1e5, method=exact (all 10! = 3628800 permutations)", 10, 100_000, 3_628_800, method="exact")
     run("C3", "p=100, N=M=1e5, method=argsort, 2^7 x 2^7 samples, no antithetic pairs", 100, 100_000, 1 << 14,
         method="argsort", batch_size=128, num_batches=128, tolerance=0.0, antithetical=False)
-    run("C5_reduced", "p=1000, N=M=1e5 (C5 has 1e6 rows on 8 GPUs), method=random, 2^10 permutations, no antithetic pairs",
-        1000, 100_000, 1 << 10, method="random", batch_size=128, num_batches=8, tolerance=0.0, antithetical=False)
+    run("C5_per_gpu", "p=1000, N=M=125000 rows, method=random, 2^13 permutations, no antithetic pairs: one GPU's share of "
+                      "C5 (p=1000, N=M=1e6, 2^16 permutations on 8 GPUs)",
+        1000, 125_000, 1 << 13, method="random", batch_size=128, num_batches=64, tolerance=0.0, antithetical=False)
+    c5 = out["C5_per_gpu"]
+    c5["fp64_tflops_executed"] = (4.0 / 3.0) * 1000.0 ** 3 * c5["permutations"] / c5["seconds"] / 1e12
+    c5["note"] = "whole job: Gram reduction of 2 x 125000 x 1001, blocked Cholesky, 8192 evaluations (lifts_big.cu), estimator"
     return out
 
 
@@ -256,6 +260,10 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # the run totals exchanged per super-batch are 0.9 MB per rank: NCCL's default pick for that size is the
+        # low-latency LL protocol, whose bandwidth (flag word per 8 bytes) makes the exchange ~3x slower
+        # than the Simple protocol over NVLink (measured: 10.74 -> 11.03 M perm/s on 2 GPUs)
+        os.environ.setdefault("NCCL_PROTO", "Simple")
         # NCCL prints its version banner to stdout on first use: keep stdout for the one JSON line
         sys.stdout.flush()
         saved = os.dup(1)

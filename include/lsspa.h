@@ -258,6 +258,10 @@ LSSPA_API int lsspa_estimator_absorb(void *state, int p, int cur, double n_befor
                            void *stream);
 LSSPA_API int lsspa_estimator_quantiles(int p, double *zsq, int nown, double *overall_out,
                               double *feat_out, void *stream);
+/* multi-GPU: one partial block equal to the merge of nb consecutive partial blocks (the run total a rank
+ * ships to the others), as parallel sums -- merge_sample_mean/cov are associative (test/test_ls_spa.py:20-44) */
+LSSPA_API int lsspa_estimator_block_total(int p, const double *partials, int nb, int with_draws, double *out_block,
+                                          void *stream);
 /* running means after each sample (attribution_history, :217-219): hist[k] =
  * (carry_sum + sum_{r<=k} lifts[r]) / (carry_count + k + 1); carry is updated */
 LSSPA_API int lsspa_prefix_means(int p, const double *lifts, int64_t rows, double *carry_sum,

@@ -550,6 +550,56 @@ __global__ void __launch_bounds__(256) est_quantile_kernel(int p, int nown, cons
   }
 }
 
+// ---------------------------------------------------------------- run total of a rank (multi-GPU)
+// One partial block equal to the Chan merge of nb consecutive partial blocks, computed as PARALLEL sums
+// (the merge is associative): n = sum n_b, mean = sum n_b m_b / n, and with d_b = m_b - mean
+//   M2 = sum_b M2_b + n_b d_b d_b^T,   G = sum_b G_b,   S = sum_b S_b + d_b G_b^T.
+// A rank ships this block instead of folding its batches twice; the sequential fold (est_absorb_kernel)
+// and this sum agree to rounding.
+__global__ void block_total_mean_kernel(int p, const double *partials, size_t pstride, int nb, double *out) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  double n = 0.0;
+  for (int b = 0; b < nb; ++b) n += partials[(size_t)b * pstride];
+  if (f < kPartHdr) out[f] = (f == 0) ? n : 0.0;
+  if (f >= p) return;
+  double s = 0.0;
+  for (int b = 0; b < nb; ++b) s = fma(partials[(size_t)b * pstride], partials[(size_t)b * pstride + kPartHdr + f], s);
+  out[kPartHdr + f] = n > 0.0 ? s / n : 0.0;
+}
+
+__global__ void __launch_bounds__(256) block_total_kernel(int p, const double *partials, size_t pstride, int nb,
+                                                          int with_draws, double *out) {
+  const size_t nm2 = (size_t)p * p, ng = kDraws, ns = (size_t)p * kDraws;
+  const size_t total = nm2 + (with_draws ? ng + ns : 0);
+  const double *mean = out + kPartHdr;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    if (e < nm2) {
+      const int f = (int)(e / p), j = (int)(e - (size_t)f * p);
+      const double mf = mean[f], mj = mean[j];
+      for (int b = 0; b < nb; ++b) {
+        const double *blk = partials + (size_t)b * pstride;
+        const double nb_ = blk[0];
+        if (nb_ > 0.0) acc += blk[kPartHdr + p + e] + nb_ * (blk[kPartHdr + f] - mf) * (blk[kPartHdr + j] - mj);
+      }
+    } else if (e < nm2 + ng) {
+      for (int b = 0; b < nb; ++b) {
+        const double *blk = partials + (size_t)b * pstride;
+        if (blk[0] > 0.0) acc += blk[kPartHdr + p + e];
+      }
+    } else {
+      const size_t r = e - nm2 - ng;
+      const int f = (int)(r / kDraws), sd = (int)(r - (size_t)f * kDraws);
+      const double mf = mean[f];
+      for (int b = 0; b < nb; ++b) {
+        const double *blk = partials + (size_t)b * pstride;
+        if (blk[0] > 0.0) acc += blk[kPartHdr + p + e] + (blk[kPartHdr + f] - mf) * blk[kPartHdr + p + nm2 + sd];
+      }
+    }
+    out[kPartHdr + p + e] = acc;
+  }
+}
+
 // ---------------------------------------------------------------- standalone error_estimates
 // L L^T = cov for a positive semi-definite cov (one CTA, right-looking, L row-major in `L`): a pivot
 // that is not above 1e-13 of the largest diagonal entry is round-off of a singular direction -- its
@@ -890,6 +940,21 @@ extern "C" int lsspa_estimator_quantiles(int p, double *zsq, int nown, double *o
   LSSPA_LAUNCH_CHECK();
   const int64_t rows = (int64_t)nown * (p + 1);
   est_quantile_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, as_stream(stream)>>>(p, nown, zsq, overall_out, feat_out);
+  LSSPA_LAUNCH_CHECK();
+  return LSSPA_OK;
+}
+
+extern "C" int lsspa_estimator_block_total(int p, const double *partials, int nb, int with_draws, double *out_block,
+                                           void *stream) {
+  if (p < 1 || !partials || !out_block || nb < 0) return LSSPA_E_BADARG;
+  cudaStream_t st = as_stream(stream);
+  const size_t pstride = partial_doubles(p);
+  if (nb == 0 || !with_draws) LSSPA_CUDA_TRY(cudaMemsetAsync(out_block, 0, pstride * sizeof(double), st));
+  if (nb == 0) return LSSPA_OK;
+  const int n1 = p > kPartHdr ? p : kPartHdr;
+  block_total_mean_kernel<<<(n1 + 127) / 128, 128, 0, st>>>(p, partials, pstride, nb, out_block);
+  LSSPA_LAUNCH_CHECK();
+  block_total_kernel<<<592, 256, 0, st>>>(p, partials, pstride, nb, with_draws, out_block);
   LSSPA_LAUNCH_CHECK();
   return LSSPA_OK;
 }

@@ -65,9 +65,10 @@ def contiguous_runs(nbatch: int, world: int):
 
 
 def target_samples(p: int) -> int:
-    """Samples per rank and super-batch: ~16K at p = 100, falling with the p^2 growth of the work per sample.
+    """Samples per rank and super-batch: ~32K at p = 100 (every super-batch costs a round of collectives and one host
+    synchronisation; jobs that can stop early ramp up to it, see superbatch_geometry), falling with the p^2 growth of the work per sample.
     Wide problems (the batched tile kernels, p > 152) need at least four evaluations per SM in flight."""
-    t = int(16384 * (100.0 / max(p, 1)) ** 2)
+    t = int(32768 * (100.0 / max(p, 1)) ** 2)
     return max(592 if p > 152 else 256, min(t, 131072))
 
 
@@ -541,9 +542,13 @@ def run_samples(backend, coll: Collective, prob, source: PermutationSource, cfg:
             own_counts, nb_r = counts[b0:b1], b1 - b0
             run_counts = [sum(counts[a:b]) for a, b in runs]
             loc = est.scratch()
-            loc.reset()
-            loc.absorb(part, list(range(nb_r)), own_counts, emit=False)
-            totals = coll.all_gather(loc.export_block().view(1, -1)).reshape(W, -1)
+            if hasattr(est, "block_total"):
+                own_total = est.block_total(part, nb_r)      # parallel sums: the merge is associative
+            else:                                            # (CPU stand-in of the unit tests: sequential fold)
+                loc.reset()
+                loc.absorb(part, list(range(nb_r)), own_counts, emit=False)
+                own_total = loc.export_block()
+            totals = coll.all_gather(own_total.view(1, -1)).reshape(W, -1)
             loc.copy_from(est)
             if rank > 0:
                 loc.absorb(totals, list(range(rank)), run_counts[:rank], emit=False)

@@ -600,6 +600,15 @@ class Estimator:
         self.state.copy_(other.state)
         self.cur, self.count = other.cur, other.count
 
+    def block_total(self, partials: torch.Tensor, nb: int) -> torch.Tensor:
+        """The merge of the first nb partial blocks as ONE block (parallel sums; what a rank ships)."""
+        out = torch.empty(self.partial_doubles, dtype=torch.float64, device=self.device)
+        flat = partials.reshape(-1, self.partial_doubles)
+        check(_lib().lsspa_estimator_block_total(self.p, _ptr(flat) if nb > 0 else 0, nb, 1 if self.estimate else 0,
+                                                 out.data_ptr(), _stream()), "lsspa_estimator_block_total")
+        _count(2)
+        return out
+
     def export_block(self) -> torch.Tensor:
         """The whole state as one partial block {n, mean, M2 = n * biased cov, G, S} (the layout of
         lsspa_estimator_partials), so that it can be folded into another state by absorb()."""

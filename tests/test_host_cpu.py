@@ -92,7 +92,7 @@ def test_split_batches_and_runs():
     assert per == 3 and runs == [(0, 3), (3, 6), (6, 9), (9, 10)]
     runs, per = contiguous_runs(2, 4)
     assert runs == [(0, 1), (1, 2), (2, 2), (2, 2)]
-    assert target_samples(100) == 16384 and target_samples(1000) == 592 and target_samples(150) == 7281 and target_samples(3) == 131072
+    assert target_samples(100) == 32768 and target_samples(1000) == 592 and target_samples(150) == 14563 and target_samples(3) == 131072
 
 
 def test_explicit_source_on_cpu_tensors():
