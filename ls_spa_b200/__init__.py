@@ -8,6 +8,7 @@ into it does.
 """
 
 from ._cabi import LsSpaCudaError
+from . import torch_ops  # noqa: F401  (registers torch.ops.ls_spa_b200.*)
 from .api import (ShapleyResults, SizeIncompatible, error_estimates, ls_spa, merge_sample_cov,
                   merge_sample_mean, reduce_data, square_shapley, validate_data)
 

@@ -601,3 +601,25 @@ def test_split_route_host_inputs(T, L, monkeypatch):
         calls["n"] = 0
         c = L.ls_spa(*dev, **kw)
         assert calls["n"] == 0 and scaled_err(c.attribution, b.attribution) < 1e-12
+
+
+def test_torch_custom_ops_match_direct_calls(T):
+    """torch.ops.ls_spa_b200.* (torch.library wrappers of the C ABI) against the golden lifts and the
+    engine's direct calls."""
+    from ls_spa_b200 import ops, samplers
+    g = load_golden("syn_p100")
+    prob = device_problem(T, g)
+    perms = T.from_numpy(g["perms_random"].astype(np.int32)).cuda()
+    a = T.ops.ls_spa_b200.lifts_chol(prob.gram, prob.R_te_scaled_cm, prob.c_te, prob.y_norm_sq, perms, False)
+    b = T.ops.ls_spa_b200.lifts(prob.R_tr_cm, prob.c_tr, prob.R_te_cm, prob.c_te, prob.y_norm_sq, perms, False)
+    assert scaled_err(a.cpu().numpy(), g["lifts_random"]) < TOL and scaled_err(b.cpu().numpy(), g["lifts_random"]) < TOL
+    tr = T.ops.ls_spa_b200.theta_r2(prob.R_tr_cm, prob.c_tr, prob.R_te_cm, prob.c_te, prob.y_norm_sq).cpu().numpy()
+    assert scaled_err(tr[:100], g["random_anti0_theta"]) < TOL and abs(tr[100] - float(g["random_anti0_r_squared"])) < TOL
+    src = samplers.PermutohedronSource(100, 42, None, T.device("cuda"))
+    got = T.ops.ls_spa_b200.perms_permutohedron(src.sv, src.shift, src.bits, 100, 0, 64).cpu().numpy()
+    assert np.array_equal(got, load_golden("streams")["permutohedron_p100_seed42"][:64])
+    Xtr, _, ytr, _ = regen(g)
+    X, y = T.from_numpy(Xtr).cuda(), T.from_numpy(ytr).cuda()
+    G = T.ops.ls_spa_b200.gram_reduce(X, y, 2.0).cpu().numpy().reshape(104, 104)
+    Z = np.column_stack([Xtr, ytr]) / 2.0
+    assert scaled_err(np.triu(G[:101, :101]), np.triu(Z.T @ Z)) < 1e-13

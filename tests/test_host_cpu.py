@@ -149,3 +149,17 @@ def test_superbatch_memory_cap():
                       estimate_errors=True, return_history=False)
     _, _, s10 = superbatch_geometry(cfg10, 1, None)
     assert s10(0) == min(target_samples(10), batch_cap(10, True))
+
+
+def test_torch_custom_ops_registered():
+    import pytest
+    import torch
+    """The tensor-level entry points exist as PyTorch custom ops (torch.library) with CUDA-only kernels."""
+    import ls_spa_b200  # noqa: F401
+    from ls_spa_b200 import torch_ops
+    for name in torch_ops.OPS:
+        op = getattr(torch.ops.ls_spa_b200, name)
+        assert op is not None and "ls_spa_b200::" + name in str(op.default._schema)
+    with pytest.raises((NotImplementedError, RuntimeError)):      # no CPU kernel: there is no CPU fallback
+        torch.ops.ls_spa_b200.theta_r2(torch.eye(3, dtype=torch.float64), torch.ones(3, dtype=torch.float64),
+                                       torch.eye(3, dtype=torch.float64), torch.ones(3, dtype=torch.float64), 1.0)
