@@ -898,6 +898,8 @@ int run_chol4(const CholParams &a, int64_t count, cudaStream_t st) {
   const size_t smem = chol4_smem_bytes<RT>(a.p, a.pt);
   int per_sm = (int)((size_t)(228 * 1024) / (smem + 1024));
   if (per_sm > 4) per_sm = 4;
+  static const int cap = [] { const char *e = getenv("LSSPA_C4_PER_SM"); return e ? atoi(e) : 4; }();   // experiments
+  if (per_sm > cap) per_sm = cap;
   if (per_sm < 1) per_sm = 1;
   int64_t grid = (int64_t)per_sm * sms;
   if (grid > count) grid = count;

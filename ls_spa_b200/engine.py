@@ -223,17 +223,20 @@ class CudaBackend:
             g = torch.cat([g, self.ridge(p, reg).unsqueeze(0)], 0)
         return self.merge_factors(g, p) if g.shape[0] > 1 else g[0]
 
-    def reduce_side(self, coll, X, y, lo, hi, p, divisor, reg, staging=None, fence=None, is_train=False):
-        """One side of reduce_data over all ranks: rows [lo, hi) of this rank -> (merged slot, TrainSide or None).
+    def reduce_start(self, coll, X, y, lo, hi, p, divisor, reg, staging=None, fence=None, is_train=False):
+        """Launch half of one side of reduce_data: Gram pass over the rows [lo, hi) of this rank, all-reduce,
+        factorisation.  Nothing is read back: the returned state goes to reduce_finish, and a caller may
+        start the other side first so that one host synchronisation serves both.
 
         Gram route (default): every rank accumulates the Gram matrix of its rows with fp64 tensor tiles,
         the ranks ALL-REDUCE it (82 KB at p = 100, 8 MB at p = 1000), the ridge term is added to its
         diagonal and every rank factors the same matrix -- so the condition / pivot flags, and with them
-        the decision to fall back, are identical everywhere.  One pass is kept when the factor is well
-        conditioned; otherwise a second CholeskyQR pass (p + 1 <= 120, no ridge) or the Householder TSQR."""
+        the decision to fall back, are identical everywhere."""
         small = ops.gram_supported(p)
+        st = dict(coll=coll, X=X, y=y, lo=lo, hi=hi, p=p, divisor=divisor, reg=reg, is_train=is_train, small=small,
+                  fac=None, flags=None)
         if not (self.use_cholqr2 and (small or ops.gram_big_supported(p))):
-            return self._tsqr_side(coll, None, X, y, lo, hi, p, divisor, reg), None
+            return st
         fac = ops.CholQR2(p, divisor, self.device) if small else ops.GramBig(p, divisor, self.device)
         chunks = []
         if hi - lo > 0:
@@ -244,16 +247,29 @@ class CudaBackend:
             slot, info = fac.factor(coll.all_reduce_sum(fac.gram()), reg, want_gram=is_train)
         else:
             slot, info = fac.factor(coll.all_reduce_sum(fac.gram()), reg)
-        train = None
-        if small and is_train and fac.lift_gram is not None:
-            # one read: pivot flag and condition bound of the factor, condition bound of its leading block
-            base = (p + 1) * (p + 1)
-            bad, cond, lift_cond = (float(v) for v in torch.cat([info, fac.lift_gram[base:base + 1]]).cpu())
-            if bad == 0 and cond <= self.SINGLE_PASS_COND:
-                R, c, _ = ops.split_factor(slot, p)
-                train = ops.TrainSide(R, c, gram=fac.lift_gram, cond=lift_cond)
-        else:
-            bad, cond = (float(v) for v in info.cpu())
+        q = p + 1
+        # what the host needs from this side, as one small device tensor: [bad pivot, cond bound of the factor,
+        # cond bound of its leading block (train side, p + 1 <= 120), sum of squares of the y column]
+        lift_cond = (fac.lift_gram[q * q:q * q + 1] if (small and is_train and fac.lift_gram is not None)
+                     else torch.full((1,), float("nan"), dtype=torch.float64, device=self.device))
+        st.update(fac=fac, chunks=chunks, slot=slot, flags=torch.cat([info, lift_cond, slot[q * q:q * q + 1]]))
+        return st
+
+    def reduce_finish(self, st, flags=None):
+        """Decide half: -> (merged slot, TrainSide or None, sum of squares of y or None).  flags: the host copy
+        of st['flags'] when the caller has already fetched it (together with the other side's).  One pass is kept
+        when the factor is well conditioned; otherwise a second CholeskyQR pass (p + 1 <= 120, no ridge) or
+        the Householder TSQR."""
+        coll, p, reg, small, is_train, fac = st["coll"], st["p"], st["reg"], st["small"], st["is_train"], st["fac"]
+        if fac is None:
+            return self._tsqr_side(coll, None, st["X"], st["y"], st["lo"], st["hi"], p, st["divisor"], reg), None, None
+        if flags is None:
+            flags = st["flags"].cpu()
+        bad, cond, lift_cond, ysq = (float(v) for v in flags)
+        slot, train = st["slot"], None
+        if bad == 0 and small and is_train and fac.lift_gram is not None and cond <= self.SINGLE_PASS_COND:
+            R, c, _ = ops.split_factor(slot, p)
+            train = ops.TrainSide(R, c, gram=fac.lift_gram, cond=lift_cond)
         if bad == 0 and not small and is_train:
             # wide problems: the blocked factorisation reports no condition bound; the estimate the lift
             # route needs anyway (equilibrated train factor) decides
@@ -263,13 +279,18 @@ class CudaBackend:
         elif bad == 0 and not small:
             cond = 0.0     # test side: everything downstream depends on R_te through R_te^T R_te, which Cholesky reproduces
         if bad == 0 and cond <= self.SINGLE_PASS_COND:
-            return slot, train
+            return slot, train, ysq
         if small and bad == 0 and reg == 0.0 and cond <= self.CHOLQR2_MAX_COND:
             slot, info2 = fac.finish_second(coll.all_reduce_sum(fac.second_gram()))
             bad2, cond2 = (float(v) for v in info2.cpu())
             if bad2 == 0 and cond2 <= 10.0 * (p + 1):
-                return slot, None
-        return self._tsqr_side(coll, chunks, X, y, lo, hi, p, divisor, reg), None
+                return slot, None, None
+        return self._tsqr_side(coll, st["chunks"], st["X"], st["y"], st["lo"], st["hi"], p, st["divisor"], reg), None, None
+
+    def reduce_side(self, coll, X, y, lo, hi, p, divisor, reg, staging=None, fence=None, is_train=False):
+        """One side of reduce_data over all ranks, start to finish -> (merged slot, TrainSide or None, ysq or None)."""
+        return self.reduce_finish(self.reduce_start(coll, X, y, lo, hi, p, divisor, reg, staging=staging, fence=fence,
+                                                    is_train=is_train))
 
     # factor condition (equilibrated) up to which one Cholesky pass is kept
     SINGLE_PASS_COND = 1e3
@@ -280,10 +301,12 @@ class CudaBackend:
     def ridge(self, p, reg):
         return ops.ridge_factor(p, reg, self.device)
 
-    def make_problem(self, train_slot, test_slot, p, train=None):
+    def make_problem(self, train_slot, test_slot, p, train=None, ysq=None):
         R_tr, c_tr, _ = ops.split_factor(train_slot, p)
-        R_te, c_te, ysq = ops.split_factor(test_slot, p)
-        return ops.ReducedProblem(R_tr, c_tr, R_te, c_te, float(ysq.item()), train=train)
+        R_te, c_te, ysq_dev = ops.split_factor(test_slot, p)
+        if ysq is None:
+            ysq = float(ysq_dev.item())
+        return ops.ReducedProblem(R_tr, c_tr, R_te, c_te, ysq, train=train)
 
     # -- sample loop --------------------------------------------------------
     def lifts(self, prob, perms, antithetical):
@@ -340,33 +363,41 @@ def reduce_problem(backend, coll: Collective, X_train, X_test, y_train, y_test, 
     if n_train_global is None:
         n_train_global = (coll.all_reduce_sum_int(n_tr_local, backend.device)
                           if row_sharded else n_tr_local)
-    fused = hasattr(backend, "reduce_side")     # the CUDA backend; the CPU stand-in of the unit tests merges triangles
-
-    def one_side(X, y, lo, hi, divisor, ridge, is_train, **kw):
-        if fused:
-            return backend.reduce_side(coll, X, y, lo, hi, p, divisor, ridge, is_train=is_train, **kw)
-        g = coll.all_gather(backend.reduce_rows(X, y, lo, hi, p, divisor))
-        if ridge != 0.0:
-            g = torch.cat([g, backend.ridge(p, ridge).unsqueeze(0)], 0)    # :310
-        return (backend.merge_factors(g, p) if g.shape[0] > 1 else g[0]), None
-
-    lo, hi = local_range(n_tr_local)
-    # train side: rows scaled by 1/sqrt(N) (reference ls_spa/ls_spa.py:309,311), ridge rows sqrt(reg) I (:310)
-    train_slot, train = one_side(X_train, y_train, lo, hi, math.sqrt(n_train_global), reg, True)
-    lo, hi = local_range(int(X_test.shape[0]))
+    fused = hasattr(backend, "reduce_start")     # the CUDA backend; the CPU stand-in of the unit tests merges triangles
+    lo_tr, hi_tr = local_range(n_tr_local)
+    lo_te, hi_te = local_range(int(X_test.shape[0]))
+    root_n = math.sqrt(n_train_global)
+    if not fused:
+        def one_side(X, y, lo, hi, divisor, ridge):
+            g = coll.all_gather(backend.reduce_rows(X, y, lo, hi, p, divisor))
+            if ridge != 0.0:
+                g = torch.cat([g, backend.ridge(p, ridge).unsqueeze(0)], 0)    # :310
+            return backend.merge_factors(g, p) if g.shape[0] > 1 else g[0]
+        # train side: rows scaled by 1/sqrt(N) (reference ls_spa/ls_spa.py:309,311), ridge rows sqrt(reg) I (:310);
+        # test side unscaled, no ridge (:315)
+        return backend.make_problem(one_side(X_train, y_train, lo_tr, hi_tr, root_n, reg),
+                                    one_side(X_test, y_test, lo_te, hi_te, 1.0, 0.0), p)
     if prefactor is not None:
         # single process, host-resident test rows: the train factor is complete, so permutations
         # can already be drawn and factored while the test rows cross PCIe.  The staging arrays of
         # the test rows are allocated first: the copies then only wait for what was enqueued before
         # the factorisations, and no block freed during them can end up under a copy.
-        staging, fence = backend.alloc_staging(hi - lo, p)
+        train_slot, train, _ = backend.reduce_side(coll, X_train, y_train, lo_tr, hi_tr, p, root_n, reg, is_train=True)
+        staging, fence = backend.alloc_staging(hi_te - lo_te, p)
         train = prefactor.run(train_slot, p, train)
-        test_slot, _ = one_side(X_test, y_test, lo, hi, 1.0, 0.0, False, staging=staging, fence=fence)
+        test_slot, _, ysq = backend.reduce_side(coll, X_test, y_test, lo_te, hi_te, p, 1.0, 0.0, staging=staging, fence=fence)
     else:
-        test_slot, _ = one_side(X_test, y_test, lo, hi, 1.0, 0.0, False)       # :315 unscaled, no ridge
-    if train is not None:
-        return backend.make_problem(train_slot, test_slot, p, train=train)
-    return backend.make_problem(train_slot, test_slot, p)
+        # both sides are enqueued before anything is read back: one host synchronisation for the whole reduction
+        st_tr = backend.reduce_start(coll, X_train, y_train, lo_tr, hi_tr, p, root_n, reg, is_train=True)
+        st_te = backend.reduce_start(coll, X_test, y_test, lo_te, hi_te, p, 1.0, 0.0)
+        if st_tr["flags"] is not None and st_te["flags"] is not None:
+            both = torch.cat([st_tr["flags"], st_te["flags"]]).cpu()
+            f_tr, f_te = both[:4], both[4:]
+        else:
+            f_tr = f_te = None
+        train_slot, train, _ = backend.reduce_finish(st_tr, f_tr)
+        test_slot, _, ysq = backend.reduce_finish(st_te, f_te)
+    return backend.make_problem(train_slot, test_slot, p, train=train, ysq=ysq)
 
 
 class Prefactor:
