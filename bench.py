@@ -241,13 +241,40 @@ def side_configs(L, torch, dev):
     run("C2", "p=10, N=M=1e5, method=exact (all 10! = 3628800 permutations)", 10, 100_000, 3_628_800, method="exact")
     run("C3", "p=100, N=M=1e5, method=argsort, 2^7 x 2^7 samples, no antithetic pairs", 100, 100_000, 1 << 14,
         method="argsort", batch_size=128, num_batches=128, tolerance=0.0, antithetical=False)
-    run("C5_per_gpu", "p=1000, N=M=125000 rows, method=random, 2^13 permutations, no antithetic pairs: one GPU's share of "
-                      "C5 (p=1000, N=M=1e6, 2^16 permutations on 8 GPUs)",
-        1000, 125_000, 1 << 13, method="random", batch_size=128, num_batches=64, tolerance=0.0, antithetical=False)
-    c5 = out["C5_per_gpu"]
-    c5["fp64_tflops_executed"] = (4.0 / 3.0) * 1000.0 ** 3 * c5["permutations"] / c5["seconds"] / 1e12
-    c5["note"] = "whole job: Gram reduction of 2 x 125000 x 1001, blocked Cholesky, 8192 evaluations (lifts_big.cu), estimator"
     return out
+
+
+def c5_line(L, torch, dist, dev, world, rank):
+    """BASELINE config 5 itself: p=1000, N=M=10^6 rows sharded over the ranks, method='random', 2^16 permutations
+    (no antithetic pairs) sharded over the ranks; at world 1 the same job with 1/8 of the rows and permutations
+    (one GPU's share).  Wall clock around ls_spa() after one warm-up call, max over ranks."""
+    p, share = 1000, (1 if world > 1 else 8)
+    rows = 1_000_000 // (world * share)
+    nperm = (1 << 16) // share
+    Xtr, Xte, ytr, yte = synth_on_device(torch, dev, p, rows, rows, 2000 + rank, dist if world > 1 else None, rows * world)
+    kw = dict(method="random", batch_size=128, num_batches=nperm // 128, tolerance=0.0, antithetical=False,
+              row_sharded=world > 1)
+    L.ls_spa(Xtr, Xte, ytr, yte, **kw)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    r = L.ls_spa(Xtr, Xte, ytr, yte, **kw)
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    dt = float(dt.item())
+    del Xtr, Xte, ytr, yte
+    torch.cuda.empty_cache()
+    peak, _ = fp64_peak_tflops() if rank == 0 else (None, None)
+    tf = (4.0 / 3.0) * p ** 3 * nperm / dt / 1e12
+    return {"workload": f"p=1000, N=M={rows * world} rows ({rows} per GPU), method=random, {nperm} permutations, no antithetic pairs"
+                        + ("" if world > 1 else " (one GPU's share of C5: 1/8 of the rows and permutations)"),
+            "seconds": dt, "permutations": nperm, "permutations_per_s": nperm / dt,
+            "fp64_tflops_executed": tf, "fp64_frac_executed_per_gpu": (tf / world / peak) if peak else None,
+            "sum_attribution_minus_r2": float(abs(r.attribution.sum() - r.r_squared)), "overall_error": float(r.overall_error),
+            "note": "whole job: Gram reduction (gram_big.cu), blocked Cholesky, wide lift kernels (lifts_big.cu), estimator"}
 
 
 def run_gpu(args):
@@ -389,6 +416,13 @@ def run_gpu(args):
                     "scaling": "strong (fixed tolerance, rows and samples sharded over the ranks)",
                     "timer": "wall clock around ls_spa() with device-resident inputs, max over ranks"})
 
+    c5 = None
+    if not args.no_cpu:
+        try:
+            c5 = c5_line(L, torch, dist if world > 1 else None, dev, world, rank)
+        except Exception as exc:      # a side line must never cost the headline
+            c5 = {"error": repr(exc)}
+
     if rank == 0:
         peaks = read_peaks()
         fp64_peak, fp64_src = fp64_peak_tflops()
@@ -445,11 +479,13 @@ def run_gpu(args):
                              "overall_error": float(last["res"].overall_error),
                              "multi_gpu_parity": parity},
         }
+        if c5 is not None:
+            out["configs"] = {"C5" if world > 1 else "C5_per_gpu": c5}
         if world == 1 and not args.no_cpu:
             try:
-                out["configs"] = side_configs(L, torch, dev)
+                out["configs"].update(side_configs(L, torch, dev))
             except Exception as exc:      # a side line must never cost the headline
-                out["configs"] = {"error": repr(exc)}
+                out["configs"]["error"] = repr(exc)
             out["cpu_baseline"] = cpu_baseline(sample_perms_per_core=1024, full=True)
             cb = out["cpu_baseline"]
             for t in ttt:

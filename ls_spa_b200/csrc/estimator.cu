@@ -392,7 +392,12 @@ __global__ void __launch_bounds__(1024) est_absorb_kernel(double *state, int p, 
   double *mrun = smem;                           // (nb+1) x p running means
   double *nrun = mrun + (size_t)(nb + 1) * p;    // nb+1 running counts
   double *n2s = nrun + (nb + 1);                 // nb batch counts
-  int *slots = reinterpret_cast<int *>(n2s + nb + (nb & 1));  // nb block indices
+  double *fa = n2s + nb;                         // per-batch merge weights (no divisions in the serial loops):
+  double *fb = fa + nb;                          //   fa = n1/nn, fb = n2/nn, fc = 1/nn, fd = fa*fb,
+  double *fc = fb + nb;                          //   fz = 1/sqrt(nn (nn-1))
+  double *fd = fc + nb;
+  double *fz = fd + nb;
+  int *slots = reinterpret_cast<int *>(fz + nb + (nb & 1));  // nb block indices
   StateView st = view_state(state, p);
   const int nxt = cur ^ 1;
   const int tid = threadIdx.x;
@@ -416,13 +421,21 @@ __global__ void __launch_bounds__(1024) est_absorb_kernel(double *state, int p, 
     }
   }
   __syncthreads();
+  for (int b = tid; b < nb; b += blockDim.x) {
+    const double n1 = nrun[b], n2 = n2s[b], nn = nrun[b + 1];
+    fa[b] = n1 / nn;
+    fb[b] = n2 / nn;
+    fc[b] = 1.0 / nn;
+    fd[b] = (n1 / nn) * (n2 / nn);
+    fz[b] = 1.0 / sqrt(nn * (nn - 1.0));
+  }
+  __syncthreads();
   for (int j = tid; j < p; j += blockDim.x) {
     double m = mrun[j];
 #pragma unroll 8
     for (int b = 0; b < nb; ++b) {
       const double pm = partials[(size_t)slots[b] * pstride + kPartHdr + j];
-      const double n1 = nrun[b], n2 = n2s[b], nn = nrun[b + 1];
-      if (n2 > 0.0) m = (n1 / nn) * m + (n2 / nn) * pm;
+      if (n2s[b] > 0.0) m = fa[b] * m + fb[b] * pm;
       mrun[(size_t)(b + 1) * p + j] = m;
     }
   }
@@ -434,11 +447,10 @@ __global__ void __launch_bounds__(1024) est_absorb_kernel(double *state, int p, 
     for (int b = 0; b < nb; ++b) {
       const double *blk = partials + (size_t)slots[b] * pstride + kPartHdr;
       const double pmf = blk[f], pmj = blk[j], pm2 = blk[p + (size_t)f * p + j];
-      const double n1 = nrun[b], n2 = n2s[b], nn = nrun[b + 1];
-      if (n2 > 0.0) {
+      if (n2s[b] > 0.0) {
         const double df = mrun[(size_t)b * p + f] - pmf;
         const double dj = mrun[(size_t)b * p + j] - pmj;
-        c = (n1 / nn) * c + pm2 / nn + (n1 / nn) * (n2 / nn) * df * dj;
+        c = fa[b] * c + pm2 * fc[b] + fd[b] * df * dj;
       }
     }
     st.cov[(size_t)f * p + j] = c;
@@ -460,8 +472,7 @@ __global__ void __launch_bounds__(1024) est_absorb_kernel(double *state, int p, 
         gr += g2;
       }
       if (zsq != nullptr && b >= own0 && b < own1) {
-        const double nn = nrun[b + 1];
-        const double z = s / sqrt(nn * (nn - 1.0));
+        const double z = s * fz[b];       // n = 1: 0 * inf = NaN, as the reference's 0 / 0
         zsq[((size_t)(b - own0) * (p + 1) + f) * kDraws + tid] = z * z;
       }
     }
@@ -909,10 +920,10 @@ extern "C" int lsspa_estimator_partials(int p, const double *lifts, const int64_
 
 extern "C" int lsspa_estimator_max_batches(int p) {
   // running means, counts and block indices of all batches of one absorb call live in shared
-  // memory: (nb + 1) * (p + 1) + 2 nb + 16 doubles
+  // memory: (nb + 1) * (p + 1) + 7 nb + 16 doubles
   const DeviceInfo &d = device_info();
   const size_t limit = (size_t)(d.smem_optin > 0 ? d.smem_optin : 227 * 1024) - 1024;
-  long nb = (long)(limit / ((size_t)(p + 3) * sizeof(double))) - 3;
+  long nb = (long)(limit / ((size_t)(p + 8) * sizeof(double))) - 3;
   if (nb > 4096) nb = 4096;
   return nb < 1 ? 0 : (int)nb;
 }
@@ -923,7 +934,7 @@ extern "C" int lsspa_estimator_absorb(void *state, int p, int cur, double n_befo
   if (!state || !partials || !slot_map || p < 1 || nb < 0 || (cur != 0 && cur != 1)) return LSSPA_E_BADARG;
   if (nb == 0) return LSSPA_OK;
   if (nb > lsspa_estimator_max_batches(p)) return LSSPA_E_UNSUPPORTED;
-  const size_t smem = ((size_t)(nb + 1) * p + (nb + 1) + 2 * (size_t)nb + 16) * sizeof(double);
+  const size_t smem = ((size_t)(nb + 1) * p + (nb + 1) + 7 * (size_t)nb + 16) * sizeof(double);
   LSSPA_CUDA_TRY(cudaFuncSetAttribute(est_absorb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   est_absorb_kernel<<<p, kDraws, smem, as_stream(stream)>>>(reinterpret_cast<double *>(state), p, cur, n_before,
                                                             partials, partial_doubles(p), slot_map, nb, own0,

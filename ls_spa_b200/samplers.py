@@ -118,8 +118,50 @@ class RandomSource(PermutationSource):
         rng.bit_generator.state = st
 
 
+_SOBOL_CONST = {}
+
+
+def sobol_tables(d: int, seed, spawn: bool = False, bits: int = 30):
+    """scipy's scrambled Sobol' direction numbers and digital shift (uint32 (d, bits), (d,)) for an
+    integer seed, built the way ``scipy.stats.qmc.Sobol(d, seed=seed)._scramble`` builds them
+    (scipy/stats/_qmc.py:1812-1828 + ``_cscramble``: the same ``default_rng(seed)`` draws, unit-diagonal
+    lower-triangular bit matrices, parity of row & direction number) but vectorised: ~1 ms at d = 100
+    where constructing the scipy engine takes ~8 ms -- which used to leave the GPU idle between the
+    reduction and the first lifts.  spawn=True: the stream ``MultivariateNormalQMC`` hands its engine
+    (it passes a Generator, which QMCEngine spawns from, _qmc.py ``_initialize``).  Checked against
+    the scipy engines by tests/test_sampler_models.py."""
+    from scipy.stats import _sobol
+    rng = np.random.default_rng(seed)
+    if spawn:
+        rng = rng.spawn(1)[0]
+    sv = np.zeros((d, bits), dtype=np.uint64)
+    _sobol._initialize_v(sv, dim=d, bits=bits)
+    c = _SOBOL_CONST.get(bits)
+    if c is None:
+        w = np.uint64(1) << np.arange(bits, dtype=np.uint64)
+        wr = np.ascontiguousarray(w[::-1])
+        c = _SOBOL_CONST[bits] = (w, wr, np.tril(np.ones((bits, bits), dtype=np.uint64), -1),
+                                  np.eye(bits, dtype=np.uint64), wr.astype(np.uint32))
+    w, wr, tri, eye, wr32 = c
+    shift = rng.integers(2, size=(d, bits), dtype=np.uint64) @ w
+    ltm = rng.integers(2, size=(d, bits, bits), dtype=np.uint64)
+    ltm *= tri
+    ltm += eye                                           # _cscramble sets the diagonals to 1
+    rows = (ltm @ wr).astype(np.uint32)                  # row p as an integer, entry k weighs 2^(bits-1-k)
+    x = rows[:, :, None] & sv.astype(np.uint32)[:, None, :]
+    par = (np.bitwise_count(x) & 1).astype(np.uint32)
+    return (par * wr32[None, :, None]).sum(axis=1, dtype=np.uint32), shift.astype(np.uint32)
+
+
 class _SobolBacked(PermutationSource):
     random_access = True
+
+    def _upload_tables(self, d, seed, spawn, device):
+        """Fast path for integer seeds and the 30-bit engines the reference's drivers use."""
+        sv, shift = sobol_tables(d, int(seed), spawn=spawn, bits=30)
+        self.bits = 30
+        self.sv = torch.from_numpy(sv.view(np.int32)).to(device)
+        self.shift = torch.from_numpy(shift.view(np.int32)).to(device)
 
     def _upload(self, engine, device):
         if engine.bits > 32:
@@ -133,9 +175,12 @@ class ArgsortSource(_SobolBacked):
     method = "argsort"
 
     def __init__(self, p, seed, total, device):
-        from scipy.stats.qmc import Sobol
         super().__init__(p, total if total is not None else 2 ** 30)
-        self._upload(Sobol(p, seed=seed), device)
+        if isinstance(seed, (int, np.integer)) and hasattr(np, "bitwise_count"):
+            self._upload_tables(p, seed, False, device)
+        else:
+            from scipy.stats.qmc import Sobol
+            self._upload(Sobol(p, seed=seed), device)
         self.total = min(self.total, 2 ** self.bits)
 
     def take(self, count):
@@ -153,10 +198,13 @@ class PermutohedronSource(_SobolBacked):
         if p < 2:
             raise LsSpaCudaError("permutohedron sampling needs p >= 2")
         super().__init__(p, total if total is not None else 2 ** 30)
-        with warnings.catch_warnings():
-            warnings.simplefilter("ignore")
-            qmc = MultivariateNormalQMC(np.zeros(p - 1), seed=seed, inv_transform=False)
-        self._upload(qmc.engine, device)
+        if isinstance(seed, (int, np.integer)) and hasattr(np, "bitwise_count"):
+            self._upload_tables(2 * math.ceil((p - 1) / 2), seed, True, device)     # engine dimension: even
+        else:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                qmc = MultivariateNormalQMC(np.zeros(p - 1), seed=seed, inv_transform=False)
+            self._upload(qmc.engine, device)
         self.total = min(self.total, 2 ** self.bits)
 
     def take(self, count):

@@ -117,3 +117,24 @@ def test_lane_level_lift_model_matches_oracle(p):
         got = lm.lifts_one(R_tr, c_tr, R_te, c_te, ynsq, perm)
         want = lo.square_shapley(R_tr, R_te, c_tr, c_te, ynsq, perm)
         assert np.max(np.abs(got - want)) < 1e-12 * max(np.max(np.abs(want)), 1e-300) + 1e-15
+
+
+def test_fast_sobol_tables_equal_scipy_engines():
+    """samplers.sobol_tables (vectorised rebuild of scipy's LMS scrambling) against the engines scipy
+    itself constructs: Sobol(d, seed) and the engine inside MultivariateNormalQMC (spawned stream)."""
+    import warnings
+    from scipy.stats.qmc import MultivariateNormalQMC, Sobol
+    from ls_spa_b200.samplers import sobol_tables
+    for d, seed in ((1, 0), (5, 3), (37, 123), (100, 42), (100, 7), (1000, 5)):
+        e = Sobol(d, seed=seed)
+        sv, shift = sobol_tables(d, seed)
+        assert sv.dtype == np.uint32 and sv.shape == (d, 30)
+        assert np.array_equal(sv, e._sv.astype(np.uint32)) and np.array_equal(shift, e._shift.astype(np.uint32)), (d, seed)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for p, seed in ((2, 1), (10, 42), (11, 5), (100, 42), (1000, 9)):
+            q = MultivariateNormalQMC(np.zeros(p - 1), seed=seed, inv_transform=False)
+            sv, shift = sobol_tables(q.engine.d, seed, spawn=True)
+            assert q.engine.bits == 30 and q.engine.d == 2 * -(-(p - 1) // 2)
+            assert np.array_equal(sv, q.engine._sv.astype(np.uint32)), (p, seed)
+            assert np.array_equal(shift, q.engine._shift.astype(np.uint32)), (p, seed)
