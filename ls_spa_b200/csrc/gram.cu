@@ -225,13 +225,6 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
                "l"(map), "r"(c0), "r"(c1), "r"(tma_smem(bar))
                : "memory");
 }
-__device__ __forceinline__ void tma_load_1d(void *dst, const CUtensorMap *map, int c0, uint64_t *bar) {
-  asm volatile("cp.async.bulk.tensor.1d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2}], [%3];" ::"r"(
-                   tma_smem(dst)),
-               "l"(map), "r"(c0), "r"(tma_smem(bar))
-               : "memory");
-}
-
 // The upper tiles (row-major order: (0,0) .. (0,NT-1), (1,1) ..) are dealt to the eight consumer warps in
 // contiguous runs of T/8 tiles, T = NT (NT + 1) / 2: every warp -- and with it every SM sub-partition --
 // gets the same number of DMMAs (+-1).  NT and the warp index are template parameters, so the run is a

@@ -31,6 +31,9 @@ PICK = {
     "issue_active_pct": "smsp__issue_active.avg.pct_of_peak_sustained_active",
     "pipe_fp64_cycles_active_pct":
         "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+    "dmma_pipe_active_pct":
+        "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active",
+    "l2_hit_rate_pct": "lts__t_sector_hit_rate.pct",
     "inst_executed": "smsp__inst_executed.sum",
     "smem_wavefronts": "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
     "smem_wavefronts_pct_of_peak":
