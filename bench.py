@@ -241,6 +241,29 @@ def side_configs(L, torch, dev):
     run("C2", "p=10, N=M=1e5, method=exact (all 10! = 3628800 permutations)", 10, 100_000, 3_628_800, method="exact")
     run("C3", "p=100, N=M=1e5, method=argsort, 2^7 x 2^7 samples, no antithetic pairs", 100, 100_000, 1 << 14,
         method="argsort", batch_size=128, num_batches=128, tolerance=0.0, antithetical=False)
+    # the guarded fallback, measured: singular values spread over 1e5 in random directions, so the condition
+    # guard refuses the Cholesky route: two-pass CholeskyQR reduction + Householder lift kernel (lifts_mma.cu)
+    g = torch.Generator(device=dev).manual_seed(5)
+    Q, _ = torch.linalg.qr(torch.randn(P, P, generator=g, device=dev, dtype=torch.float64))
+    mixm = (Q * torch.logspace(0, -5, P, device=dev, dtype=torch.float64)) @ Q.T
+    n = 100_000
+    Xtr = torch.randn(n, P, generator=g, device=dev, dtype=torch.float64) @ mixm
+    Xte = torch.randn(n, P, generator=g, device=dev, dtype=torch.float64) @ mixm
+    th = torch.randn(P, generator=g, device=dev, dtype=torch.float64)
+    ytr = Xtr @ th + 1e-3 * torch.randn(n, generator=g, device=dev, dtype=torch.float64)
+    yte = Xte @ th + 1e-3 * torch.randn(n, generator=g, device=dev, dtype=torch.float64)
+    kw = dict(method="permutohedron", batch_size=128, num_batches=128, tolerance=0.0, antithetical=True)
+    from ls_spa_b200 import ops as _ops
+    L.ls_spa(Xtr, Xte, ytr, yte, **kw)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    r = L.ls_spa(Xtr, Xte, ytr, yte, **kw)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out["ill_conditioned_p100"] = {
+        "workload": "p=100, N=M=1e5, cond(X) = 1e5 in random directions, permutohedron, 2^14 antithetic pairs, tolerance 0",
+        "route": _ops.LIFT_ROUTE, "seconds": dt, "permutations": 2 << 14, "permutations_per_s": (2 << 14) / dt,
+        "sum_attribution_minus_r2": float(abs(r.attribution.sum() - r.r_squared))}
     return out
 
 

@@ -872,6 +872,105 @@ __global__ void __launch_bounds__(kC4Threads, MINB) lifts_chol4_kernel(CholParam
   }
 }
 
+// Elimination half of the split route (MODE 2 of lifts_chol_kernel) on the packed layout: four warps,
+// four CTAs per SM.  The factors of one evaluation (R's upper tiles with c~, then the inverses of the
+// diagonal blocks, as lsspa_lifts_chol_factor wrote them) are copied into the packed tile array with
+// 16-byte cp.async, the inverses over the diagonal tiles (last block: side buffer, see above), then
+// phase 2 and the cost / lift / scatter epilogue of lifts_chol4_kernel.
+template <int RT, int PT, int MINB>
+__global__ void __launch_bounds__(kC4Threads, MINB) lifts_elim4_kernel(CholParams a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int p = a.p;
+  constexpr int NR = 8 * RT;
+  constexpr int TOT = pk_off(PT, RT);
+  constexpr int64_t FD = chol_fact_doubles(RT, PT);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c = lane >> 2, q = lane & 3;
+  double *A = reinterpret_cast<double *>(smem_raw);
+  double *Dlast = A + TOT;
+  double *wcost = Dlast + 64;
+  double *cost = wcost + (size_t)4 * NR;
+  double *acc = cost + (p + 2);
+  int *perm_s = reinterpret_cast<int *>(acc + p + (p & 1));
+  const int halves = a.anti ? 2 : 1;
+  const double weight = a.anti ? 0.5 : 1.0;
+  constexpr int LP = PT - 1;
+  const double *cvec = A + pk_off(LP, RT) + (p - 8 * LP) * pk_ld(LP, RT);
+
+  for (int64_t sidx = blockIdx.x; sidx < a.count; sidx += gridDim.x) {
+    for (int h = 0; h < halves; ++h) {
+      __syncthreads();
+      for (int k = tid; k <= p; k += kC4Threads)
+        perm_s[k] = (k == p) ? p : a.perms[sidx * p + (h == 0 ? k : p - 1 - k)];
+      const double *src = a.fact + (sidx * halves + h) * FD;
+      // tile column L: 8 columns of rows(L) doubles, contiguous in the record; 16 bytes per copy
+#pragma unroll
+      for (int L = 0; L < PT; ++L) {
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int rows = pk_rows(L, RT);
+        int off = 0;
+#pragma unroll
+        for (int k = 0; k < L; ++k) off += 8 * pk_rows(k, RT);
+        const int n2 = 8 * rows / 2;   // double2 in this tile column
+        for (int e = tid; e < n2; e += kC4Threads) {
+          const int cc = e / (rows / 2), r2 = e - cc * (rows / 2);
+          const unsigned dsta = (unsigned)__cvta_generic_to_shared(A + pk_off(L, RT) + cc * pk_ld(L, RT) + 2 * r2);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dsta), "l"(src + off + 2 * e) : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (warp == 3) {
+        double s0 = 0.0;
+        for (int i = lane; i < p; i += 32) s0 = fma(a.cte[i], a.cte[i], s0);
+        s0 = warp_sum(s0);
+        if (lane == 0) cost[0] = s0;
+      }
+      for (int e = tid; e < 4 * NR; e += kC4Threads) wcost[e] = 0.0;
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+      // inverses of the diagonal blocks (8 x 8, leading dimension 8) over the diagonal tiles
+      {
+        const double *dsrc = src + (FD - 64 * RT);
+        for (int e = tid; e < 32 * RT; e += kC4Threads) {
+          const int sblk = e >> 5, l = e & 31;          // block, lane-like index: 2 l = cc * 8 + 2 qq
+          const double2 v = __ldg(reinterpret_cast<const double2 *>(dsrc) + e);
+          const int cc = l >> 2, qq = l & 3;
+          if (sblk < RT - 1)
+            *reinterpret_cast<double2 *>(A + pk_off_rt<RT>(sblk) + cc * pk_ld_rt<RT>(sblk) + 8 * sblk + 2 * qq) = v;
+          else
+            *reinterpret_cast<double2 *>(Dlast + cc * 8 + 2 * qq) = v;
+        }
+      }
+      __syncthreads();
+      double *wc = wcost + (size_t)warp * NR;
+      {
+        double xr[RT][2];
+        double r_in = 0.0;
+        for (int it = warp; it < RT; it += 4) {
+          load_x<RT>(xr, r_in, a, perm_s, it, p, c, q);
+          elim_all4<RT>(xr, r_in, wc, A, Dlast, cvec, p, c, q);
+        }
+      }
+      __syncthreads();
+      for (int k = tid; k < p; k += kC4Threads) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) sacc += wcost[(size_t)w * NR + k];
+        cost[k + 1] = sacc;
+      }
+      __syncthreads();
+      for (int k = tid; k < p; k += kC4Threads) {
+        const double lift = (cost[k] - cost[k + 1]) * a.inv_ynsq;
+        const int f = perm_s[k];
+        acc[f] = (h == 0 ? 0.0 : acc[f]) + weight * lift;
+      }
+    }
+    __syncthreads();
+    for (int f = tid; f < p; f += kC4Threads) a.out[sidx * p + f] = acc[f];
+  }
+}
+
 template <int RT>
 size_t chol4_smem_bytes(int p, int pt) {
   const int tot = (pt == RT) ? pk_off(RT, RT) : pk_off(RT + 1, RT);
@@ -891,8 +990,18 @@ int launch_chol4(const CholParams &a, int grid, size_t smem, int sms, cudaStream
 }
 
 // p = 49 .. 128 (RT = 7 .. 16): CTAs per SM from the packed footprint
+template <int RT, int PT, int MINB>
+int launch_elim4(const CholParams &a, int grid, size_t smem, cudaStream_t st) {
+  LSSPA_CUDA_TRY(cudaFuncSetAttribute(lifts_elim4_kernel<RT, PT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  LSSPA_CUDA_TRY(cudaFuncSetAttribute(lifts_elim4_kernel<RT, PT, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared));
+  lifts_elim4_kernel<RT, PT, MINB><<<grid, kC4Threads, smem, st>>>(a);
+  LSSPA_LAUNCH_CHECK();
+  return LSSPA_OK;
+}
+
 template <int RT>
-int run_chol4(const CholParams &a, int64_t count, cudaStream_t st) {
+int run_chol4(const CholParams &a, int64_t count, int mode, cudaStream_t st) {
   const DeviceInfo &d = device_info();
   const int sms = d.sm_count > 0 ? d.sm_count : 148;
   const size_t smem = chol4_smem_bytes<RT>(a.p, a.pt);
@@ -904,6 +1013,8 @@ int run_chol4(const CholParams &a, int64_t count, cudaStream_t st) {
   int64_t grid = (int64_t)per_sm * sms;
   if (grid > count) grid = count;
   constexpr int MINB = RT <= 13 ? 4 : (RT <= 15 ? 3 : 2);   // resident CTAs the register budget is cut for
+  if (mode == 2)
+    return (a.pt == RT) ? launch_elim4<RT, RT, MINB>(a, (int)grid, smem, st) : launch_elim4<RT, RT + 1, MINB>(a, (int)grid, smem, st);
   return (a.pt == RT) ? launch_chol4<RT, RT, MINB>(a, (int)grid, smem, sms, st)
                       : launch_chol4<RT, RT + 1, MINB>(a, (int)grid, smem, sms, st);
 }
@@ -1165,18 +1276,18 @@ static int chol_run(int mode, int p, const double *gram, const double *R_te_cm, 
     const char *e = getenv("LSSPA_CHOL_PACKED");     // 0: the eight-warp kernel everywhere (A/B timing)
     return !(e && e[0] == '0');
   }();
-  if (mode == 0 && packed) {
+  if ((mode == 0 || mode == 2) && packed) {
     switch (a.rt) {
-      case 7: return run_chol4<7>(a, count, st);
-      case 8: return run_chol4<8>(a, count, st);
-      case 9: return run_chol4<9>(a, count, st);
-      case 10: return run_chol4<10>(a, count, st);
-      case 11: return run_chol4<11>(a, count, st);
-      case 12: return run_chol4<12>(a, count, st);
-      case 13: return run_chol4<13>(a, count, st);
-      case 14: return run_chol4<14>(a, count, st);
-      case 15: return run_chol4<15>(a, count, st);
-      case 16: return run_chol4<16>(a, count, st);
+      case 7: return run_chol4<7>(a, count, mode, st);
+      case 8: return run_chol4<8>(a, count, mode, st);
+      case 9: return run_chol4<9>(a, count, mode, st);
+      case 10: return run_chol4<10>(a, count, mode, st);
+      case 11: return run_chol4<11>(a, count, mode, st);
+      case 12: return run_chol4<12>(a, count, mode, st);
+      case 13: return run_chol4<13>(a, count, mode, st);
+      case 14: return run_chol4<14>(a, count, mode, st);
+      case 15: return run_chol4<15>(a, count, mode, st);
+      case 16: return run_chol4<16>(a, count, mode, st);
       default: break;
     }
   }
