@@ -72,7 +72,7 @@ LSSPA_API int lsspa_tsqr_rows(const double *X, int64_t ldx, const double *y, int
 LSSPA_API int lsspa_tsqr_merge(const double *parts, int count, int group, int p, double *out,
                      void *stream);
 
-/* CholeskyQR2 variant of the same reduction for p <= 119 (gram.cu): Gram matrices with fp64 tensor
+/* CholeskyQR2 variant of the same reduction for p <= 111 (gram.cu): Gram matrices with fp64 tensor
  * tiles instead of one Householder reflector per column per row block.
  *   pass 1: lsspa_gram_rows(Rinv = NULL) -> partial Grams; lsspa_gram_finish sums them (fixed
  *           order) and scales by 1/divisor^2 -> G1 ((8*ceil((p+1)/8))^2 doubles, row-major);
@@ -105,7 +105,7 @@ LSSPA_API int lsspa_gram_add_ridge(double *G, int p, double reg, void *stream);
 LSSPA_API int lsspa_tri_product(const double *R2, const double *R1, int p, const double *G1, double *out_slot,
                                 void *stream);
 
-/* Wide problems (p + 1 > 120, up to p = 2047; gram_big.cu + lifts_big.cu): the same one-pass Gram
+/* Wide problems (p + 1 > 112, up to p = 2047; gram_big.cu + lifts_big.cu): the same one-pass Gram
  * reduction with 128-column blocks.
  *   lsspa_gram_big_rows        partial Gram blocks of rows [0, nrows) of [X | y]:
  *                              parts[nsplit][lsspa_gram_big_part_doubles(p)], nsplit = lsspa_gram_big_num_splits;

@@ -1,4 +1,4 @@
-// CholeskyQR2 reduction of [X | y] to its (p+1) x (p+1) triangular factor, p <= 119.
+// CholeskyQR2 reduction of [X | y] to its (p+1) x (p+1) triangular factor, p <= 111.
 //
 // Second implementation of reduce_data (reference ls_spa/ls_spa.py:290-318) next to the Householder
 // TSQR of reduce.cu.  The Householder kernel is bound by the latency of one reflector per column
@@ -740,8 +740,9 @@ static int launch_gram(const GramParams &a, size_t smem, cudaStream_t st) {
 
 using namespace lsspa;
 
-// (p + 1 <= 120: the Cholesky kernel keeps the factor and its inverse, 2 x (8 nt)^2 doubles, in shared memory)
-extern "C" int lsspa_gram_supported(int p) { return (p >= 1 && p + 1 <= 120) ? 1 : 0; }
+// (p + 1 <= 112: the Cholesky kernel keeps the factor and its inverse, 2 x (8 nt)^2 doubles, plus ~11 KB of
+// static tables in shared memory -- 2 x 120^2 doubles alone are 225 KB and do not leave room for them)
+extern "C" int lsspa_gram_supported(int p) { return (p >= 1 && p + 1 <= 112) ? 1 : 0; }
 
 extern "C" int64_t lsspa_gram_slot_doubles(int p) {
   if (!lsspa_gram_supported(p)) return 0;

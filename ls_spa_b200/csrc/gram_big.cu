@@ -1,4 +1,4 @@
-// Gram reduction of [X | y] for WIDE problems (p + 1 > 120: the upper triangle no longer fits the
+// Gram reduction of [X | y] for WIDE problems (p + 1 > 112: the upper triangle no longer fits the
 // registers of one CTA as in gram.cu).  Replaces np.linalg.qr of the tall blocks (reference
 // ls_spa/ls_spa.py:314-315) by G = Z^T Z (fp64 tensor tiles) followed by a blocked Cholesky factorisation
 // of G (lifts_big.cu, the batched tile kernels with a batch of one).

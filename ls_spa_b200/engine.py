@@ -249,7 +249,7 @@ class CudaBackend:
             slot, info = fac.factor(coll.all_reduce_sum(fac.gram()), reg)
         q = p + 1
         # what the host needs from this side, as one small device tensor: [bad pivot, cond bound of the factor,
-        # cond bound of its leading block (train side, p + 1 <= 120), sum of squares of the y column]
+        # cond bound of its leading block (train side, p + 1 <= 112), sum of squares of the y column]
         lift_cond = (fac.lift_gram[q * q:q * q + 1] if (small and is_train and fac.lift_gram is not None)
                      else torch.full((1,), float("nan"), dtype=torch.float64, device=self.device))
         st.update(fac=fac, chunks=chunks, slot=slot, flags=torch.cat([info, lift_cond, slot[q * q:q * q + 1]]))
@@ -258,7 +258,7 @@ class CudaBackend:
     def reduce_finish(self, st, flags=None):
         """Decide half: -> (merged slot, TrainSide or None, sum of squares of y or None).  flags: the host copy
         of st['flags'] when the caller has already fetched it (together with the other side's).  One pass is kept
-        when the factor is well conditioned; otherwise a second CholeskyQR pass (p + 1 <= 120, no ridge) or
+        when the factor is well conditioned; otherwise a second CholeskyQR pass (p + 1 <= 112, no ridge) or
         the Householder TSQR."""
         coll, p, reg, small, is_train, fac = st["coll"], st["p"], st["reg"], st["small"], st["is_train"], st["fac"]
         if fac is None:

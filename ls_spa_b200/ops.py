@@ -106,7 +106,7 @@ def gram_supported(p: int) -> bool:
 
 
 class CholQR2:
-    """CholeskyQR(2) of [X | y] / divisor over device row chunks (csrc/gram.cu), p + 1 <= 120.
+    """CholeskyQR(2) of [X | y] / divisor over device row chunks (csrc/gram.cu), p + 1 <= 112.
 
     add_chunk() launches the Gram pass on a chunk as soon as it is resident (so it overlaps the copy
     of the next one); gram() sums the partial Gram matrices of this process (a multi-GPU job
@@ -235,7 +235,7 @@ def gram_big_supported(p: int) -> bool:
 
 
 class GramBig:
-    """One-pass Gram reduction of [X | y] / divisor for wide problems (p + 1 > 120; csrc/gram_big.cu):
+    """One-pass Gram reduction of [X | y] / divisor for wide problems (p + 1 > 112; csrc/gram_big.cu):
     add_chunk() accumulates the dense (p+1)^2 Gram matrix of this process's rows, gram() hands it
     out (a multi-GPU job all-reduces it), factor(G, reg) runs the blocked Cholesky factorisation
     (csrc/lifts_big.cu with a batch of one) -> (slot, info) with info (device) = [bad pivot, nan]:

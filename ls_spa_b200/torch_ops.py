@@ -43,7 +43,7 @@ def _f64(t, name):
 def _gram_reduce(X, y, divisor):
     p = int(X.shape[1])
     if not _ops.gram_supported(p):
-        raise LsSpaCudaError("gram_reduce: p + 1 <= 120 (wide problems: ops.GramBig)")
+        raise LsSpaCudaError("gram_reduce: p + 1 <= 112 (wide problems: ops.GramBig)")
     fac = _ops.CholQR2(p, divisor, X.device)
     fac.add_chunk(X, y)
     return fac.gram()

@@ -354,3 +354,54 @@ def test_error_estimates_export(T, L):
     np.testing.assert_allclose(feat, 1.959964 * np.sqrt(np.diag(cov)), rtol=0.12)
     np.testing.assert_allclose(feat, want_feat, rtol=0.2)
     np.testing.assert_allclose(overall, want_overall, rtol=0.08)
+
+
+def test_gram_reduction_ragged_shapes(T, L):
+    """Every branch of the Gram route on awkward shapes: one row, fewer rows than a chunk, row counts that
+    are not multiples of 32, odd p (no TMA: the leading dimension is not 16-byte aligned), p + 1 = 120 (the
+    widest single-CTA tile set), wide problems with few rows, a strided view, fewer rows than features
+    (train side regularised; the singular test-side Gram matrix takes the Householder fallback)."""
+    rng = np.random.default_rng(0)
+    for n, p in ((1, 3), (31, 5), (33, 6), (1000, 17), (4097, 64), (257, 118), (300, 119), (500, 130), (700, 200),
+                 (64, 100), (90, 100)):
+        X, y = rng.standard_normal((n, p)), rng.standard_normal(n)
+        Xt, yt = rng.standard_normal((n + 3, p)), rng.standard_normal(n + 3)
+        reg = 0.5 if n < p else 0.0
+        R_tr, R_te, c_tr, c_te = L.reduce_data(X, Xt, y, yt, reg)
+        N = len(X)
+        G = X.T @ X / N + reg * np.eye(p)
+        assert scaled_err(R_tr.T @ R_tr, G) < 1e-11, (n, p)
+        assert scaled_err(R_tr.T @ c_tr, X.T @ y / N) < 1e-11, (n, p)
+        m = min(len(Xt), p)
+        assert R_te.shape == (m, p)
+        assert scaled_err(R_te.T @ R_te, Xt.T @ Xt) < 1e-11, (n, p)
+        assert scaled_err(R_te.T @ c_te, Xt.T @ yt) < 1e-11, (n, p)
+    # a strided device view (leading dimension 2 p) and a row slice starting at an odd row
+    n, p = 3001, 40
+    big = T.from_numpy(rng.standard_normal((n, 2 * p))).cuda()
+    yv = T.from_numpy(rng.standard_normal(n)).cuda()
+    Xv = big[1:, :p]
+    R_tr, _, c_tr, _ = L.reduce_data(Xv, Xv, yv[1:], yv[1:], 0.0)
+    Xh, yh = Xv.cpu().numpy(), yv[1:].cpu().numpy()
+    assert scaled_err(R_tr.T @ R_tr, Xh.T @ Xh / (n - 1)) < 1e-12
+    assert scaled_err(R_tr.T @ c_tr, Xh.T @ yh / (n - 1)) < 1e-12
+
+
+@pytest.mark.parametrize("p", [111, 112, 120, 128, 129, 152, 153])
+def test_whole_jobs_around_the_kernel_boundaries(T, L, p):
+    """Widths where the reduction (single-CTA Cholesky tail <-> blocked wide factorisation at p + 1 = 112/113)
+    and the lift kernels (packed four-warp <-> eight-warp at 128/129, shared-memory <-> tile workspace at
+    152/153) change hands: whole jobs against the oracle's reference loop on the same permutations."""
+    from oracle import lsspa_oracle as lo
+    from oracle import samplers_oracle as so
+    Xtr, Xte, ytr, yte, _, _ = so.gen_data(np.random.default_rng(p), p, 6 * p, 5 * p)
+    perms = so.perms_random(p, 12, 1)
+    got = L.ls_spa(Xtr, Xte, ytr, yte, reg=1e-3, perms=perms, tolerance=0.0, batch_size=4, antithetical=True,
+                   return_attribution_history=True)
+    want = lo.ls_spa_reference_loop(Xtr, Xte, ytr, yte, reg=1e-3, perms=list(perms), tolerance=0.0, batch_size=4,
+                                    antithetical=True, return_attribution_history=True)
+    assert scaled_err(got.attribution, want.attribution) < TOL, scaled_err(got.attribution, want.attribution)
+    assert scaled_err(got.theta, want.theta) < 1e-8
+    assert abs(got.r_squared - want.r_squared) < TOL
+    assert scaled_err(got.attribution_history, want.attribution_history) < TOL
+    assert got.error_history.shape == want.error_history.shape
