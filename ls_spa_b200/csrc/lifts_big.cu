@@ -223,21 +223,59 @@ __global__ void __launch_bounds__(256) big_diag_kernel(BigParams a) {
   }
   for (int e = tid; e < kNB * kNB; e += 256) V[e / kNB][e % kNB] = 0.0;
   __syncthreads();
-  // right-looking Cholesky on the upper triangle
-  for (int k = 0; k < kNB; ++k) {
-    const double d = S[k][k];
-    const bool ok = d > 1e-280;
-    const double ri = ok ? rsqrt(d) : 0.0;
-    if (!ok && tid == 0 && kNB * j + k < a.p) atomicExch(a.status, 1);
-    if (tid >= k && tid < kNB) urow[tid] = (tid == k) ? (ok ? d * ri : 0.0) : S[k][tid] * ri;
-    __syncthreads();
-    if (tid >= k && tid < kNB) S[k][tid] = urow[tid];
-    for (int e = tid; e < kNB * kNB; e += 256) {
-      const int m = e / kNB, n = e % kNB;
-      if (m > k && n >= m) S[m][n] = fma(-urow[m], urow[n], S[m][n]);
+  // right-looking Cholesky on the upper triangle with the tile in REGISTERS: thread (ty = warp, tx = lane)
+  // owns the entries (i, j) = (ty + 8 ii, tx + 32 jj).  Row k belongs to warp k % 8, which gets the pivot
+  // by one shuffle, scales its row and publishes it through the double-buffered urow: one barrier per
+  // column.  (The column loop is split into blocks of eight so that every register index is static.)
+  {
+    double ar[8][2];
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii)
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) ar[ii][jj] = S[warp + 8 * ii][lane + 32 * jj];
+    double *ub = urow;            // 2 x kNB
+#pragma unroll
+    for (int kb = 0; kb < 8; ++kb) {
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        const int k = 8 * kb + kk;
+        double *uc = ub + (k & 1) * kNB;
+        if (warp == kk) {
+          const double d = __shfl_sync(kFull, ar[kb][k >> 5], k & 31);
+          const bool ok = d > 1e-280;
+          const double ri = ok ? rsqrt(d) : 0.0;
+          if (!ok && lane == 0 && kNB * j + k < a.p) atomicExch(a.status, 1);
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) {
+            const int n = lane + 32 * jj;
+            if (n >= k) {
+              const double v = (n == k) ? (ok ? d * ri : 0.0) : ar[kb][jj] * ri;
+              ar[kb][jj] = v;
+              uc[n] = v;
+            }
+          }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int ii = kb; ii < 8; ++ii) {
+          const int m = warp + 8 * ii;
+          if (m > k) {
+            const double um = uc[m];
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+              const int n = lane + 32 * jj;
+              if (n >= m) ar[ii][jj] = fma(-um, uc[n], ar[ii][jj]);
+            }
+          }
+        }
+      }
     }
-    __syncthreads();
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii)
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) S[warp + 8 * ii][lane + 32 * jj] = ar[ii][jj];
   }
+  __syncthreads();
   // inverse of the upper-triangular U: column n by back substitution, four lanes per column (they split
   // the dot product of each step and combine with two shuffles; a column only ever touches its own
   // entries of V, so warp-level synchronisation suffices).  Zero pivots give zero rows / columns.
@@ -734,7 +772,7 @@ extern "C" int lsspa_gram_big_factor(const double *G_acc, int p, double scale, d
   a.nevals = 1;
   cudaStream_t st = as_stream(stream);
   const size_t panel_smem = ((size_t)kStages * kStageD + kTileD) * sizeof(double) + (2 * kStages + 1) * sizeof(uint64_t);
-  const size_t diag_smem = ((size_t)2 * kNB * (kNB + 1) + kNB) * sizeof(double);
+  const size_t diag_smem = ((size_t)2 * kNB * (kNB + 1) + 2 * kNB) * sizeof(double);
   LSSPA_CUDA_TRY(cudaFuncSetAttribute(big_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)diag_smem));
   LSSPA_CUDA_TRY(cudaFuncSetAttribute(big_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem));
   dense_to_tiles_kernel<<<dim3((unsigned)a.T, (unsigned)a.T), 256, 0, st>>>(a, G_acc, scale, reg);
@@ -794,7 +832,7 @@ extern "C" int lsspa_lifts_big(int p, const double *gram, const double *R_te_cm,
   const size_t gather_smem = (size_t)8 * rowlen * sizeof(double) + (size_t)kNB * a.T * sizeof(int);
   const size_t panel_smem = ((size_t)kStages * kStageD + kTileD) * sizeof(double) + (2 * kStages + 1) * sizeof(uint64_t);
   const size_t cost_smem = ((size_t)3 * p + 1 + 32 * 32) * sizeof(double) + (size_t)p * sizeof(int);
-  const size_t diag_smem = ((size_t)2 * kNB * (kNB + 1) + kNB) * sizeof(double);
+  const size_t diag_smem = ((size_t)2 * kNB * (kNB + 1) + 2 * kNB) * sizeof(double);
   LSSPA_CUDA_TRY(cudaFuncSetAttribute(big_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)diag_smem));
   LSSPA_CUDA_TRY(cudaFuncSetAttribute(big_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gather_smem));
   LSSPA_CUDA_TRY(cudaFuncSetAttribute(big_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_smem));
