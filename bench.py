@@ -409,6 +409,25 @@ def run_gpu(args):
     e2e_val = perms_per_step / float(e2e_s.item())
     r = last["e2e"]
     d2h = 8 * (r.attribution.size + r.theta.size + r.attribution_errors.size + r.error_history.size + 2)
+    # the optional fp32 TRANSFER mode: the same values rounded to float32 in pinned host memory cross the
+    # link as float32 (half the bytes) and are widened on the device; the arithmetic stays fp64
+    host32 = [t.float().cpu().pin_memory() for t in (Xtr, Xte, ytr, yte)]
+
+    def step_e2e32():
+        last["e2e32"] = L.ls_spa(host32[0], host32[1], host32[2], host32[3], **kw)
+
+    step_e2e32()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e32()
+    barrier()
+    e2e32_s = torch.tensor([(time.perf_counter() - t0) / args.steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e32_s, op=dist.ReduceOp.MAX)
+    e2e32_val = perms_per_step / float(e2e32_s.item())
+    e2e32_diff = float(np.max(np.abs(last["e2e32"].attribution - last["e2e"].attribution)) / np.max(np.abs(last["e2e"].attribution)))
+    del host32
     # the link alone: the same pinned buffers copied once more (reported next to e2e)
     dst = torch.empty_like(Xtr)
     torch.cuda.synchronize()
@@ -470,6 +489,9 @@ def run_gpu(args):
                        "l2": "inputs (2 x 808 MB / n_gpus) larger than L2; no explicit flush"},
             "e2e": {"value": e2e_val, "unit": "permutations/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "timer": "wall clock around ls_spa() incl. H2D/D2H, max over ranks",
+                    "float32_inputs": {"value": e2e32_val, "unit": "permutations/s", "h2d_bytes_per_step": h2d // 2,
+                                       "note": "optional fp32 transfer mode: float32 pinned host inputs, widened on the "
+                                               "device, fp64 arithmetic", "max_scaled_attribution_diff_vs_f64_inputs": e2e32_diff},
                     "h2d_link_gbs_measured": h2d_gbs,
                     "link_floor_permutations_per_s": perms_per_step / (h2d / (h2d_gbs * 1e9))},
             "gpu_launches": launches,

@@ -114,7 +114,7 @@ def _coerce(a, two_d: bool):
     if isinstance(a, torch.Tensor):
         return a
     arr = np.array(a)
-    if arr.dtype != np.float64:
+    if arr.dtype not in (np.float64, np.float32):      # float32 stays: it is widened on the device, after the copy
         arr = arr.astype(np.float64)
     if not two_d and arr.ndim != 1:
         raise ValueError("y_train / y_test must be one-dimensional")
@@ -228,7 +228,8 @@ def ls_spa(X_train, X_test, y_train, y_test, reg: float = 0.0, method: str | Non
     test_on_host = not (isinstance(X_test, torch.Tensor) and X_test.is_cuda)
     if (coll.world == 1 and test_on_host and perms is None and meth != "exact" and total is not None
             and ops.split_route_supported(p) and os.environ.get("LSSPA_SPLIT_ROUTE", "1") != "0"):
-        pre = engine.Prefactor(backend, cfg, get_source, 8 * int(X_test.shape[0]) * (p + 1))
+        esize = 4 if getattr(X_test, "dtype", None) in (np.float32, torch.float32) else 8
+        pre = engine.Prefactor(backend, cfg, get_source, esize * int(X_test.shape[0]) * (p + 1))
     prob = engine.reduce_problem(backend, coll, X_train, X_test, y_train, y_test, float(reg), p,
                                  row_sharded=row_sharded, prefactor=pre)
     source = pre.source if (pre is not None and pre.source is not None) else get_source()

@@ -135,10 +135,13 @@ class CudaBackend:
             return
         Xh = X if isinstance(X, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(X))
         yh = y if isinstance(y, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(y))
-        if Xh.dtype != torch.float64:
+        # float32 host data crosses the link as float32 (half the bytes) and is widened on the device -- exact,
+        # so the arithmetic below is the same fp64 arithmetic on the same values; any other dtype is widened here
+        if Xh.dtype not in (torch.float64, torch.float32):
             Xh = Xh.to(torch.float64)
-        if yh.dtype != torch.float64:
+        if yh.dtype not in (torch.float64, torch.float32):
             yh = yh.to(torch.float64)
+        narrow_x, narrow_y = Xh.dtype == torch.float32, yh.dtype == torch.float32
         rows = hi - lo
         chunk = max(1, min(rows, (128 << 20) // (8 * (p + 1))))
         if self.copy_stream is None:
@@ -163,6 +166,8 @@ class CudaBackend:
         else:
             self.copy_stream.wait_stream(main)
         free_ev = [None, None]
+        tmpx = torch.empty((chunk, p), dtype=torch.float32, device=self.device) if narrow_x else None
+        tmpy = torch.empty(chunk, dtype=torch.float32, device=self.device) if narrow_y else None
         for i, r0 in enumerate(range(lo, hi, chunk)):
             r1 = min(r0 + chunk, hi)
             if keep:
@@ -172,8 +177,16 @@ class CudaBackend:
             with torch.cuda.stream(self.copy_stream):
                 if not keep and free_ev[i % 2] is not None:
                     self.copy_stream.wait_event(free_ev[i % 2])
-                bx.copy_(Xh[r0:r1], non_blocking=True)
-                by.copy_(yh[r0:r1], non_blocking=True)
+                if narrow_x:       # (the staging buffer is only touched on the copy stream, in order)
+                    tmpx[: r1 - r0].copy_(Xh[r0:r1], non_blocking=True)
+                    bx.copy_(tmpx[: r1 - r0])
+                else:
+                    bx.copy_(Xh[r0:r1], non_blocking=True)
+                if narrow_y:
+                    tmpy[: r1 - r0].copy_(yh[r0:r1], non_blocking=True)
+                    by.copy_(tmpy[: r1 - r0])
+                else:
+                    by.copy_(yh[r0:r1], non_blocking=True)
                 ready = torch.cuda.Event()
                 ready.record(self.copy_stream)
             main.wait_event(ready)
