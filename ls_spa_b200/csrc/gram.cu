@@ -459,7 +459,20 @@ __global__ void gram_sum_kernel(const double *parts, int count, int n2, int nc, 
   G[e] = s * scale;
 }
 
+// 1/sqrt(d) from the 20-bit MUFU seed and two correction steps (cubic, then quadratic): the library
+// rsqrt() carries a slow-path call on the pivot chain of chol_factor_kernel
+__device__ __forceinline__ double rsqrt_seed3(double d) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  double e = fma(-d * r, r, 1.0);
+  r = fma(r * e, fma(0.375, e, 0.5), r);
+  e = fma(-d * r, r, 1.0);
+  return fma(0.5 * r, e, r);
+}
+
 // Cholesky G = R^T R (upper, G row-major nc x nc, leading q x q block used), then R^-1.
+// One CTA, every instruction executed a handful of times: the run time is the INSTRUCTION FETCH of the code
+// touched (cold: the row passes evict it from L2 between launches), so the cold loops are kept rolled.
 // info[0] = 0 ok / 1 non-positive or tiny pivot (relative to the column's own norm),
 // info[1] = a bound >= cond_2(R') of the column-equilibrated factor R' = R D^-1 (the smaller of
 // |R'|_F |R'^-1|_F and sqrt(max row sum |G'|) sqrt(|R'^-1|_1 |R'^-1|_inf)),
@@ -474,6 +487,7 @@ __global__ void __launch_bounds__(1024) chol_factor_kernel(const double *G, int 
   __shared__ double s_fail, red[64];
   const int tid = threadIdx.x, nt = blockDim.x;
   const int tx = tid & 31, ty = tid >> 5, lane = tx, w = ty;
+#pragma unroll 1
   for (int e = tid; e < nc * nc; e += nt) {
     const int i = e / nc, j = e - i * nc;
     A[e] = (i < q && j < q && j >= i) ? G[e] : 0.0;
@@ -484,21 +498,24 @@ __global__ void __launch_bounds__(1024) chol_factor_kernel(const double *G, int 
   // everything that needs the Gram matrix itself is taken from the shared-memory copy BEFORE it is
   // overwritten by the factor: column scales d_k = sqrt(G_kk), the Gershgorin row sums of the equilibrated
   // matrix (whole matrix / leading block without the target column) and the record for the lift route
-  __shared__ double dsq[128], gdiag[128];
+  __shared__ double dsq[128], rdsq[128], rdiag[128], gdiag[128];
   __shared__ double b_g[2][128], b_c[2][128], b_r[2][128];
   const int pp = q - 1;   // leading block = the features without the target column
+#pragma unroll 1
   for (int k = tid; k < q; k += nt) {
     gdiag[k] = A[(size_t)k * nc + k];
-    dsq[k] = sqrt(fmax(A[(size_t)k * nc + k], 0.0));
+    const double d = sqrt(fmax(A[(size_t)k * nc + k], 0.0));
+    dsq[k] = d;
+    rdsq[k] = d > 0.0 ? 1.0 / d : 0.0;
   }
   __syncthreads();
+#pragma unroll 1
   for (int t = w; t < q; t += 32) {
-    const double dt = dsq[t];
     double g = 0.0, gp = 0.0;
+#pragma unroll 1
     for (int k = lane; k < q; k += 32) {
-      const double dk = dsq[k];
       const double gij = (k >= t) ? A[(size_t)t * nc + k] : A[(size_t)k * nc + t];   // upper part
-      const double ge = (dt > 0.0 && dk > 0.0) ? fabs(gij) / (dt * dk) : 0.0;
+      const double ge = fabs(gij) * (rdsq[t] * rdsq[k]);
       g += ge;
       if (k < pp) gp += ge;
     }
@@ -512,6 +529,7 @@ __global__ void __launch_bounds__(1024) chol_factor_kernel(const double *G, int 
   if (gram_out != nullptr) {
     // Gh = [R D^-1 | c]^T [R D^-1 | c] = the Gram matrix with its feature rows / columns scaled to a unit
     // diagonal, and D -- what lsspa_lifts_gram derives from the factor, here straight from G (= R^T R)
+#pragma unroll 1
     for (int e = tid; e < q * q; e += nt) {
       const int i = e / q, j = e - i * q;
       const double gij = (j >= i) ? A[(size_t)i * nc + j] : A[(size_t)j * nc + i];
@@ -519,11 +537,13 @@ __global__ void __launch_bounds__(1024) chol_factor_kernel(const double *G, int 
       const double dj = (j < pp) ? (dsq[j] > 0.0 ? dsq[j] : 1.0) : 1.0;
       gram_out[e] = gij / (di * dj);
     }
+#pragma unroll 1
     for (int k = tid; k < pp; k += nt) gram_out[(size_t)q * q + 8 + k] = dsq[k] > 0.0 ? dsq[k] : 1.0;
   }
   __syncthreads();
   const long long c0 = clock64();
   double dmax = 0.0;
+#pragma unroll 1
   for (int i = 0; i < q; ++i) dmax = fmax(dmax, A[(size_t)i * nc + i]);
   // Right-looking Cholesky with the matrix in REGISTERS: thread (ty, tx) owns the entries (i, j) with
   // i = ty + 32 ii, j = tx + 32 jj.  Row k belongs to warp k % 32, which gets the pivot by one shuffle,
@@ -549,7 +569,7 @@ __global__ void __launch_bounds__(1024) chol_factor_kernel(const double *G, int 
         const bool good = d > 1e-14 * gdiag[k] && dmax > 0.0;
         if (!good && tx == 0) s_fail = 1.0;
         const double dd = d > 0.0 ? d : 1.0;
-        const double ri = rsqrt(dd);
+        const double ri = rsqrt_seed3(dd);
 #pragma unroll
         for (int jj = kb; jj < 4; ++jj) {
           const int j = tx + 32 * jj;
@@ -585,17 +605,24 @@ __global__ void __launch_bounds__(1024) chol_factor_kernel(const double *G, int 
   __syncthreads();
   const long long c1 = clock64();
   // inverse: column n of R^-1 by back substitution, four lanes per column (they split the dot product of
-  // each step and combine with two shuffles; a column only touches its own entries of Vi)
+  // each step and combine with two shuffles; a column only touches its own entries of Vi).  The reciprocals
+  // of the diagonal are taken once, in parallel: no division on the chain of 101 dependent steps.
+#pragma unroll 1
+  for (int k = tid; k < q; k += nt) rdiag[k] = 1.0 / A[(size_t)k * nc + k];
+  __syncthreads();
   {
     const int n = tid >> 2, part = tid & 3;
+#pragma unroll 1
     for (int i = q - 1; i >= 0; --i) {
       const double *row = A + (size_t)i * nc;
       double sacc = 0.0;
-      if (n < q && i <= n)
+      if (n < q && i <= n) {
+#pragma unroll 4
         for (int k = i + 1 + part; k <= n; k += 4) sacc = fma(-row[k], Vi[(size_t)k * nc + n], sacc);
+      }
       sacc += __shfl_xor_sync(kFull, sacc, 1);
       sacc += __shfl_xor_sync(kFull, sacc, 2);
-      if (n < q && i <= n && part == 0) Vi[(size_t)i * nc + n] = (sacc + ((i == n) ? 1.0 : 0.0)) / row[i];
+      if (n < q && i <= n && part == 0) Vi[(size_t)i * nc + n] = (sacc + ((i == n) ? 1.0 : 0.0)) * rdiag[i];
       __syncwarp();
     }
   }
@@ -604,15 +631,17 @@ __global__ void __launch_bounds__(1024) chol_factor_kernel(const double *G, int 
   // Frobenius bounds of the whole factor (fr, fi) and of its leading pp x pp block (frp, fip): the
   // inverse of the leading block of a triangular matrix is the leading block of its inverse
   double fr = 0.0, fi = 0.0, frp = 0.0, fip = 0.0;
-  for (int e = tid; e < nc * nc; e += nt) {
-    const int i = e / nc, j = e - i * nc;
-    if (i < q && j < q) {
-      const double di = dsq[i], dj = dsq[j];
-      const double rr = (dj > 0.0) ? A[e] / dj : 0.0;
-      const double v = Vi[e] * di;
+  // (R and R^-1 are upper triangular: warp per row, lanes over the columns j >= i; reciprocal scales from rdsq)
+#pragma unroll 1
+  for (int i = w; i < q; i += 32) {
+    const double di = dsq[i];
+#pragma unroll 1
+    for (int j = i + lane; j < q; j += 32) {
+      const double rr = A[(size_t)i * nc + j] * rdsq[j];
+      const double v = Vi[(size_t)i * nc + j] * di;
       fr = fma(rr, rr, fr);
       fi = fma(v, v, fi);
-      if (i < pp && j < pp) {
+      if (j < pp) {          // i <= j < pp
         frp = fma(rr, rr, frp);
         fip = fma(v, v, fip);
       }
@@ -630,11 +659,14 @@ __global__ void __launch_bounds__(1024) chol_factor_kernel(const double *G, int 
     redp[32 + w] = fip;
   }
   __syncthreads();
+  const long long c3 = clock64();
   // second bound: sqrt(Gershgorin bound on the largest eigenvalue of the equilibrated Gram matrix)
   // * sqrt(|R'^-1|_1 |R'^-1|_inf) with R'^-1 = D R^-1; thread t takes row / column t.  [1]: leading block.
+#pragma unroll 1
   for (int t = w; t < q; t += 32) {          // warp per row / column t, lanes over k
     const double dt = dsq[t];
     double cs = 0.0, rs = 0.0, csp = 0.0, rsp = 0.0;
+#pragma unroll 1
     for (int k = lane; k < q; k += 32) {
       const double ce = fabs(Vi[(size_t)k * nc + t]) * dsq[k];     // column t of D R^-1
       const double re = fabs(Vi[(size_t)t * nc + k]) * dt;         // row t
@@ -657,52 +689,68 @@ __global__ void __launch_bounds__(1024) chol_factor_kernel(const double *G, int 
     }
   }
   __syncthreads();
-  if (tid == 0) {
-    double bound[2];
+  const long long c4 = clock64();
+  // the final combination is done by warp 0 with its lanes over the rows / warps (a single thread walking
+  // these ~600 shared-memory values and ~100 FP64 divisions was half of this kernel's time)
+  double bound0 = 0.0, bound1 = 0.0, dlo = 1e300, dhi = 0.0;
+  if (w == 0) {
+#pragma unroll 1
     for (int blk = 0; blk < 2; ++blk) {
       const int n = blk == 0 ? q : pp;
       const double *rd = blk == 0 ? red : redp;
-      double a = 0.0, b = 0.0, gm = 0.0, cm = 0.0, rm = 0.0;
-      for (int k = 0; k < nt / 32; ++k) {
-        a += rd[k];
-        b += rd[32 + k];
-      }
-      for (int t = 0; t < n; ++t) {
+      double a = (lane < nt / 32) ? rd[lane] : 0.0, b = (lane < nt / 32) ? rd[32 + lane] : 0.0;
+      a = warp_sum(a);
+      b = warp_sum(b);
+      double gm = 0.0, cm = 0.0, rm = 0.0;
+#pragma unroll 1
+      for (int t = lane; t < n; t += 32) {
         gm = fmax(gm, b_g[blk][t]);
         cm = fmax(cm, b_c[blk][t]);
         rm = fmax(rm, b_r[blk][t]);
       }
+      gm = warp_max(gm);
+      cm = warp_max(cm);
+      rm = warp_max(rm);
       double frob = sqrt(a) * sqrt(b), sharp = sqrt(gm) * sqrt(cm * rm);
       if (!(frob == frob)) frob = INFINITY;
       if (!(sharp == sharp)) sharp = INFINITY;
-      bound[blk] = fmin(frob, sharp);
+      if (blk == 0) bound0 = fmin(frob, sharp);
+      else bound1 = fmin(frob, sharp);
     }
-    double dmin = 1e300, dmax = 0.0;
-    for (int k = 0; k < pp; ++k) {
+    double dneg = -1e300;
+#pragma unroll 1
+    for (int k = lane; k < pp; k += 32) {
       const double d = (dsq[k] > 0.0) ? fabs(A[(size_t)k * nc + k]) / dsq[k] : 0.0;
-      dmin = fmin(dmin, d);
-      dmax = fmax(dmax, d);
+      dneg = fmax(dneg, -d);
+      dhi = fmax(dhi, d);
     }
+    dlo = -warp_max(dneg);
+    dhi = warp_max(dhi);
+  }
+  if (tid == 0) {
     info[0] = s_fail;
-    info[1] = bound[0];
+    info[1] = bound0;
     if (gram_out != nullptr) {
       // the record lsspa_lifts_gram leaves behind its Gram matrix: [0] condition bound of the equilibrated
       // train factor (leading block), [1] min / max of its diagonal
       double *ginfo = gram_out + (size_t)q * q;
-      ginfo[0] = (s_fail != 0.0) ? INFINITY : bound[1];
-      ginfo[1] = (dmax > 0.0) ? dmin / dmax : 0.0;
-      ginfo[2] = bound[1];
-      ginfo[3] = bound[1];
+      ginfo[0] = (s_fail != 0.0) ? INFINITY : bound1;
+      ginfo[1] = (dhi > 0.0) ? dlo / dhi : 0.0;
+      ginfo[2] = bound1;
+      ginfo[3] = bound1;
       // phase cycles of this (single-CTA) kernel, for tools/prof_gram.py: factorisation, inverse, bounds
       ginfo[4] = (double)(c1 - c0);
       ginfo[5] = (double)(c2 - c1);
       ginfo[6] = (double)(clock64() - c2);
+      ginfo[7] = (double)(c3 - c2) + 1e-9 * (double)(c4 - c3);
     }
   }
+#pragma unroll 1
   for (int e = tid; e < q * q; e += nt) {
     const int i = e / q, j = e - i * q;
     R_out[e] = A[(size_t)i * nc + j];
   }
+#pragma unroll 1
   for (int e = tid; e < nc * ldr; e += nt) {
     const int i = e / ldr, j = e - i * ldr;
     Rinv_out[e] = (j < nc) ? Vi[(size_t)i * nc + j] : 0.0;
