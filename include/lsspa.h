@@ -258,6 +258,17 @@ LSSPA_API int lsspa_estimator_absorb(void *state, int p, int cur, double n_befor
                            void *stream);
 LSSPA_API int lsspa_estimator_quantiles(int p, double *zsq, int nown, double *overall_out,
                               double *feat_out, void *stream);
+/* absorb + quantiles in the form the sample loop consumes (ls_spa/ls_spa.py:222-230 keeps the overall error of
+ * every batch for the stop test / error_history, but the per-feature errors only of the batch it ends on):
+ * the same fold as lsspa_estimator_absorb, overall_out[own1-own0] = the overall error after every owned
+ * batch, feat_out[p] = the per-feature errors after batch feat_batch (own0 <= feat_batch < own1; -1: none).
+ * The squared draws never leave the kernel: per owned batch only [groups of 4 features][1024] partial norms
+ * are written.  workspace: lsspa_estimator_errors_workspace_doubles(p, own1 - own0) doubles. */
+LSSPA_API int64_t lsspa_estimator_errors_workspace_doubles(int p, int nown);
+LSSPA_API int lsspa_estimator_absorb_errors(void *state, int p, int cur, double n_before, const double *partials,
+                                            const int32_t *slot_map, int nb, int own0, int own1, int feat_batch,
+                                            double *overall_out, double *feat_out, double *workspace,
+                                            void *stream);
 /* multi-GPU: one partial block equal to the merge of nb consecutive partial blocks (the run total a rank
  * ships to the others), as parallel sums -- merge_sample_mean/cov are associative (test/test_ls_spa.py:20-44) */
 LSSPA_API int lsspa_estimator_block_total(int p, const double *partials, int nb, int with_draws, double *out_block,

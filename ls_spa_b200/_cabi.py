@@ -68,6 +68,8 @@ SIGNATURES = {
     "lsspa_estimator_absorb": (c_i32, [vp, c_i32, c_i32, c_f64, vp, vp, c_i32, c_i32, c_i32, vp, c_i32, vp]),
     "lsspa_estimator_block_total": (c_i32, [c_i32, vp, c_i32, c_i32, vp, vp]),
     "lsspa_estimator_quantiles": (c_i32, [c_i32, vp, c_i32, vp, vp, vp]),
+    "lsspa_estimator_errors_workspace_doubles": (c_i64, [c_i32, c_i32]),
+    "lsspa_estimator_absorb_errors": (c_i32, [vp, c_i32, c_i32, c_f64, vp, vp, c_i32, c_i32, c_i32, c_i32, vp, vp, vp, vp]),
     "lsspa_error_draws": (c_i32, [c_i32, vp, c_u64, vp, vp, vp]),
     "lsspa_prefix_means": (c_i32, [c_i32, vp, c_i64, vp, c_f64, vp, vp]),
     "lsspa_merge_moments": (c_i32, [c_i32, vp, vp, c_f64, vp, vp, c_f64, vp]),

@@ -380,6 +380,45 @@ __device__ __forceinline__ unsigned long long kth_largest_key(const unsigned lon
   return K;
 }
 
+// np.quantile(sqrt(v), 0.95) of the 1024 non-negative values a warp holds (32 per lane; valid on lane 0).
+// A NaN value (an estimate after a single sample: 0 / sqrt(n (n-1)), the reference returns nan there too)
+// makes the whole quantile NaN, so that it can never pass the `< tolerance` stop test.
+__device__ __forceinline__ double quantile95_sqrt(const double (&v)[kPerLane], int lane) {
+  bool nan_row = false;
+#pragma unroll
+  for (int i = 0; i < kPerLane; ++i) nan_row |= !(v[i] == v[i]);
+  nan_row = __any_sync(kFull, nan_row);
+  unsigned long long key[kPerLane];
+#pragma unroll
+  for (int i = 0; i < kPerLane; ++i) key[i] = (unsigned long long)__double_as_longlong(v[i] > 0.0 ? v[i] : 0.0);
+  // linear interpolation (reference :340-341) between the ascending ranks lo and lo + 1, i.e. the
+  // (kDraws - lo)-th and (kDraws - lo - 1)-th largest
+  const double pos = (double)(kDraws - 1) * 0.95;
+  const int lo = (int)floor(pos);
+  const unsigned long long klo = kth_largest_key(key, kDraws - lo);
+  // the next rank up is klo again when ties leave fewer than kDraws - lo - 1 keys above it,
+  // otherwise the smallest key above klo
+  int n_gt = 0;
+  unsigned long long above = ~0ULL;
+#pragma unroll
+  for (int i = 0; i < kPerLane; ++i) {
+    if (key[i] > klo) {
+      ++n_gt;
+      above = key[i] < above ? key[i] : above;
+    }
+  }
+  n_gt = __reduce_add_sync(kFull, n_gt);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(kFull, above, o);
+    above = other < above ? other : above;
+  }
+  const unsigned long long khi = (n_gt >= kDraws - lo - 1) ? above : klo;
+  const double t = pos - (double)lo;
+  const double a = sqrt(__longlong_as_double((long long)klo)), c = sqrt(__longlong_as_double((long long)khi));
+  return nan_row ? __longlong_as_double(0x7ff8000000000000LL) : c - (c - a) * (1.0 - t);
+}
+
 // Fold `nb` consecutive batches (partial blocks partials[slot_map[b]]) into the state, in order.
 // grid = p CTAs of 1024 threads; CTA f owns covariance row f and draw-sum column f.  For the
 // batches b in [own0, own1) the squared error draws z_sf^2 (covariance unbiased_cov / n after
@@ -520,44 +559,160 @@ __global__ void __launch_bounds__(256) est_quantile_kernel(int p, int nown, cons
   double v[kPerLane];
 #pragma unroll
   for (int i = 0; i < kPerLane; ++i) v[i] = zb[32 * i + lane];
-  // a NaN draw (an estimate after a single sample: 0 / sqrt(n (n-1)), the reference returns nan there
-  // too) makes the whole quantile NaN, so that it can never pass the `< tolerance` stop test
-  bool nan_row = false;
-#pragma unroll
-  for (int i = 0; i < kPerLane; ++i) nan_row |= !(v[i] == v[i]);
-  nan_row = __any_sync(kFull, nan_row);
-  unsigned long long key[kPerLane];
-#pragma unroll
-  for (int i = 0; i < kPerLane; ++i) key[i] = (unsigned long long)__double_as_longlong(v[i] > 0.0 ? v[i] : 0.0);
-  // np.quantile(., 0.95) of the square roots (reference :340-341): linear interpolation between
-  // the ascending ranks lo and lo + 1, i.e. the (kDraws - lo)-th and (kDraws - lo - 1)-th largest
-  const double pos = (double)(kDraws - 1) * 0.95;
-  const int lo = (int)floor(pos);
-  const unsigned long long klo = kth_largest_key(key, kDraws - lo);
-  // the next rank up is klo again when ties leave fewer than kDraws - lo - 1 keys above it,
-  // otherwise the smallest key above klo
-  int n_gt = 0;
-  unsigned long long above = ~0ULL;
-#pragma unroll
-  for (int i = 0; i < kPerLane; ++i) {
-    if (key[i] > klo) {
-      ++n_gt;
-      above = key[i] < above ? key[i] : above;
-    }
-  }
-  n_gt = __reduce_add_sync(kFull, n_gt);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const unsigned long long other = __shfl_xor_sync(kFull, above, o);
-    above = other < above ? other : above;
-  }
+  const double q = quantile95_sqrt(v, lane);
   if (lane == 0) {
-    const unsigned long long khi = (n_gt >= kDraws - lo - 1) ? above : klo;
-    const double t = pos - (double)lo;
-    const double a = sqrt(__longlong_as_double((long long)klo)), c = sqrt(__longlong_as_double((long long)khi));
-    const double q = nan_row ? __longlong_as_double(0x7ff8000000000000LL) : c - (c - a) * (1.0 - t);
     if (f < p) feat_out[(size_t)b * p + f] = q;
     else overall_out[b] = q;
+  }
+}
+
+// ---------------------------------------------------------------- draw sums + error norms in one pass
+// The draw-sum half of est_absorb_kernel for callers that only need what the sample loop consumes: the
+// OVERALL error after every owned batch and the per-feature errors after ONE batch (the last one, or the
+// batch the job stops at).  CTA = (group of kErrFG features, 256 draws); a thread folds its draw for the
+// group's features (independent chains) and adds their squared z to the group's share of |z_s|^2, so the
+// 100 MB of squared draws per super-batch that est_absorb_kernel writes (and est_rowsum / est_quantile
+// read back) shrink to [owned batch][group][draw] partial norms.  Same recurrences, same order in b.
+constexpr int kErrFG = 4;
+
+__global__ void __launch_bounds__(256) est_draws_kernel(double *__restrict__ state, int p, int cur, double n_before,
+                                                         const double *__restrict__ partials, size_t pstride,
+                                                         const int *__restrict__ slot_map, int nb, int own0, int own1,
+                                                         int feat_batch, double *__restrict__ pnorm,
+                                                         double *__restrict__ zlast) {
+  extern __shared__ double smem[];
+  double *nrun = smem;                       // nb + 1 running counts
+  double *n2s = nrun + (nb + 1);             // nb batch counts
+  double *fz = n2s + nb;                     // 1 / sqrt(nn (nn - 1))
+  double *fa = fz + nb;                      // n1 / nn
+  double *fb = fa + nb;                      // n2 / nn
+  double *pm = fb + nb;                      // nb x FG batch means of the group's features
+  double *d1 = pm + (size_t)nb * kErrFG;     // nb x FG  m_old - m_new
+  double *d2 = d1 + (size_t)nb * kErrFG;     // nb x FG  batch mean - m_new
+  int *slots = reinterpret_cast<int *>(d2 + (size_t)nb * kErrFG);
+  StateView st = view_state(state, p);
+  const int nxt = cur ^ 1;
+  const int tid = threadIdx.x;
+  const int grp = blockIdx.x, ngrp = gridDim.x;
+  const int f0 = grp * kErrFG;
+  const int s = blockIdx.y * 256 + tid;
+  for (int b = tid; b < nb; b += 256) {
+    const int sl = slot_map[b];
+    slots[b] = sl;
+    n2s[b] = partials[(size_t)sl * pstride];
+  }
+  __syncthreads();
+  for (int e = tid; e < nb * kErrFG; e += 256) {
+    const int b = e / kErrFG, k = e - b * kErrFG;
+    pm[e] = (f0 + k < p) ? partials[(size_t)slots[b] * pstride + kPartHdr + f0 + k] : 0.0;
+  }
+  if (tid == 0) {
+    double n = n_before;
+    nrun[0] = n;
+    for (int b = 0; b < nb; ++b) {
+      n += n2s[b];
+      nrun[b + 1] = n;
+    }
+  }
+  __syncthreads();
+  for (int b = tid; b < nb; b += 256) {
+    const double nn = nrun[b + 1];
+    fz[b] = 1.0 / sqrt(nn * (nn - 1.0));
+    fa[b] = nrun[b] / nn;
+    fb[b] = n2s[b] / nn;
+  }
+  __syncthreads();
+  if (tid < kErrFG) {
+    // running mean of one feature: the recurrence of est_absorb_kernel (m = n1/nn m + n2/nn pm)
+    const int k = tid;
+    double m = (f0 + k < p) ? st.mean[cur][f0 + k] : 0.0;
+    for (int b = 0; b < nb; ++b) {
+      double mn = m;
+      if (n2s[b] > 0.0) mn = fa[b] * m + fb[b] * pm[b * kErrFG + k];
+      d1[b * kErrFG + k] = m - mn;
+      d2[b * kErrFG + k] = pm[b * kErrFG + k] - mn;
+      m = mn;
+    }
+  }
+  __syncthreads();
+  double sk[kErrFG];
+#pragma unroll
+  for (int k = 0; k < kErrFG; ++k) sk[k] = (f0 + k < p) ? st.S[(size_t)(f0 + k) * kDraws + s] : 0.0;
+  double gr = st.G[cur][s];
+  const size_t offG = kPartHdr + (size_t)p + (size_t)p * p;
+  constexpr int UB = 8;       // batches whose loads are in flight together
+  for (int b0 = 0; b0 < nb; b0 += UB) {
+    double g2[UB], ps[UB][kErrFG];
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const int b = (b0 + u < nb) ? b0 + u : nb - 1;
+      const double *blk = partials + (size_t)slots[b] * pstride + offG;
+      g2[u] = blk[s];
+#pragma unroll
+      for (int k = 0; k < kErrFG; ++k)
+        ps[u][k] = blk[kDraws + (size_t)((f0 + k < p) ? f0 + k : p - 1) * kDraws + s];
+    }
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const int b = b0 + u;
+      if (b < nb) {
+        if (n2s[b] > 0.0) {
+#pragma unroll
+          for (int k = 0; k < kErrFG; ++k) sk[k] += d1[b * kErrFG + k] * gr + ps[u][k] + d2[b * kErrFG + k] * g2[u];
+          gr += g2[u];
+        }
+        if (b >= own0 && b < own1) {
+          const double w = fz[b];       // n = 1: 0 * inf = NaN, as the reference's 0 / 0
+          double acc = 0.0;
+#pragma unroll
+          for (int k = 0; k < kErrFG; ++k) {
+            const double z = sk[k] * w;
+            if (f0 + k < p) {
+              acc += z * z;
+              if (b == feat_batch) zlast[(size_t)(f0 + k) * kDraws + s] = z * z;
+            }
+          }
+          pnorm[((size_t)(b - own0) * ngrp + grp) * kDraws + s] = acc;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kErrFG; ++k)
+    if (f0 + k < p) st.S[(size_t)(f0 + k) * kDraws + s] = sk[k];
+  if (grp == 0) st.G[nxt][s] = gr;
+}
+
+// |z_s|^2 of every owned batch: the group partial norms of est_draws_kernel added in a fixed order
+__global__ void est_normsum_kernel(int nown, int ngrp, const double *__restrict__ pnorm, double *__restrict__ norm2) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (size_t)nown * kDraws) return;
+  const size_t b = e / kDraws, sd = e - b * kDraws;
+  const double *pb = pnorm + b * ngrp * kDraws + sd;
+  double acc = 0.0;
+#pragma unroll 8
+  for (int g = 0; g < ngrp; ++g) acc += pb[(size_t)g * kDraws];
+  norm2[e] = acc;
+}
+
+// Quantiles for est_draws_kernel: warp per row; rows [0, nown) = overall error of an owned batch (from
+// est_normsum_kernel), rows [nown, nown + p) = features of the one batch whose squared draws were kept
+// (only when feat_out != nullptr).
+__global__ void __launch_bounds__(256) est_quantile_fused_kernel(int p, int nown, const double *norm2,
+                                                                  const double *zlast, double *overall_out,
+                                                                  double *feat_out) {
+  const int lane = threadIdx.x & 31;
+  const int rowid = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int rows = nown + (feat_out != nullptr ? p : 0);
+  if (rowid >= rows) return;
+  const double *zb = rowid < nown ? norm2 + (size_t)rowid * kDraws : zlast + (size_t)(rowid - nown) * kDraws;
+  double v[kPerLane];
+#pragma unroll
+  for (int i = 0; i < kPerLane; ++i) v[i] = zb[32 * i + lane];
+  const double q = quantile95_sqrt(v, lane);
+  if (lane == 0) {
+    if (rowid < nown) overall_out[rowid] = q;
+    else feat_out[rowid - nown] = q;
   }
 }
 
@@ -567,19 +722,25 @@ __global__ void __launch_bounds__(256) est_quantile_kernel(int p, int nown, cons
 //   M2 = sum_b M2_b + n_b d_b d_b^T,   G = sum_b G_b,   S = sum_b S_b + d_b G_b^T.
 // A rank ships this block instead of folding its batches twice; the sequential fold (est_absorb_kernel)
 // and this sum agree to rounding.
-__global__ void block_total_mean_kernel(int p, const double *partials, size_t pstride, int nb, double *out) {
+// (slot_map: block b is partials[slot_map[b]], nullptr = consecutive blocks)
+__global__ void block_total_mean_kernel(int p, const double *partials, size_t pstride, int nb, const int *slot_map,
+                                        double *out) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   double n = 0.0;
-  for (int b = 0; b < nb; ++b) n += partials[(size_t)b * pstride];
+  for (int b = 0; b < nb; ++b) n += partials[(size_t)(slot_map ? slot_map[b] : b) * pstride];
   if (f < kPartHdr) out[f] = (f == 0) ? n : 0.0;
   if (f >= p) return;
   double s = 0.0;
-  for (int b = 0; b < nb; ++b) s = fma(partials[(size_t)b * pstride], partials[(size_t)b * pstride + kPartHdr + f], s);
+#pragma unroll 8
+  for (int b = 0; b < nb; ++b) {
+    const double *blk = partials + (size_t)(slot_map ? slot_map[b] : b) * pstride;
+    s = fma(blk[0], blk[kPartHdr + f], s);
+  }
   out[kPartHdr + f] = n > 0.0 ? s / n : 0.0;
 }
 
 __global__ void __launch_bounds__(256) block_total_kernel(int p, const double *partials, size_t pstride, int nb,
-                                                          int with_draws, double *out) {
+                                                          const int *slot_map, int with_draws, double *out) {
   const size_t nm2 = (size_t)p * p, ng = kDraws, ns = (size_t)p * kDraws;
   const size_t total = nm2 + (with_draws ? ng + ns : 0);
   const double *mean = out + kPartHdr;
@@ -588,26 +749,98 @@ __global__ void __launch_bounds__(256) block_total_kernel(int p, const double *p
     if (e < nm2) {
       const int f = (int)(e / p), j = (int)(e - (size_t)f * p);
       const double mf = mean[f], mj = mean[j];
+#pragma unroll 8
       for (int b = 0; b < nb; ++b) {
-        const double *blk = partials + (size_t)b * pstride;
+        const double *blk = partials + (size_t)(slot_map ? slot_map[b] : b) * pstride;
         const double nb_ = blk[0];
-        if (nb_ > 0.0) acc += blk[kPartHdr + p + e] + nb_ * (blk[kPartHdr + f] - mf) * (blk[kPartHdr + j] - mj);
+        const double m2 = blk[kPartHdr + p + e], bf = blk[kPartHdr + f], bj = blk[kPartHdr + j];   // (loads first:
+        if (nb_ > 0.0) acc += m2 + nb_ * (bf - mf) * (bj - mj);                                   //  they pipeline)
       }
     } else if (e < nm2 + ng) {
+#pragma unroll 8
       for (int b = 0; b < nb; ++b) {
-        const double *blk = partials + (size_t)b * pstride;
-        if (blk[0] > 0.0) acc += blk[kPartHdr + p + e];
+        const double *blk = partials + (size_t)(slot_map ? slot_map[b] : b) * pstride;
+        const double n_b = blk[0], g = blk[kPartHdr + p + e];
+        if (n_b > 0.0) acc += g;
       }
     } else {
       const size_t r = e - nm2 - ng;
       const int f = (int)(r / kDraws), sd = (int)(r - (size_t)f * kDraws);
       const double mf = mean[f];
+#pragma unroll 8
       for (int b = 0; b < nb; ++b) {
-        const double *blk = partials + (size_t)b * pstride;
-        if (blk[0] > 0.0) acc += blk[kPartHdr + p + e] + (blk[kPartHdr + f] - mf) * blk[kPartHdr + p + nm2 + sd];
+        const double *blk = partials + (size_t)(slot_map ? slot_map[b] : b) * pstride;
+        const double n_b = blk[0], sv = blk[kPartHdr + p + e], bf = blk[kPartHdr + f], g = blk[kPartHdr + p + nm2 + sd];
+        if (n_b > 0.0) acc += sv + (bf - mf) * g;
       }
     }
     out[kPartHdr + p + e] = acc;
+  }
+}
+
+// Run total of the moments for lsspa_estimator_absorb_errors: the same sums as block_total_mean_kernel /
+// block_total_kernel (M2 part), with the batches ALSO spread over threads -- thread (element, chunk c) adds the
+// batches c, c + 8, ... (their loads are independent and in flight together), the eight chunk sums are added
+// in a fixed order.  run_mean: one CTA of 128 features x 8 chunks; run_m2: CTA = 32 elements x 8 chunks.
+__global__ void __launch_bounds__(1024) run_mean_kernel(int p, const double *__restrict__ partials, size_t pstride, int nb,
+                                                         const int *__restrict__ slot_map, double *__restrict__ out) {
+  __shared__ double part[8][128];
+  __shared__ double s_n;
+  const int fl = threadIdx.x & 127, ch = threadIdx.x >> 7;
+  const int f = blockIdx.x * 128 + fl;
+  double cnt = 0.0, acc = 0.0;
+  for (int b = ch; b < nb; b += 8) {
+    const double *blk = partials + (size_t)slot_map[b] * pstride;
+    const double n_b = blk[0], m = blk[kPartHdr + (f < p ? f : 0)];
+    cnt += n_b;
+    if (n_b > 0.0) acc = fma(n_b, m, acc);
+  }
+  part[ch][fl] = acc;
+  __syncthreads();
+  // total count: every chunk row saw all its batches; add the eight chunk counts through shared memory
+  __shared__ double cpart[8];
+  if (fl == 0) cpart[ch] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double n = 0.0;
+    for (int c = 0; c < 8; ++c) n += cpart[c];
+    s_n = n;
+  }
+  __syncthreads();
+  const double n = s_n;
+  if (blockIdx.x == 0 && threadIdx.x < kPartHdr) out[threadIdx.x] = (threadIdx.x == 0) ? n : 0.0;
+  if (ch == 0 && f < p) {
+    double t = 0.0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) t += part[c][fl];
+    out[kPartHdr + f] = n > 0.0 ? t / n : 0.0;
+  }
+}
+
+__global__ void __launch_bounds__(256) run_m2_kernel(int p, const double *__restrict__ partials, size_t pstride, int nb,
+                                                      const int *__restrict__ slot_map, double *__restrict__ out) {
+  __shared__ double part[8][32];
+  const int el = threadIdx.x & 31, ch = threadIdx.x >> 5;
+  const size_t nm2 = (size_t)p * p;
+  const size_t e = (size_t)blockIdx.x * 32 + el;
+  const size_t ec = e < nm2 ? e : nm2 - 1;
+  const int f = (int)(ec / p), j = (int)(ec - (size_t)f * p);
+  const double *mean = out + kPartHdr;
+  const double mf = mean[f], mj = mean[j];
+  double acc = 0.0;
+#pragma unroll 4
+  for (int b = ch; b < nb; b += 8) {
+    const double *blk = partials + (size_t)slot_map[b] * pstride;
+    const double n_b = blk[0], m2 = blk[kPartHdr + p + ec], bf = blk[kPartHdr + f], bj = blk[kPartHdr + j];
+    if (n_b > 0.0) acc += m2 + n_b * (bf - mf) * (bj - mj);
+  }
+  part[ch][el] = acc;
+  __syncthreads();
+  if (ch == 0 && e < nm2) {
+    double t = 0.0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) t += part[c][el];
+    out[kPartHdr + p + e] = t;
   }
 }
 
@@ -955,6 +1188,68 @@ extern "C" int lsspa_estimator_quantiles(int p, double *zsq, int nown, double *o
   return LSSPA_OK;
 }
 
+extern "C" int64_t lsspa_estimator_errors_workspace_doubles(int p, int nown) {
+  if (p < 1 || nown < 0) return 0;
+  const int ngrp = (p + kErrFG - 1) / kErrFG;
+  // group partial norms, |z|^2 per owned batch, squared draws of one batch, the run total block, one slot index
+  return ((int64_t)nown * ngrp + nown + p) * kDraws + (int64_t)partial_doubles(p) + 2;
+}
+
+extern "C" int lsspa_estimator_absorb_errors(void *state, int p, int cur, double n_before, const double *partials,
+                                             const int32_t *slot_map, int nb, int own0, int own1, int feat_batch,
+                                             double *overall_out, double *feat_out, double *workspace,
+                                             void *stream) {
+  if (!state || !partials || !slot_map || p < 1 || nb < 0 || (cur != 0 && cur != 1)) return LSSPA_E_BADARG;
+  if (own0 < 0 || own1 > nb || own1 < own0 || !workspace) return LSSPA_E_BADARG;
+  const int nown = own1 - own0;
+  if (nown > 0 && !overall_out) return LSSPA_E_BADARG;
+  if (feat_batch >= 0 && (feat_batch < own0 || feat_batch >= own1 || !feat_out)) return LSSPA_E_BADARG;
+  if (nb == 0) return LSSPA_OK;
+  if (nb > lsspa_estimator_max_batches(p)) return LSSPA_E_UNSUPPORTED;
+  cudaStream_t st = as_stream(stream);
+  const size_t pstride = partial_doubles(p);
+  const int ngrp = (p + kErrFG - 1) / kErrFG;
+  double *pnorm = workspace;
+  double *norm2 = pnorm + (size_t)nown * ngrp * kDraws;
+  double *zlast = norm2 + (size_t)nown * kDraws;
+  double *total = zlast + (size_t)p * kDraws;
+  int *slot0 = reinterpret_cast<int *>(total + pstride);
+  // draw sums, error norms (reads the live mean; writes S, the other G copy and the norms)
+  {
+    const size_t smem = ((size_t)(nb + 1) + 4 * (size_t)nb + 3 * (size_t)nb * kErrFG) * sizeof(double) +
+                        (size_t)nb * sizeof(int) + 16;
+    LSSPA_CUDA_TRY(cudaFuncSetAttribute(est_draws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    est_draws_kernel<<<dim3((unsigned)ngrp, kDraws / 256), 256, smem, st>>>(
+        reinterpret_cast<double *>(state), p, cur, n_before, partials, pstride, slot_map, nb, own0, own1, feat_batch,
+        pnorm, zlast);
+    LSSPA_LAUNCH_CHECK();
+  }
+  // mean and covariance: the moments of the whole run as PARALLEL sums (merge_sample_mean / merge_sample_cov
+  // are associative, reference test/test_ls_spa.py:20-44), then one Chan merge into the state -- instead of a
+  // fold whose nb dependent steps each wait for a load
+  {
+    run_mean_kernel<<<(p + 127) / 128, 1024, 0, st>>>(p, partials, pstride, nb, slot_map, total);
+    LSSPA_LAUNCH_CHECK();
+    run_m2_kernel<<<(unsigned)ceil_div((int64_t)p * p, 32), 256, 0, st>>>(p, partials, pstride, nb, slot_map, total);
+    LSSPA_LAUNCH_CHECK();
+    LSSPA_CUDA_TRY(cudaMemsetAsync(slot0, 0, 2 * sizeof(int), st));
+    const size_t smem = ((size_t)2 * p + 2 + 7 + 16) * sizeof(double);
+    LSSPA_CUDA_TRY(cudaFuncSetAttribute(est_absorb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    est_absorb_kernel<<<p, 128, smem, st>>>(reinterpret_cast<double *>(state), p, cur, n_before, total, pstride, slot0,
+                                            1, 0, 0, nullptr, 0);
+    LSSPA_LAUNCH_CHECK();
+  }
+  if (nown > 0) {
+    est_normsum_kernel<<<(unsigned)ceil_div((int64_t)nown * kDraws, 256), 256, 0, st>>>(nown, ngrp, pnorm, norm2);
+    LSSPA_LAUNCH_CHECK();
+    const int rows = nown + (feat_batch >= 0 ? p : 0);
+    est_quantile_fused_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, st>>>(p, nown, norm2, zlast, overall_out,
+                                                                        feat_batch >= 0 ? feat_out : nullptr);
+    LSSPA_LAUNCH_CHECK();
+  }
+  return LSSPA_OK;
+}
+
 extern "C" int lsspa_estimator_block_total(int p, const double *partials, int nb, int with_draws, double *out_block,
                                            void *stream) {
   if (p < 1 || !partials || !out_block || nb < 0) return LSSPA_E_BADARG;
@@ -963,9 +1258,9 @@ extern "C" int lsspa_estimator_block_total(int p, const double *partials, int nb
   if (nb == 0 || !with_draws) LSSPA_CUDA_TRY(cudaMemsetAsync(out_block, 0, pstride * sizeof(double), st));
   if (nb == 0) return LSSPA_OK;
   const int n1 = p > kPartHdr ? p : kPartHdr;
-  block_total_mean_kernel<<<(n1 + 127) / 128, 128, 0, st>>>(p, partials, pstride, nb, out_block);
+  block_total_mean_kernel<<<(n1 + 127) / 128, 128, 0, st>>>(p, partials, pstride, nb, nullptr, out_block);
   LSSPA_LAUNCH_CHECK();
-  block_total_kernel<<<592, 256, 0, st>>>(p, partials, pstride, nb, with_draws, out_block);
+  block_total_kernel<<<592, 256, 0, st>>>(p, partials, pstride, nb, nullptr, with_draws, out_block);
   LSSPA_LAUNCH_CHECK();
   return LSSPA_OK;
 }

@@ -651,9 +651,15 @@ def run_samples(backend, coll: Collective, prob, source: PermutationSource, cfg:
                             slots = [r * per + i for r, (a, b) in enumerate(runs) for i in range(b - a)]
                         else:
                             gathered, slots = part, list(range(nb))
-                        est.absorb(gathered, slots[:keep], counts[:keep], emit=False)
+                        # (the per-feature errors are only computed for the last batch of a fold: the
+                        # replay, which ends on the stop batch, supplies them)
+                        _, feat_r = est.absorb(gathered, slots[:keep], counts[:keep], own=(keep - 1, keep), emit=True)
+                        feat_last = feat_r[-1]
+                    else:
+                        feat_last = feat[keep - 1]
+                else:
+                    feat_last = feat[nb - 1]
                 err_hist.extend(errs[:keep].tolist())
-                feat_last = feat[keep - 1]
             else:
                 err_parts.append(overall)
                 feat_last = feat[nb - 1]

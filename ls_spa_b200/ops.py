@@ -626,10 +626,15 @@ class Estimator:
         self.state.copy_(snap[0])
         self.cur, self.count = snap[1], snap[2]
 
-    def absorb(self, partials: torch.Tensor, slots, counts, own=(0, 0), emit: bool = False):
+    def absorb(self, partials: torch.Tensor, slots, counts, own=(0, 0), emit: bool = False,
+               every_feature: bool = False):
         """Fold the batches whose partial blocks are partials[slots[b]] (counts[b] samples each), in
         order.  With emit=True returns (overall[own1-own0], per_feature[own1-own0, p]) device tensors
-        holding the 0.95-quantile error estimates after each batch b in [own0, own1)."""
+        holding the 0.95-quantile error estimates after each batch b in [own0, own1).  The sample loop
+        only ever reads the per-feature errors of the LAST owned batch (the reference keeps
+        attribution_errors of the batch it ends on, ls_spa/ls_spa.py:222-236), so by default only that
+        row of per_feature is computed (the others are NaN) and the squared draws stay inside the fused
+        kernel; every_feature=True takes the two-kernel route that fills every row."""
         lib = _lib()
         nb = len(slots)
         own0, own1 = own
@@ -637,26 +642,38 @@ class Estimator:
         overall = feat = None
         if emit:
             overall = torch.empty(own1 - own0, dtype=torch.float64, device=self.device)
-            feat = torch.empty((own1 - own0, self.p), dtype=torch.float64, device=self.device)
+            feat = torch.full((own1 - own0, self.p), float("nan"), dtype=torch.float64, device=self.device)
         pos = 0
         flat = partials.reshape(-1, self.partial_doubles)
         while pos < nb:
             n = min(self.max_batches, nb - pos)
             smap = torch.tensor(slots[pos:pos + n], dtype=torch.int32).to(self.device, non_blocking=True)
             o0, o1 = max(own0, pos) - pos, min(own1, pos + n) - pos
-            zsq = None
-            if emit and o1 > o0:
-                zsq = torch.empty((o1 - o0, self.p + 1, ERR_DRAWS), dtype=torch.float64, device=self.device)
-            check(lib.lsspa_estimator_absorb(self.state.data_ptr(), self.p, self.cur, float(self.count),
-                                             flat.data_ptr(), smap.data_ptr(), n, max(o0, 0), max(o1, 0),
-                                             _ptr(zsq), 1 if self.estimate else 0, _stream()),
-                  "lsspa_estimator_absorb")
-            _count(1)
-            if zsq is not None:
+            if emit and o1 > o0 and not every_feature:
                 lo = pos + o0 - own0
-                check(lib.lsspa_estimator_quantiles(self.p, zsq.data_ptr(), o1 - o0, overall[lo:].data_ptr(),
-                                                    feat[lo:].data_ptr(), _stream()), "lsspa_estimator_quantiles")
-                _count(2)
+                fb = o1 - 1 if pos + o1 == own1 else -1           # the chunk that holds the last owned batch
+                ws = torch.empty(int(lib.lsspa_estimator_errors_workspace_doubles(self.p, o1 - o0)),
+                                 dtype=torch.float64, device=self.device)
+                check(lib.lsspa_estimator_absorb_errors(self.state.data_ptr(), self.p, self.cur, float(self.count),
+                                                        flat.data_ptr(), smap.data_ptr(), n, o0, o1, fb,
+                                                        overall[lo:].data_ptr(),
+                                                        feat[own1 - own0 - 1:].data_ptr() if fb >= 0 else None,
+                                                        ws.data_ptr(), _stream()), "lsspa_estimator_absorb_errors")
+                _count(6)
+            else:
+                zsq = None
+                if emit and o1 > o0:
+                    zsq = torch.empty((o1 - o0, self.p + 1, ERR_DRAWS), dtype=torch.float64, device=self.device)
+                check(lib.lsspa_estimator_absorb(self.state.data_ptr(), self.p, self.cur, float(self.count),
+                                                 flat.data_ptr(), smap.data_ptr(), n, max(o0, 0), max(o1, 0),
+                                                 _ptr(zsq), 1 if self.estimate else 0, _stream()),
+                      "lsspa_estimator_absorb")
+                _count(1)
+                if zsq is not None:
+                    lo = pos + o0 - own0
+                    check(lib.lsspa_estimator_quantiles(self.p, zsq.data_ptr(), o1 - o0, overall[lo:].data_ptr(),
+                                                        feat[lo:].data_ptr(), _stream()), "lsspa_estimator_quantiles")
+                    _count(2)
             self.cur ^= 1
             self.count += int(sum(counts[pos:pos + n]))
             pos += n

@@ -358,6 +358,43 @@ def test_estimator_state_matches_merge_formulas(T):
     np.testing.assert_allclose(out["overall_error"], want_overall, rtol=0.1)
 
 
+@pytest.mark.parametrize("p", [5, 23, 100, 130])
+def test_fused_error_fold_matches_two_kernel_route(T, p):
+    """lsspa_estimator_absorb_errors (draw fold + norms in one kernel, per-feature errors of the last batch
+    only) against lsspa_estimator_absorb + lsspa_estimator_quantiles (every squared draw written out):
+    same state, same overall errors for every batch, same per-feature errors on the last one --
+    uneven batches, an empty one, a one-sample start (NaN estimate), two folds in a row."""
+    from ls_spa_b200 import ops
+    rng = np.random.default_rng(p)
+    sizes = [1, 40, 0, 17, 64, 3]
+    n = sum(sizes)
+    rows = rng.standard_normal((2 * n, p)) * rng.uniform(0.1, 3.0, p) + rng.standard_normal(p)
+    dev = T.device("cuda")
+    d = T.from_numpy(rows).to(dev)
+    outs = []
+    for every in (True, False):
+        est = ops.Estimator(p, 7, True, dev)
+        res = []
+        for fold in range(2):
+            cuts, at = [], fold * n
+            for sz in sizes:
+                cuts.append((at, sz, at))
+                at += sz
+            part = est.partials(d, cuts)
+            own = (0, len(sizes)) if fold == 0 else (2, 5)
+            overall, feat = est.absorb(part, list(range(len(sizes))), sizes, own=own, emit=True, every_feature=every)
+            res.append((overall.cpu().numpy(), feat[-1].cpu().numpy()))
+        outs.append((res, est.state.cpu().numpy().copy(), est.count))
+    (ra, sa, ca), (rb, sb, cb) = outs
+    assert ca == cb == 2 * n
+    np.testing.assert_allclose(sb, sa, rtol=1e-11, atol=1e-12)
+    for (oa, fa), (ob, fb) in zip(ra, rb):
+        assert oa.shape == ob.shape
+        np.testing.assert_allclose(ob, oa, rtol=1e-10, equal_nan=True)
+        np.testing.assert_allclose(fb, fa, rtol=1e-10, equal_nan=True)
+    assert np.isnan(ra[0][0][0]) and np.isnan(rb[0][0][0])      # one sample: 0/0, never below a tolerance
+
+
 def test_early_stop_matches_history_semantics(T, L):
     """Stops at the first batch whose estimated error is below the tolerance; later batches
     are not folded in (reference `break`, ls_spa/ls_spa.py:229)."""
