@@ -192,31 +192,57 @@ __device__ __forceinline__ void dmma_e(double &d0, double &d1, double a, double 
       : "d"(a), "d"(b));
 }
 
-__host__ __device__ inline int mma_ldx(int ft) { return ((8 * ft) % 16 == 8) ? 8 * ft : 8 * ft + 8; }
+// row pitch of the staged rows: the A / B fragments read element (row 4 ks + q, column 8 t + c), so within
+// a half-warp (c = 0..3, q = 0..3) the bank pairs are distinct iff q * pitch covers 0, 4, 8, 12 (mod 16):
+// pitch = 4 (mod 8).  (A pitch of 8 mod 16 makes q = 0 / 2 and 1 / 3 collide: two-way conflicts on the one
+// shared-memory load per DMMA, which then saturates the LSU before the FP64 pipe.)
+__host__ __device__ inline int mma_ldx(int ft) { return 8 * ft + 4; }
 
 // rows [k0, k0 + rows) of the batch, centered, zero padded to kMmaRows x ldx.  A warp takes whole
-// rows (lane -> features lane, lane + 32, ...): coalesced, no index arithmetic, 4 rows in flight.
-__device__ __forceinline__ void stage_rows(double *Xs, int ldx, const double *lifts, const double *mean, int p,
-                                           int64_t row0, int rows, int tid, int nt) {
+// rows (lane -> features lane, lane + 32, ...): coalesced, no index arithmetic.  The loads of four rows
+// (from clamped, always valid addresses) are issued into registers BEFORE the first shared-memory store:
+// written as load - subtract - store per element, every load waited for its predecessor's store (one
+// L2 round trip per element, 64 in a row per warp -- a third of part_s_mma_kernel's run time).
+__device__ __forceinline__ void stage_rows(double *Xs, int ldx, const double *__restrict__ lifts,
+                                           const double *__restrict__ mean, int p, int64_t row0, int rows, int tid,
+                                           int nt) {
   const int lane = tid & 31, w = tid >> 5, nw = nt >> 5;
   double mu[4];
+  int fc[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) mu[j] = (lane + 32 * j < p) ? mean[lane + 32 * j] : 0.0;
-#pragma unroll 4
-  for (int r = w; r < kMmaRows; r += nw) {
-    const double *src = lifts + (row0 + r) * p;
-    double *dst = Xs + (size_t)r * ldx;
+  for (int j = 0; j < 4; ++j) {
+    const int f = lane + 32 * j;
+    fc[j] = f < p ? f : p - 1;
+    mu[j] = mean[fc[j]];
+  }
+  constexpr int RB = 4;
+  for (int rb = w; rb < kMmaRows; rb += RB * nw) {
+    double v[RB][4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int f = lane + 32 * j;
-      if (f < ldx) dst[f] = (r < rows && f < p) ? src[f] - mu[j] : 0.0;
+    for (int u = 0; u < RB; ++u) {
+      const int r = rb + u * nw;
+      const double *src = lifts + (row0 + (r < rows ? r : rows - 1)) * p;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[u][j] = __ldg(src + fc[j]);
+    }
+#pragma unroll
+    for (int u = 0; u < RB; ++u) {
+      const int r = rb + u * nw;
+      if (r < kMmaRows) {
+        double *dst = Xs + (size_t)r * ldx;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int f = lane + 32 * j;
+          if (f < ldx) dst[f] = (r < rows && f < p) ? v[u][j] - mu[j] : 0.0;
+        }
+      }
     }
   }
 }
 
 // M2: warp g owns tile rows g and FT-1-g of the upper triangle (FT + 1 tiles, balanced)
 template <int MAXFT>
-__global__ void __launch_bounds__(256) part_m2_mma_kernel(int p, const double *lifts, const int64_t *desc,
+__global__ void __launch_bounds__(256, 2) part_m2_mma_kernel(int p, const double *lifts, const int64_t *desc,
                                                           double *partials, size_t pstride) {
   extern __shared__ __align__(16) double Xs[];
   const int b = blockIdx.x;
@@ -279,17 +305,17 @@ __global__ void __launch_bounds__(256) part_m2_mma_kernel(int p, const double *l
   }
 }
 
-// S and G: CTA = (block of kSDraws draws, batch).  A warp task = (half of the feature tiles, pair
-// of draw tiles T0, T1); the Gaussians of a row are generated in the lanes that need them: lane
-// (c, q) of k-step ks owns row 4 ks + q, even c draws the pair (T0*8 + c, T0*8 + c + 1), odd c the
-// pair (T1*8 + c - 1, T1*8 + c), and one shuffle with lane ^ 4 gives every lane column c of both.
+// S and G: CTA = (block of kSDraws draws, batch).  A warp task = (all feature tiles, one tile of 8 draws).
+// The Gaussians are generated in the lanes that need them, one generator call per lane for TWO k-steps:
+// lane (c, q) draws the pair (draws 8 T + (c & ~1), + 1) of row 4 (ks + (c & 1)) + q, and one shuffle with
+// lane ^ 4 gives every lane column c of both k-steps (even c: own g0 now, the partner's g0 next; odd c: the
+// partner's g1 now, own g1 next) -- 2 x FT DMMAs per generator call.
 constexpr int kSDraws = 128;
 
 template <int MAXFT>
-__global__ void __launch_bounds__(256) part_s_mma_kernel(int p, const double *lifts, const int64_t *desc,
+__global__ void __launch_bounds__(256, 2) part_s_mma_kernel(int p, const double *lifts, const int64_t *desc,
                                                          uint64_t seed, double *partials, size_t pstride) {
   extern __shared__ __align__(16) double Xs[];
-  constexpr int FH = (MAXFT + 1) / 2;
   const int b = blockIdx.y, db = blockIdx.x;
   const int64_t r0 = desc[3 * b], cnt = desc[3 * b + 1], gidx0 = desc[3 * b + 2];
   double *base = partials + (size_t)b * pstride;
@@ -297,20 +323,18 @@ __global__ void __launch_bounds__(256) part_s_mma_kernel(int p, const double *li
   double *Gout = base + kPartHdr + p + (size_t)p * p;
   double *Sout = Gout + kDraws;
   const int FT = (p + 7) / 8, ldx = mma_ldx(FT);
-  const int fh0 = (FT + 1) / 2;                     // tiles of the first half
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int c = lane >> 2, q = lane & 3;
   const bool even = (c & 1) == 0;
-  constexpr int kPairs = kSDraws / 16;              // draw-tile pairs per CTA
+  constexpr int kTiles = kSDraws / 8;               // draw tiles per CTA
   const int64_t nchunks = (cnt + kMmaRows - 1) / kMmaRows;
-  for (int task = w; task < 2 * kPairs; task += 8) {
-    const int half = task / kPairs, pairi = task - half * kPairs;
-    const int T0 = db * (kSDraws / 8) + 2 * pairi, T1 = T0 + 1;
-    const int tbeg = half == 0 ? 0 : fh0, tnum = half == 0 ? fh0 : FT - fh0;
-    double acc[FH][2][2];
+  for (int task = w; task < kTiles; task += 8) {
+    const int T = db * kTiles + task;
+    double acc[MAXFT][2];
 #pragma unroll
-    for (int i = 0; i < FH; ++i) acc[i][0][0] = acc[i][0][1] = acc[i][1][0] = acc[i][1][1] = 0.0;
-    double gs0 = 0.0, gs1 = 0.0;
+    for (int i = 0; i < MAXFT; ++i) acc[i][0] = acc[i][1] = 0.0;
+    double gs = 0.0;
+    const uint32_t pr = (uint32_t)((T * 8 + (c & ~1)) >> 1);
     for (int64_t ch = 0; ch < nchunks; ++ch) {
       const int64_t k0 = ch * kMmaRows;
       const int rows = (int)((cnt - k0 < kMmaRows) ? cnt - k0 : kMmaRows);
@@ -320,43 +344,35 @@ __global__ void __launch_bounds__(256) part_s_mma_kernel(int p, const double *li
         __syncthreads();
       }
       const int ksteps = (rows + 3) / 4;
-      const uint32_t pr = even ? (uint32_t)((T0 * 8 + c) >> 1) : (uint32_t)((T1 * 8 + c - 1) >> 1);
-      for (int ks = 0; ks < ksteps; ++ks) {
-        const int r = 4 * ks + q;
+      for (int ks = 0; ks < ksteps; ks += 2) {
+        const int rg = 4 * (ks + (even ? 0 : 1)) + q;
         float g0 = 0.f, g1 = 0.f;
-        if (r < rows) gauss_pair(seed, (uint64_t)(gidx0 + k0 + r), pr, g0, g1);
+        if (rg < rows) gauss_pair(seed, (uint64_t)(gidx0 + k0 + rg), pr, g0, g1);
         const float recv = __shfl_xor_sync(kFull, even ? g1 : g0, 4);
-        const double b0 = (double)(even ? g0 : recv), b1 = (double)(even ? recv : g1);
-        gs0 += b0;
-        gs1 += b1;
-        const double *xrow = Xs + (size_t)r * ldx + 8 * tbeg + c;
+        const double b0 = (double)(even ? g0 : recv);     // k-step ks
+        const double b1 = (double)(even ? recv : g1);     // k-step ks + 1 (rows beyond the batch: zeros)
+        gs += b0 + b1;
+        const double *x0 = Xs + (size_t)(4 * ks + q) * ldx + c;
 #pragma unroll
-        for (int i = 0; i < FH; ++i) {
-          if (i < tnum) {
-            const double xa = xrow[8 * i];
-            dmma_e(acc[i][0][0], acc[i][0][1], xa, b0);
-            dmma_e(acc[i][1][0], acc[i][1][1], xa, b1);
-          }
+        for (int i = 0; i < MAXFT; ++i)
+          if (i < FT) dmma_e(acc[i][0], acc[i][1], x0[8 * i], b0);
+        if (ks + 1 < ksteps) {
+          const double *x1 = x0 + (size_t)4 * ldx;
+#pragma unroll
+          for (int i = 0; i < MAXFT; ++i)
+            if (i < FT) dmma_e(acc[i][0], acc[i][1], x1[8 * i], b1);
         }
       }
     }
-    // C layout: lane (c, q) holds S[feature 8 (tbeg + i) + c][draw 8 T + 2q + e]
+    // C layout: lane (c, q) holds S[feature 8 i + c][draw 8 T + 2q + e]
 #pragma unroll
-    for (int i = 0; i < FH; ++i) {
-      const int fa = 8 * (tbeg + i) + c;
-      if (i < tnum && fa < p) {
-        *reinterpret_cast<double2 *>(Sout + (size_t)fa * kDraws + 8 * T0 + 2 * q) = make_double2(acc[i][0][0], acc[i][0][1]);
-        *reinterpret_cast<double2 *>(Sout + (size_t)fa * kDraws + 8 * T1 + 2 * q) = make_double2(acc[i][1][0], acc[i][1][1]);
-      }
+    for (int i = 0; i < MAXFT; ++i) {
+      const int fa = 8 * i + c;
+      if (i < FT && fa < p)
+        *reinterpret_cast<double2 *>(Sout + (size_t)fa * kDraws + 8 * T + 2 * q) = make_double2(acc[i][0], acc[i][1]);
     }
-    if (half == 0) {
-      gs0 = quad_sum(gs0);
-      gs1 = quad_sum(gs1);
-      if (q == 0) {
-        Gout[8 * T0 + c] = gs0;
-        Gout[8 * T1 + c] = gs1;
-      }
-    }
+    gs = quad_sum(gs);
+    if (q == 0) Gout[8 * T + c] = gs;
   }
 }
 
