@@ -738,66 +738,11 @@ __global__ void __launch_bounds__(256) est_quantile_fused_kernel(int p, int nown
 //   M2 = sum_b M2_b + n_b d_b d_b^T,   G = sum_b G_b,   S = sum_b S_b + d_b G_b^T.
 // A rank ships this block instead of folding its batches twice; the sequential fold (est_absorb_kernel)
 // and this sum agree to rounding.
-// (slot_map: block b is partials[slot_map[b]], nullptr = consecutive blocks)
-__global__ void block_total_mean_kernel(int p, const double *partials, size_t pstride, int nb, const int *slot_map,
-                                        double *out) {
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  double n = 0.0;
-  for (int b = 0; b < nb; ++b) n += partials[(size_t)(slot_map ? slot_map[b] : b) * pstride];
-  if (f < kPartHdr) out[f] = (f == 0) ? n : 0.0;
-  if (f >= p) return;
-  double s = 0.0;
-#pragma unroll 8
-  for (int b = 0; b < nb; ++b) {
-    const double *blk = partials + (size_t)(slot_map ? slot_map[b] : b) * pstride;
-    s = fma(blk[0], blk[kPartHdr + f], s);
-  }
-  out[kPartHdr + f] = n > 0.0 ? s / n : 0.0;
-}
-
-__global__ void __launch_bounds__(256) block_total_kernel(int p, const double *partials, size_t pstride, int nb,
-                                                          const int *slot_map, int with_draws, double *out) {
-  const size_t nm2 = (size_t)p * p, ng = kDraws, ns = (size_t)p * kDraws;
-  const size_t total = nm2 + (with_draws ? ng + ns : 0);
-  const double *mean = out + kPartHdr;
-  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
-    double acc = 0.0;
-    if (e < nm2) {
-      const int f = (int)(e / p), j = (int)(e - (size_t)f * p);
-      const double mf = mean[f], mj = mean[j];
-#pragma unroll 8
-      for (int b = 0; b < nb; ++b) {
-        const double *blk = partials + (size_t)(slot_map ? slot_map[b] : b) * pstride;
-        const double nb_ = blk[0];
-        const double m2 = blk[kPartHdr + p + e], bf = blk[kPartHdr + f], bj = blk[kPartHdr + j];   // (loads first:
-        if (nb_ > 0.0) acc += m2 + nb_ * (bf - mf) * (bj - mj);                                   //  they pipeline)
-      }
-    } else if (e < nm2 + ng) {
-#pragma unroll 8
-      for (int b = 0; b < nb; ++b) {
-        const double *blk = partials + (size_t)(slot_map ? slot_map[b] : b) * pstride;
-        const double n_b = blk[0], g = blk[kPartHdr + p + e];
-        if (n_b > 0.0) acc += g;
-      }
-    } else {
-      const size_t r = e - nm2 - ng;
-      const int f = (int)(r / kDraws), sd = (int)(r - (size_t)f * kDraws);
-      const double mf = mean[f];
-#pragma unroll 8
-      for (int b = 0; b < nb; ++b) {
-        const double *blk = partials + (size_t)(slot_map ? slot_map[b] : b) * pstride;
-        const double n_b = blk[0], sv = blk[kPartHdr + p + e], bf = blk[kPartHdr + f], g = blk[kPartHdr + p + nm2 + sd];
-        if (n_b > 0.0) acc += sv + (bf - mf) * g;
-      }
-    }
-    out[kPartHdr + p + e] = acc;
-  }
-}
-
-// Run total of the moments for lsspa_estimator_absorb_errors: the same sums as block_total_mean_kernel /
-// block_total_kernel (M2 part), with the batches ALSO spread over threads -- thread (element, chunk c) adds the
-// batches c, c + 8, ... (their loads are independent and in flight together), the eight chunk sums are added
-// in a fixed order.  run_mean: one CTA of 128 features x 8 chunks; run_m2: CTA = 32 elements x 8 chunks.
+// The kernels of that sum (lsspa_estimator_block_total, and the moment half of lsspa_estimator_absorb_errors):
+// the batches are ALSO spread over threads -- thread (element, chunk c) adds the batches c, c + 8, ... (their
+// loads are independent and in flight together), the eight chunk sums are added in a fixed order.
+// run_mean: CTA = 128 features x 8 chunks; run_total: CTA = 32 elements x 8 chunks.  slot_map: block b is
+// partials[slot_map[b]] (nullptr = consecutive blocks).
 __global__ void __launch_bounds__(1024) run_mean_kernel(int p, const double *__restrict__ partials, size_t pstride, int nb,
                                                          const int *__restrict__ slot_map, double *__restrict__ out) {
   __shared__ double part[8][128];
@@ -806,7 +751,7 @@ __global__ void __launch_bounds__(1024) run_mean_kernel(int p, const double *__r
   const int f = blockIdx.x * 128 + fl;
   double cnt = 0.0, acc = 0.0;
   for (int b = ch; b < nb; b += 8) {
-    const double *blk = partials + (size_t)slot_map[b] * pstride;
+    const double *blk = partials + (size_t)(slot_map ? slot_map[b] : b) * pstride;
     const double n_b = blk[0], m = blk[kPartHdr + (f < p ? f : 0)];
     cnt += n_b;
     if (n_b > 0.0) acc = fma(n_b, m, acc);
@@ -833,26 +778,47 @@ __global__ void __launch_bounds__(1024) run_mean_kernel(int p, const double *__r
   }
 }
 
-__global__ void __launch_bounds__(256) run_m2_kernel(int p, const double *__restrict__ partials, size_t pstride, int nb,
-                                                      const int *__restrict__ slot_map, double *__restrict__ out) {
+__global__ void __launch_bounds__(256) run_total_kernel(int p, const double *__restrict__ partials, size_t pstride,
+                                                         int nb, const int *__restrict__ slot_map, int with_draws,
+                                                         double *__restrict__ out) {
   __shared__ double part[8][32];
   const int el = threadIdx.x & 31, ch = threadIdx.x >> 5;
-  const size_t nm2 = (size_t)p * p;
+  const size_t nm2 = (size_t)p * p, ng = kDraws, ns = (size_t)p * kDraws;
+  const size_t total = nm2 + (with_draws ? ng + ns : 0);
   const size_t e = (size_t)blockIdx.x * 32 + el;
-  const size_t ec = e < nm2 ? e : nm2 - 1;
-  const int f = (int)(ec / p), j = (int)(ec - (size_t)f * p);
+  const size_t ec = e < total ? e : total - 1;
   const double *mean = out + kPartHdr;
-  const double mf = mean[f], mj = mean[j];
   double acc = 0.0;
+  if (ec < nm2) {                 // M2 = sum_b M2_b + n_b d_b d_b^T
+    const int f = (int)(ec / p), j = (int)(ec - (size_t)f * p);
+    const double mf = mean[f], mj = mean[j];
 #pragma unroll 4
-  for (int b = ch; b < nb; b += 8) {
-    const double *blk = partials + (size_t)slot_map[b] * pstride;
-    const double n_b = blk[0], m2 = blk[kPartHdr + p + ec], bf = blk[kPartHdr + f], bj = blk[kPartHdr + j];
-    if (n_b > 0.0) acc += m2 + n_b * (bf - mf) * (bj - mj);
+    for (int b = ch; b < nb; b += 8) {
+      const double *blk = partials + (size_t)(slot_map ? slot_map[b] : b) * pstride;
+      const double n_b = blk[0], m2 = blk[kPartHdr + p + ec], bf = blk[kPartHdr + f], bj = blk[kPartHdr + j];
+      if (n_b > 0.0) acc += m2 + n_b * (bf - mf) * (bj - mj);
+    }
+  } else if (ec < nm2 + ng) {     // G = sum_b G_b
+#pragma unroll 4
+    for (int b = ch; b < nb; b += 8) {
+      const double *blk = partials + (size_t)(slot_map ? slot_map[b] : b) * pstride;
+      const double n_b = blk[0], g = blk[kPartHdr + p + ec];
+      if (n_b > 0.0) acc += g;
+    }
+  } else {                        // S = sum_b S_b + d_b G_b^T
+    const size_t r = ec - nm2 - ng;
+    const int f = (int)(r / kDraws), sd = (int)(r - (size_t)f * kDraws);
+    const double mf = mean[f];
+#pragma unroll 4
+    for (int b = ch; b < nb; b += 8) {
+      const double *blk = partials + (size_t)(slot_map ? slot_map[b] : b) * pstride;
+      const double n_b = blk[0], sv = blk[kPartHdr + p + ec], bf = blk[kPartHdr + f], g = blk[kPartHdr + p + nm2 + sd];
+      if (n_b > 0.0) acc += sv + (bf - mf) * g;
+    }
   }
   part[ch][el] = acc;
   __syncthreads();
-  if (ch == 0 && e < nm2) {
+  if (ch == 0 && e < total) {
     double t = 0.0;
 #pragma unroll
     for (int c = 0; c < 8; ++c) t += part[c][el];
@@ -1246,7 +1212,7 @@ extern "C" int lsspa_estimator_absorb_errors(void *state, int p, int cur, double
   {
     run_mean_kernel<<<(p + 127) / 128, 1024, 0, st>>>(p, partials, pstride, nb, slot_map, total);
     LSSPA_LAUNCH_CHECK();
-    run_m2_kernel<<<(unsigned)ceil_div((int64_t)p * p, 32), 256, 0, st>>>(p, partials, pstride, nb, slot_map, total);
+    run_total_kernel<<<(unsigned)ceil_div((int64_t)p * p, 32), 256, 0, st>>>(p, partials, pstride, nb, slot_map, 0, total);
     LSSPA_LAUNCH_CHECK();
     LSSPA_CUDA_TRY(cudaMemsetAsync(slot0, 0, 2 * sizeof(int), st));
     const size_t smem = ((size_t)2 * p + 2 + 7 + 16) * sizeof(double);
@@ -1273,10 +1239,10 @@ extern "C" int lsspa_estimator_block_total(int p, const double *partials, int nb
   const size_t pstride = partial_doubles(p);
   if (nb == 0 || !with_draws) LSSPA_CUDA_TRY(cudaMemsetAsync(out_block, 0, pstride * sizeof(double), st));
   if (nb == 0) return LSSPA_OK;
-  const int n1 = p > kPartHdr ? p : kPartHdr;
-  block_total_mean_kernel<<<(n1 + 127) / 128, 128, 0, st>>>(p, partials, pstride, nb, nullptr, out_block);
+  run_mean_kernel<<<(p + 127) / 128, 1024, 0, st>>>(p, partials, pstride, nb, nullptr, out_block);
   LSSPA_LAUNCH_CHECK();
-  block_total_kernel<<<592, 256, 0, st>>>(p, partials, pstride, nb, nullptr, with_draws, out_block);
+  const int64_t total = (int64_t)p * p + (with_draws ? kDraws + (int64_t)p * kDraws : 0);
+  run_total_kernel<<<(unsigned)ceil_div(total, 32), 256, 0, st>>>(p, partials, pstride, nb, nullptr, with_draws, out_block);
   LSSPA_LAUNCH_CHECK();
   return LSSPA_OK;
 }
