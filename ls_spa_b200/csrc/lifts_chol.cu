@@ -650,7 +650,9 @@ __device__ __forceinline__ double2 acc_tile4(const double *A, int kend, int L, i
 
 constexpr int kC4Threads = 128;
 
-template <int RT, int PT, int MINB>
+// MODE 0: the whole evaluation.  MODE 1: factor only (split route): phases 0 and 1, then R's upper tiles (with
+// c~) and the inverses of the diagonal blocks go to a.fact in the record layout lifts_elim4_kernel reads.
+template <int RT, int PT, int MINB, int MODE>
 __global__ void __launch_bounds__(kC4Threads, MINB) lifts_chol4_kernel(CholParams a, int sms) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int p = a.p;
@@ -721,13 +723,15 @@ __global__ void __launch_bounds__(kC4Threads, MINB) lifts_chol4_kernel(CholParam
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
       }
-      if (warp == 3) {
-        double s0 = 0.0;
-        for (int i = lane; i < p; i += 32) s0 = fma(a.cte[i], a.cte[i], s0);
-        s0 = warp_sum(s0);
-        if (lane == 0) cost[0] = s0;
+      if constexpr (MODE == 0) {
+        if (warp == 3) {
+          double s0 = 0.0;
+          for (int i = lane; i < p; i += 32) s0 = fma(a.cte[i], a.cte[i], s0);
+          s0 = warp_sum(s0);
+          if (lane == 0) cost[0] = s0;
+        }
+        for (int e = tid; e < 4 * NR; e += kC4Threads) wcost[e] = 0.0;
       }
-      for (int e = tid; e < 4 * NR; e += kC4Threads) wcost[e] = 0.0;
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncthreads();
       const long long t_b = LSSPA_CLOCK();
@@ -828,6 +832,37 @@ __global__ void __launch_bounds__(kC4Threads, MINB) lifts_chol4_kernel(CholParam
         }
       }
       const long long t_c = LSSPA_CLOCK();
+      if constexpr (MODE == 1) {
+        // ---- split route: the record of this evaluation (tile column L = 8 columns of rows(L) doubles,
+        // contiguous; then the RT inverses of the diagonal blocks, 64 doubles each in (c, 2q + e) order).
+        // The diagonal tiles of the record hold what the packed array holds there (the inverse; U in the
+        // last block) -- the elimination kernel overwrites them from the tail anyway.
+        constexpr int64_t FD = chol_fact_doubles(RT, PT);
+        double2 *dst = reinterpret_cast<double2 *>(a.fact + (sidx * halves + h) * FD);
+#pragma unroll
+        for (int L = 0; L < PT; ++L) {
+          constexpr int dummy = 0;
+          (void)dummy;
+          const int rows = pk_rows(L, RT);
+          int off = 0;
+#pragma unroll
+          for (int k = 0; k < L; ++k) off += 8 * pk_rows(k, RT);
+          const int n2 = 8 * rows / 2;
+          for (int e = tid; e < n2; e += kC4Threads) {
+            const int cc = e / (rows / 2), r2 = e - cc * (rows / 2);
+            dst[off / 2 + e] = *reinterpret_cast<const double2 *>(A + pk_off(L, RT) + cc * pk_ld(L, RT) + 2 * r2);
+          }
+        }
+        for (int e = tid; e < 32 * RT; e += kC4Threads) {
+          const int sblk = e >> 5, l = e & 31, cc = l >> 2, qq = l & 3;
+          const double *srcd = (sblk < RT - 1) ? A + pk_off_rt<RT>(sblk) + cc * pk_ld_rt<RT>(sblk) + 8 * sblk + 2 * qq
+                                               : Dlast + cc * 8 + 2 * qq;
+          dst[(FD - 64 * RT) / 2 + e] = *reinterpret_cast<const double2 *>(srcd);
+        }
+        (void)t_a; (void)t_b; (void)t_c; (void)t_work; (void)t_w1; (void)t_w2; (void)t_sf;
+        (void)wc; (void)cvec; (void)weight; (void)cost; (void)acc;
+        continue;
+      }
       // ---- phase 2: elimination of X = R_te[:, perm], row tiles warp, warp + 4, ...
       {
         double xr[RT][2];
@@ -868,7 +903,8 @@ __global__ void __launch_bounds__(kC4Threads, MINB) lifts_chol4_kernel(CholParam
       }
     }
     __syncthreads();
-    for (int f = tid; f < p; f += kC4Threads) a.out[sidx * p + f] = acc[f];
+    if constexpr (MODE == 0)
+      for (int f = tid; f < p; f += kC4Threads) a.out[sidx * p + f] = acc[f];
   }
 }
 
@@ -978,13 +1014,13 @@ size_t chol4_smem_bytes(int p, int pt) {
   return d * sizeof(double) + (size_t)(p + 1) * sizeof(int) + 16;
 }
 
-template <int RT, int PT, int MINB>
+template <int RT, int PT, int MINB, int MODE>
 int launch_chol4(const CholParams &a, int grid, size_t smem, int sms, cudaStream_t st) {
-  LSSPA_CUDA_TRY(cudaFuncSetAttribute(lifts_chol4_kernel<RT, PT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  LSSPA_CUDA_TRY(cudaFuncSetAttribute(lifts_chol4_kernel<RT, PT, MINB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
-  LSSPA_CUDA_TRY(cudaFuncSetAttribute(lifts_chol4_kernel<RT, PT, MINB>,
+  LSSPA_CUDA_TRY(cudaFuncSetAttribute(lifts_chol4_kernel<RT, PT, MINB, MODE>,
                                       cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  lifts_chol4_kernel<RT, PT, MINB><<<grid, kC4Threads, smem, st>>>(a, sms);
+  lifts_chol4_kernel<RT, PT, MINB, MODE><<<grid, kC4Threads, smem, st>>>(a, sms);
   LSSPA_LAUNCH_CHECK();
   return LSSPA_OK;
 }
@@ -1015,8 +1051,11 @@ int run_chol4(const CholParams &a, int64_t count, int mode, cudaStream_t st) {
   constexpr int MINB = RT <= 13 ? 4 : (RT <= 15 ? 3 : 2);   // resident CTAs the register budget is cut for
   if (mode == 2)
     return (a.pt == RT) ? launch_elim4<RT, RT, MINB>(a, (int)grid, smem, st) : launch_elim4<RT, RT + 1, MINB>(a, (int)grid, smem, st);
-  return (a.pt == RT) ? launch_chol4<RT, RT, MINB>(a, (int)grid, smem, sms, st)
-                      : launch_chol4<RT, RT + 1, MINB>(a, (int)grid, smem, sms, st);
+  if (mode == 1)
+    return (a.pt == RT) ? launch_chol4<RT, RT, MINB, 1>(a, (int)grid, smem, sms, st)
+                        : launch_chol4<RT, RT + 1, MINB, 1>(a, (int)grid, smem, sms, st);
+  return (a.pt == RT) ? launch_chol4<RT, RT, MINB, 0>(a, (int)grid, smem, sms, st)
+                      : launch_chol4<RT, RT + 1, MINB, 0>(a, (int)grid, smem, sms, st);
 }
 
 size_t chol_smem_bytes(int p) {
@@ -1276,7 +1315,7 @@ static int chol_run(int mode, int p, const double *gram, const double *R_te_cm, 
     const char *e = getenv("LSSPA_CHOL_PACKED");     // 0: the eight-warp kernel everywhere (A/B timing)
     return !(e && e[0] == '0');
   }();
-  if ((mode == 0 || mode == 2) && packed) {
+  if (packed) {
     switch (a.rt) {
       case 7: return run_chol4<7>(a, count, mode, st);
       case 8: return run_chol4<8>(a, count, mode, st);

@@ -421,7 +421,7 @@ class Prefactor:
     factors)."""
 
     MAX_BYTES = 12 << 30          # device memory spent on stored factors
-    FACTOR_RATE = 9e6             # evaluations/s assumed for sizing the overlap window
+    FACTOR_RATE = 18e6            # evaluations/s assumed for sizing the overlap window (packed factor kernel, p = 100)
     LINK_RATE = 50e9              # bytes/s assumed for the host link
 
     def __init__(self, backend, cfg: JobConfig, get_source, test_bytes: int):
