@@ -119,11 +119,75 @@ class CudaBackend:
         self.use_cholqr2 = os.environ.get("LSSPA_REDUCE", "cholqr2") != "householder"
 
     # -- reduction ----------------------------------------------------------
-    def _row_chunks(self, X, y, lo, hi, p, keep=False, staging=None, fence=None):
+    @staticmethod
+    def _host_views(X, y):
+        """Host inputs as torch views.  float32 host data crosses the link as float32 (half the bytes) and is
+        widened on the device -- exact, so the arithmetic is the same fp64 arithmetic on the same values; any
+        other dtype is widened here."""
+        Xh = X if isinstance(X, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(X))
+        yh = y if isinstance(y, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(y))
+        if Xh.dtype not in (torch.float64, torch.float32):
+            Xh = Xh.to(torch.float64)
+        if yh.dtype not in (torch.float64, torch.float32):
+            yh = yh.to(torch.float64)
+        return Xh, yh
+
+    @staticmethod
+    def _chunk_rows(rows, p):
+        return max(1, min(rows, (128 << 20) // (8 * (p + 1))))
+
+    def start_copies(self, X, y, lo, hi, p, staging, fence):
+        """Enqueue the copies of ALL chunks of the host rows [lo, hi) on the copy stream, now ->
+        [(X_chunk, y_chunk, ready event, narrow X chunk or None, narrow y chunk or None)] for
+        _row_chunks(prefetched=...).  The link then runs back to back with whatever the copy stream was given
+        before (the other side's rows), whatever the host does in between (reading flags, drawing
+        permutations).  The copy stream only ever runs DMA: float32 rows land in a float32 array of their own
+        and are widened into `staging` by the consumer's stream -- a widening kernel on the copy stream would
+        queue behind the persistent lift kernels that run meanwhile, and stall the link with it."""
+        Xh, yh = self._host_views(X, y)
+        narrow_x, narrow_y = Xh.dtype == torch.float32, yh.dtype == torch.float32
+        rows = hi - lo
+        chunk = self._chunk_rows(rows, p)
+        if self.copy_stream is None:
+            self.copy_stream = torch.cuda.Stream(device=self.device)
+        bigX, bigy = staging
+        # (allocated on the current stream like `staging`; the event orders the copies behind the allocation)
+        nX = torch.empty((rows, p), dtype=torch.float32, device=self.device) if narrow_x else None
+        ny = torch.empty(rows, dtype=torch.float32, device=self.device) if narrow_y else None
+        if narrow_x or narrow_y:
+            fence = torch.cuda.Event()
+            fence.record()
+        self.copy_stream.wait_event(fence)
+        out = []
+        with torch.cuda.stream(self.copy_stream):
+            for r0 in range(lo, hi, chunk):
+                r1 = min(r0 + chunk, hi)
+                bx, by = bigX[r0 - lo: r1 - lo], bigy[r0 - lo: r1 - lo]
+                nxc = nX[r0 - lo: r1 - lo] if narrow_x else None
+                nyc = ny[r0 - lo: r1 - lo] if narrow_y else None
+                (nxc if narrow_x else bx).copy_(Xh[r0:r1], non_blocking=True)
+                (nyc if narrow_y else by).copy_(yh[r0:r1], non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(self.copy_stream)
+                out.append((bx, by, ready, nxc, nyc))
+        return out
+
+    def _row_chunks(self, X, y, lo, hi, p, keep=False, staging=None, fence=None, prefetched=None):
         """Yield device (X_chunk, y_chunk) covering rows [lo, hi); host inputs are streamed on a copy
         stream so that the copy of chunk i+1 overlaps the work on chunk i.  keep=False recycles two
         staging buffers (single-pass consumers); keep=True lands the chunks in one resident device
-        array (the CholeskyQR2 reduction reads the rows twice)."""
+        array (the CholeskyQR2 reduction reads the rows twice).  prefetched: the copies were already
+        enqueued by start_copies; only their events are awaited here."""
+        if prefetched is not None:
+            main = torch.cuda.current_stream()
+            for bx, by, ready, nxc, nyc in prefetched:
+                main.wait_event(ready)
+                if nxc is not None:
+                    bx.copy_(nxc)
+                if nyc is not None:
+                    by.copy_(nyc)
+                yield bx, by, None
+            return
         if isinstance(X, torch.Tensor) and X.is_cuda:
             # device-resident inputs: the kernels read raw float64 storage on THIS device, so any other
             # dtype (torch's default is float32) or device is converted here (a no-op for float64 rows)
@@ -133,17 +197,10 @@ class CudaBackend:
                 Xv = Xv.contiguous()
             yield Xv, yv, None
             return
-        Xh = X if isinstance(X, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(X))
-        yh = y if isinstance(y, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(y))
-        # float32 host data crosses the link as float32 (half the bytes) and is widened on the device -- exact,
-        # so the arithmetic below is the same fp64 arithmetic on the same values; any other dtype is widened here
-        if Xh.dtype not in (torch.float64, torch.float32):
-            Xh = Xh.to(torch.float64)
-        if yh.dtype not in (torch.float64, torch.float32):
-            yh = yh.to(torch.float64)
+        Xh, yh = self._host_views(X, y)
         narrow_x, narrow_y = Xh.dtype == torch.float32, yh.dtype == torch.float32
         rows = hi - lo
-        chunk = max(1, min(rows, (128 << 20) // (8 * (p + 1))))
+        chunk = self._chunk_rows(rows, p)
         if self.copy_stream is None:
             self.copy_stream = torch.cuda.Stream(device=self.device)
         main = torch.cuda.current_stream()
@@ -236,7 +293,8 @@ class CudaBackend:
             g = torch.cat([g, self.ridge(p, reg).unsqueeze(0)], 0)
         return self.merge_factors(g, p) if g.shape[0] > 1 else g[0]
 
-    def reduce_start(self, coll, X, y, lo, hi, p, divisor, reg, staging=None, fence=None, is_train=False):
+    def reduce_start(self, coll, X, y, lo, hi, p, divisor, reg, staging=None, fence=None, is_train=False,
+                     prefetched=None):
         """Launch half of one side of reduce_data: Gram pass over the rows [lo, hi) of this rank, all-reduce,
         factorisation.  Nothing is read back: the returned state goes to reduce_finish, and a caller may
         start the other side first so that one host synchronisation serves both.
@@ -253,7 +311,8 @@ class CudaBackend:
         fac = ops.CholQR2(p, divisor, self.device) if small else ops.GramBig(p, divisor, self.device)
         chunks = []
         if hi - lo > 0:
-            for Xc, yc, _ in self._row_chunks(X, y, lo, hi, p, keep=True, staging=staging, fence=fence):
+            for Xc, yc, _ in self._row_chunks(X, y, lo, hi, p, keep=True, staging=staging, fence=fence,
+                                              prefetched=prefetched):
                 fac.add_chunk(Xc, yc)          # the Gram pass on this chunk overlaps the next copy
                 chunks.append((Xc, yc))
         if small:
@@ -300,10 +359,11 @@ class CudaBackend:
                 return slot, None, None
         return self._tsqr_side(coll, st["chunks"], st["X"], st["y"], st["lo"], st["hi"], p, st["divisor"], reg), None, None
 
-    def reduce_side(self, coll, X, y, lo, hi, p, divisor, reg, staging=None, fence=None, is_train=False):
+    def reduce_side(self, coll, X, y, lo, hi, p, divisor, reg, staging=None, fence=None, is_train=False,
+                    prefetched=None):
         """One side of reduce_data over all ranks, start to finish -> (merged slot, TrainSide or None, ysq or None)."""
         return self.reduce_finish(self.reduce_start(coll, X, y, lo, hi, p, divisor, reg, staging=staging, fence=fence,
-                                                    is_train=is_train))
+                                                    is_train=is_train, prefetched=prefetched))
 
     # factor condition (equilibrated) up to which one Cholesky pass is kept
     SINGLE_PASS_COND = 1e3
@@ -395,10 +455,17 @@ def reduce_problem(backend, coll: Collective, X_train, X_test, y_train, y_test, 
         # can already be drawn and factored while the test rows cross PCIe.  The staging arrays of
         # the test rows are allocated first: the copies then only wait for what was enqueued before
         # the factorisations, and no block freed during them can end up under a copy.
-        train_slot, train, _ = backend.reduce_side(coll, X_train, y_train, lo_tr, hi_tr, p, root_n, reg, is_train=True)
+        # The copies of the test rows are enqueued on the copy stream right behind the train rows', before the
+        # host waits for the train flags: the link never idles between the two sides.
         staging, fence = backend.alloc_staging(hi_te - lo_te, p)
+        st_tr = backend.reduce_start(coll, X_train, y_train, lo_tr, hi_tr, p, root_n, reg, is_train=True)
+        pre = None
+        if hi_te - lo_te > 0 and not (isinstance(X_test, torch.Tensor) and X_test.is_cuda):
+            pre = backend.start_copies(X_test, y_test, lo_te, hi_te, p, staging, fence)
+        train_slot, train, _ = backend.reduce_finish(st_tr)
         train = prefactor.run(train_slot, p, train)
-        test_slot, _, ysq = backend.reduce_side(coll, X_test, y_test, lo_te, hi_te, p, 1.0, 0.0, staging=staging, fence=fence)
+        test_slot, _, ysq = backend.reduce_side(coll, X_test, y_test, lo_te, hi_te, p, 1.0, 0.0, staging=staging, fence=fence,
+                                                prefetched=pre)
     else:
         # both sides are enqueued before anything is read back: one host synchronisation for the whole reduction
         st_tr = backend.reduce_start(coll, X_train, y_train, lo_tr, hi_tr, p, root_n, reg, is_train=True)
