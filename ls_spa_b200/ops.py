@@ -134,15 +134,23 @@ class CholQR2:
         _count(1)
         return buf
 
-    def _sum(self, parts):
-        if not parts:
-            return torch.zeros(self.n2, dtype=torch.float64, device=self.device)
-        allp = parts[0] if len(parts) == 1 else torch.cat(parts, 0)
-        G = torch.empty(self.n2, dtype=torch.float64, device=allp.device)
-        check(_lib().lsspa_gram_finish(allp.data_ptr(), allp.shape[0], self.p, self.scale, G.data_ptr(),
+    def _finish(self, parts, scale):
+        G = torch.empty(self.n2, dtype=torch.float64, device=parts.device)
+        check(_lib().lsspa_gram_finish(parts.data_ptr(), parts.shape[0], self.p, scale, G.data_ptr(),
                                        _stream()), "lsspa_gram_finish")
         _count(1)
         return G
+
+    def _sum(self, parts):
+        """Partial Gram matrices of all chunks -> one scaled matrix.  With several chunks (host-resident rows)
+        every chunk but the last was already reduced to ONE matrix while the next chunk was on the link
+        (add_chunk), so that what follows the last copy is one small sum, not a pass over all partials."""
+        if not parts:
+            return torch.zeros(self.n2, dtype=torch.float64, device=self.device)
+        if len(parts) == 1:
+            return self._finish(parts[0], self.scale)
+        sums = [q if q.dim() == 1 else self._finish(q, 1.0) for q in parts]
+        return self._finish(torch.stack(sums, 0), self.scale)
 
     def add_chunk(self, Xc: torch.Tensor, yc: torch.Tensor) -> None:
         if Xc.shape[0] == 0:
@@ -155,6 +163,8 @@ class CholQR2:
             Xc = Xc.contiguous()
         self.device = Xc.device
         self.chunks.append((Xc, yc))
+        if self.parts1 and self.parts1[-1].dim() == 2:
+            self.parts1[-1] = self._finish(self.parts1[-1], 1.0)     # the previous chunk, now that another follows
         self.parts1.append(self._rows(Xc, yc, None))
 
     def gram(self) -> torch.Tensor:
