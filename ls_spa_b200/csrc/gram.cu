@@ -659,7 +659,6 @@ __global__ void __launch_bounds__(1024) chol_factor_kernel(const double *G, int 
     redp[32 + w] = fip;
   }
   __syncthreads();
-  const long long c3 = clock64();
   // second bound: sqrt(Gershgorin bound on the largest eigenvalue of the equilibrated Gram matrix)
   // * sqrt(|R'^-1|_1 |R'^-1|_inf) with R'^-1 = D R^-1; thread t takes row / column t.  [1]: leading block.
 #pragma unroll 1
@@ -689,7 +688,6 @@ __global__ void __launch_bounds__(1024) chol_factor_kernel(const double *G, int 
     }
   }
   __syncthreads();
-  const long long c4 = clock64();
   // the final combination is done by warp 0 with its lanes over the rows / warps (a single thread walking
   // these ~600 shared-memory values and ~100 FP64 divisions was half of this kernel's time)
   double bound0 = 0.0, bound1 = 0.0, dlo = 1e300, dhi = 0.0;
@@ -738,11 +736,12 @@ __global__ void __launch_bounds__(1024) chol_factor_kernel(const double *G, int 
       ginfo[1] = (dhi > 0.0) ? dlo / dhi : 0.0;
       ginfo[2] = bound1;
       ginfo[3] = bound1;
-      // phase cycles of this (single-CTA) kernel, for tools/prof_gram.py: factorisation, inverse, bounds
+      // phase cycles of this (single-CTA) kernel as thread 0 sees them, for tools/prof_gram.py: factorisation,
+      // inverse, bounds.  (BAR.SYNC defers blocking: a clock read after a barrier is taken when THIS warp
+      // arrives, so the wait for the slowest warp of a phase is booked to the next phase.)
       ginfo[4] = (double)(c1 - c0);
       ginfo[5] = (double)(c2 - c1);
       ginfo[6] = (double)(clock64() - c2);
-      ginfo[7] = (double)(c3 - c2) + 1e-9 * (double)(c4 - c3);
     }
   }
 #pragma unroll 1

@@ -21,4 +21,4 @@ torch.cuda.synchronize()
 print(f"reduce_problem (both sides, p={p}, N=M={n}): {e0.elapsed_time(e1) / 5:.3f} ms; cond {prob.cond_estimate:.1f} chol {prob.use_chol}")
 base = (p + 1) * (p + 1)
 if prob.gram is not None:
-    print("chol_factor phase cycles (factor, inverse, bounds):", prob.gram[base + 4: base + 8].tolist())
+    print("chol_factor phase cycles (factor, inverse, bounds):", prob.gram[base + 4: base + 7].tolist())
