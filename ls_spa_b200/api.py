@@ -230,15 +230,30 @@ def ls_spa(X_train, X_test, y_train, y_test, reg: float = 0.0, method: str | Non
             and ops.split_route_supported(p) and os.environ.get("LSSPA_SPLIT_ROUTE", "1") != "0"):
         esize = 4 if getattr(X_test, "dtype", None) in (np.float32, torch.float32) else 8
         pre = engine.Prefactor(backend, cfg, get_source, esize * int(X_test.shape[0]) * (p + 1))
+    # host-side preparation that needs nothing from the reduction runs while the device is still busy with it
+    # (reduce_problem calls this right before it waits for the reduction's flags)
+    ready_early = {}
+
+    def prepare():
+        ready_early["est"] = backend.make_estimator(cfg)
+        if pre is None:
+            ready_early["source"] = get_source()
+
     prob = engine.reduce_problem(backend, coll, X_train, X_test, y_train, y_test, float(reg), p,
-                                 row_sharded=row_sharded, prefactor=pre)
-    source = pre.source if (pre is not None and pre.source is not None) else get_source()
-    res, history, done = engine.run_samples(backend, coll, prob, source, cfg, pre=pre)
+                                 row_sharded=row_sharded, prefactor=pre, prepare=prepare)
+    if pre is not None and pre.source is not None:
+        source = pre.source
+    else:
+        source = ready_early["source"] if "source" in ready_early else get_source()
+    # the epilogue (theta, R^2) depends on the reduced problem only: its kernel goes in ahead of the sample
+    # loop and is read after it, instead of one more launch-and-wait at the end of the job
+    early = backend.theta_r2_start(prob) if hasattr(backend, "theta_r2_start") else None
+    res, history, done = engine.run_samples(backend, coll, prob, source, cfg, pre=pre, est=ready_early.get("est"))
     if getattr(source, "host_generator", None) is not None:
         source.sync_generator()      # the caller's generator moves past the permutations drawn
     if done == 0 and p >= 9:
         raise ValueError("no permutations were supplied")
-    theta, r2 = backend.theta_r2(prob)
+    theta, r2 = backend.theta_r2_finish(early) if early is not None else backend.theta_r2(prob)
 
     never = res["n_history"] == 0
     return ShapleyResults(

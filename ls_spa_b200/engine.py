@@ -325,6 +325,11 @@ class CudaBackend:
         lift_cond = (fac.lift_gram[q * q:q * q + 1] if (small and is_train and fac.lift_gram is not None)
                      else torch.full((1,), float("nan"), dtype=torch.float64, device=self.device))
         st.update(fac=fac, chunks=chunks, slot=slot, flags=torch.cat([info, lift_cond, slot[q * q:q * q + 1]]))
+        if small and is_train and fac.lift_gram is not None:
+            # the train half of the problem in the lift kernels' layout, assembled NOW (device work only, behind
+            # the factorisation) rather than after the host has read the flags: the common outcome keeps it
+            R, c, _ = ops.split_factor(slot, p)
+            st["spec_train"] = ops.TrainSide(R, c, gram=fac.lift_gram, cond=float("inf"))
         return st
 
     def reduce_finish(self, st, flags=None):
@@ -340,8 +345,12 @@ class CudaBackend:
         bad, cond, lift_cond, ysq = (float(v) for v in flags)
         slot, train = st["slot"], None
         if bad == 0 and small and is_train and fac.lift_gram is not None and cond <= self.SINGLE_PASS_COND:
-            R, c, _ = ops.split_factor(slot, p)
-            train = ops.TrainSide(R, c, gram=fac.lift_gram, cond=lift_cond)
+            train = st.get("spec_train")
+            if train is not None:
+                train.set_cond(lift_cond)
+            else:
+                R, c, _ = ops.split_factor(slot, p)
+                train = ops.TrainSide(R, c, gram=fac.lift_gram, cond=lift_cond)
         if bad == 0 and not small and is_train:
             # wide problems: the blocked factorisation reports no condition bound; the estimate the lift
             # route needs anyway (equilibrated train factor) decides
@@ -397,8 +406,17 @@ class CudaBackend:
         return out
 
     def theta_r2(self, prob):
+        return self.theta_r2_finish(self.theta_r2_start(prob))
+
+    def theta_r2_start(self, prob):
+        """Enqueue the epilogue kernel (it needs the reduced problem only, so a job launches it ahead of
+        the sample loop and reads it with the final results)."""
         theta, r2 = ops.theta_r2(prob)
-        return theta.cpu().numpy(), float(r2.item())
+        return torch.cat([theta, r2.reshape(1)])
+
+    def theta_r2_finish(self, packed):
+        host = packed.cpu().numpy()
+        return host[:-1].copy(), float(host[-1])
 
     def zeros(self, *shape):
         return torch.zeros(shape, dtype=torch.float64, device=self.device)
@@ -421,7 +439,7 @@ class CudaBackend:
 # the job
 # ---------------------------------------------------------------------------
 def reduce_problem(backend, coll: Collective, X_train, X_test, y_train, y_test, reg, p,
-                   n_train_global=None, row_sharded=False, prefactor=None):
+                   n_train_global=None, row_sharded=False, prefactor=None, prepare=None):
     """Both tall-skinny reductions, row-sharded over the ranks of `coll`.
 
     With row_sharded=False every rank was handed the full arrays and reduces its own
@@ -462,6 +480,8 @@ def reduce_problem(backend, coll: Collective, X_train, X_test, y_train, y_test, 
         pre = None
         if hi_te - lo_te > 0 and not (isinstance(X_test, torch.Tensor) and X_test.is_cuda):
             pre = backend.start_copies(X_test, y_test, lo_te, hi_te, p, staging, fence)
+        if prepare is not None:
+            prepare()
         train_slot, train, _ = backend.reduce_finish(st_tr)
         train = prefactor.run(train_slot, p, train)
         test_slot, _, ysq = backend.reduce_side(coll, X_test, y_test, lo_te, hi_te, p, 1.0, 0.0, staging=staging, fence=fence,
@@ -470,13 +490,28 @@ def reduce_problem(backend, coll: Collective, X_train, X_test, y_train, y_test, 
         # both sides are enqueued before anything is read back: one host synchronisation for the whole reduction
         st_tr = backend.reduce_start(coll, X_train, y_train, lo_tr, hi_tr, p, root_n, reg, is_train=True)
         st_te = backend.reduce_start(coll, X_test, y_test, lo_te, hi_te, p, 1.0, 0.0)
+        spec = None
         if st_tr["flags"] is not None and st_te["flags"] is not None:
+            if st_tr.get("spec_train") is not None:
+                # the whole problem in the lift kernels' layout, enqueued behind the two factorisations while
+                # the host has not yet seen their flags (half a dozen small kernels that used to run one
+                # host round trip apart, after the read)
+                spec = backend.make_problem(st_tr["slot"], st_te["slot"], p, train=st_tr["spec_train"], ysq=float("nan"))
+            if prepare is not None:
+                prepare()              # host work of the caller that needs no result of the reduction
+                prepare = None
             both = torch.cat([st_tr["flags"], st_te["flags"]]).cpu()
             f_tr, f_te = both[:4], both[4:]
         else:
             f_tr = f_te = None
         train_slot, train, _ = backend.reduce_finish(st_tr, f_tr)
         test_slot, _, ysq = backend.reduce_finish(st_te, f_te)
+        if (spec is not None and ysq is not None and train is st_tr.get("spec_train")
+                and train_slot is st_tr["slot"] and test_slot is st_te["slot"]):
+            spec.finalize(ysq)
+            return spec
+    if prepare is not None and not (fused and prefactor is not None):
+        prepare()
     return backend.make_problem(train_slot, test_slot, p, train=train, ysq=ysq)
 
 
@@ -570,7 +605,7 @@ def superbatch_geometry(cfg: JobConfig, world: int, source_total, max_batches: i
     return limit, bs_eff, size
 
 
-def run_samples(backend, coll: Collective, prob, source: PermutationSource, cfg: JobConfig, pre=None):
+def run_samples(backend, coll: Collective, prob, source: PermutationSource, cfg: JobConfig, pre=None, est=None):
     """The estimator loop (reference ls_spa/ls_spa.py:196-236), one super-batch at a time.
 
     Returns (result dict, history or None, samples drawn).  result: count, mean, overall_error,
@@ -578,7 +613,7 @@ def run_samples(backend, coll: Collective, prob, source: PermutationSource, cfg:
     p, W, rank = cfg.p, coll.world, coll.rank
     limit, bs_eff, sb_size = superbatch_geometry(cfg, W, source.total)
     sb_index = {"next": 0}
-    est = backend.make_estimator(cfg)
+    est = est if est is not None else backend.make_estimator(cfg)
     quirk = (cfg.max_samples - 1) if (cfg.penultimate_check and cfg.max_samples and cfg.estimate_errors) else None
     can_stop = cfg.estimate_errors and cfg.tolerance > 0.0
 
@@ -740,13 +775,23 @@ def run_samples(backend, coll: Collective, prob, source: PermutationSource, cfg:
         source.check()
     if hasattr(prob, "check"):
         prob.check()
-    res = est.read()
-    if err_parts:
-        err_hist = torch.cat(err_parts).cpu().numpy().tolist()
+    if isinstance(feat_last, torch.Tensor) and feat_last.is_cuda and hasattr(est, "state"):
+        # mean, per-feature errors and (when nothing could stop the job) the error history in ONE transfer
+        tail = [est.state[est.cur * p:(est.cur + 1) * p], feat_last.reshape(-1)] + (err_parts if err_parts else [])
+        host = torch.cat(tail).cpu().numpy()
+        res = dict(count=est.count, mean=host[:p].copy())
+        feat_host = host[p:2 * p].copy()
+        if err_parts:
+            err_hist = host[2 * p:].tolist()
+    else:
+        res = est.read()
+        if err_parts:
+            err_hist = torch.cat(err_parts).cpu().numpy().tolist()
+        feat_host = (feat_last.cpu().numpy().copy() if feat_last is not None else np.zeros(p))
     res["error_history"] = np.asarray(err_hist, dtype=np.float64)
     res["n_history"] = len(err_hist)
     res["overall_error"] = float(err_hist[-1]) if err_hist else 0.0
-    res["attribution_errors"] = (feat_last.cpu().numpy().copy() if feat_last is not None else np.zeros(p))
+    res["attribution_errors"] = feat_host
     history = None
     if hist_chunks is not None:
         history = (torch.cat(hist_chunks, 0)[: res["count"]].cpu().numpy() if hist_chunks else np.zeros((0, p)))

@@ -388,9 +388,9 @@ class TrainSide:
         self.big = bool(_lib().lsspa_lifts_big_supported(p))     # wide problems: batched tile kernels (lifts_big.cu)
         if gram is not None and cond is not None and forced not in ("v1", "householder"):
             base = (p + 1) * (p + 1)
-            self.gram, self.cond_estimate = gram, float(cond)
-            self.use_chol = forced == "chol" or self.cond_estimate <= CHOL_COND_LIMIT
+            self.gram = gram
             self.scale = gram[base + 8:base + 8 + p]
+            self.set_cond(cond)
         elif forced not in ("v1", "householder") and (_lib().lsspa_lifts_chol_supported(p) or self.big):
             n = _lib().lsspa_lifts_gram_doubles(p)
             self.gram = torch.empty(n, dtype=torch.float64, device=dev)
@@ -402,6 +402,16 @@ class TrainSide:
             self.cond_estimate = float(info[0])    # of the column-equilibrated train factor
             self.use_chol = forced == "chol" or self.cond_estimate <= CHOL_COND_LIMIT
             self.scale = self.gram[base + 8:base + 8 + p]
+
+
+    def set_cond(self, cond) -> None:
+        """Condition bound of the equilibrated train factor -> route.  A caller that builds this object
+        before it has read the bound from the device (cond = inf) sets it here afterwards."""
+        forced = os.environ.get("LSSPA_LIFTS_IMPL", "")
+        if self.gram is None or forced in ("v1", "householder"):
+            return
+        self.cond_estimate = float(cond)
+        self.use_chol = forced == "chol" or self.cond_estimate <= CHOL_COND_LIMIT
 
 
 class ReducedProblem:
@@ -426,6 +436,12 @@ class ReducedProblem:
         if train.scale is not None:
             # the Cholesky route works on unit-norm train columns: scale the test columns alike
             self.R_te_scaled_cm = self.R_te_cm / train.scale.unsqueeze(1)
+
+    def finalize(self, y_norm_sq: float) -> None:
+        """For a problem assembled before the reduction's flags were read (engine.reduce_problem): the
+        host-side scalars, once they are known."""
+        self.y_norm_sq = float(y_norm_sq)
+        self.cond_estimate, self.use_chol = self.train.cond_estimate, self.train.use_chol
 
     # device memory the tile workspace of the wide route may take (it is processed in passes)
     BIG_WS_BUDGET = 24 << 30
