@@ -308,14 +308,23 @@ class CudaBackend:
                   fac=None, flags=None)
         if not (self.use_cholqr2 and (small or ops.gram_big_supported(p))):
             return st
-        fac = ops.CholQR2(p, divisor, self.device) if small else ops.GramBig(p, divisor, self.device)
+        count_rows = divisor is None                 # (small only, see reduce_problem)
+        fac = (ops.CholQR2(p, 1.0 if count_rows else divisor, self.device) if small
+               else ops.GramBig(p, divisor, self.device))
         chunks = []
         if hi - lo > 0:
             for Xc, yc, _ in self._row_chunks(X, y, lo, hi, p, keep=True, staging=staging, fence=fence,
                                               prefetched=prefetched):
                 fac.add_chunk(Xc, yc)          # the Gram pass on this chunk overlaps the next copy
                 chunks.append((Xc, yc))
-        if small:
+        n_dev = None
+        if small and count_rows:
+            # [unscaled Gram | local row count] in one all-reduce; G / N on the device
+            mine = torch.full((1,), float(hi - lo), dtype=torch.float64, device=self.device)
+            red = coll.all_reduce_sum(torch.cat([fac.gram(), mine]))
+            n_dev = red[-1:]
+            slot, info = fac.factor(red[:-1] / n_dev, reg, want_gram=is_train)
+        elif small:
             slot, info = fac.factor(coll.all_reduce_sum(fac.gram()), reg, want_gram=is_train)
         else:
             slot, info = fac.factor(coll.all_reduce_sum(fac.gram()), reg)
@@ -324,7 +333,8 @@ class CudaBackend:
         # cond bound of its leading block (train side, p + 1 <= 112), sum of squares of the y column]
         lift_cond = (fac.lift_gram[q * q:q * q + 1] if (small and is_train and fac.lift_gram is not None)
                      else torch.full((1,), float("nan"), dtype=torch.float64, device=self.device))
-        st.update(fac=fac, chunks=chunks, slot=slot, flags=torch.cat([info, lift_cond, slot[q * q:q * q + 1]]))
+        st.update(fac=fac, chunks=chunks, slot=slot,
+                  flags=torch.cat([info, lift_cond, slot[q * q:q * q + 1]] + ([n_dev] if n_dev is not None else [])))
         if small and is_train and fac.lift_gram is not None:
             # the train half of the problem in the lift kernels' layout, assembled NOW (device work only, behind
             # the factorisation) rather than after the host has read the flags: the common outcome keeps it
@@ -342,7 +352,11 @@ class CudaBackend:
             return self._tsqr_side(coll, None, st["X"], st["y"], st["lo"], st["hi"], p, st["divisor"], reg), None, None
         if flags is None:
             flags = st["flags"].cpu()
-        bad, cond, lift_cond, ysq = (float(v) for v in flags)
+        vals = [float(v) for v in flags]
+        bad, cond, lift_cond, ysq = vals[:4]
+        if len(vals) > 4:                        # the global row count came with the flags (reduce_start)
+            st["divisor"] = math.sqrt(vals[4])
+            fac.scale = 1.0 / vals[4]
         slot, train = st["slot"], None
         if bad == 0 and small and is_train and fac.lift_gram is not None and cond <= self.SINGLE_PASS_COND:
             train = st.get("spec_train")
@@ -451,13 +465,18 @@ def reduce_problem(backend, coll: Collective, X_train, X_test, y_train, y_test, 
         return min(coll.rank * per, n), min((coll.rank + 1) * per, n)
 
     n_tr_local = int(X_train.shape[0])
-    if n_train_global is None:
+    fused = hasattr(backend, "reduce_start")     # the CUDA backend; the CPU stand-in of the unit tests merges triangles
+    # Row-sharded inputs: the global row count N (the train rows are scaled by 1/sqrt(N), reference :309) is a
+    # sum over the ranks.  On the Gram route it rides on the all-reduce of the Gram matrix and the scaling is
+    # applied on the device, so a job does not begin with a collective and a host round trip of its own.
+    defer_n = (n_train_global is None and row_sharded and coll.world > 1 and fused and prefactor is None
+               and getattr(backend, "use_cholqr2", False) and ops.gram_supported(p))
+    if n_train_global is None and not defer_n:
         n_train_global = (coll.all_reduce_sum_int(n_tr_local, backend.device)
                           if row_sharded else n_tr_local)
-    fused = hasattr(backend, "reduce_start")     # the CUDA backend; the CPU stand-in of the unit tests merges triangles
     lo_tr, hi_tr = local_range(n_tr_local)
     lo_te, hi_te = local_range(int(X_test.shape[0]))
-    root_n = math.sqrt(n_train_global)
+    root_n = None if defer_n else math.sqrt(n_train_global)     # None: 1/sqrt(N) with N from the Gram all-reduce
     if not fused:
         def one_side(X, y, lo, hi, divisor, ridge):
             g = coll.all_gather(backend.reduce_rows(X, y, lo, hi, p, divisor))
@@ -501,7 +520,8 @@ def reduce_problem(backend, coll: Collective, X_train, X_test, y_train, y_test, 
                 prepare()              # host work of the caller that needs no result of the reduction
                 prepare = None
             both = torch.cat([st_tr["flags"], st_te["flags"]]).cpu()
-            f_tr, f_te = both[:4], both[4:]
+            k_tr = int(st_tr["flags"].numel())
+            f_tr, f_te = both[:k_tr], both[k_tr:]
         else:
             f_tr = f_te = None
         train_slot, train, _ = backend.reduce_finish(st_tr, f_tr)
