@@ -247,7 +247,7 @@ def ls_spa(X_train, X_test, y_train, y_test, reg: float = 0.0, method: str | Non
         source = ready_early["source"] if "source" in ready_early else get_source()
     # the epilogue (theta, R^2) depends on the reduced problem only: its kernel goes in ahead of the sample
     # loop and is read after it, instead of one more launch-and-wait at the end of the job
-    early = backend.theta_r2_start(prob) if hasattr(backend, "theta_r2_start") else None
+    early = backend.theta_r2_start(prob) if (hasattr(backend, "theta_r2_start") and engine.HOST_OVERLAP) else None
     res, history, done = engine.run_samples(backend, coll, prob, source, cfg, pre=pre, est=ready_early.get("est"))
     if getattr(source, "host_generator", None) is not None:
         source.sync_generator()      # the caller's generator moves past the permutations drawn

@@ -107,6 +107,10 @@ class Collective:
         return int(t.item())
 
 
+# LSSPA_HOST_OVERLAP=0: no speculative problem assembly / early host preparation (A/B timing)
+HOST_OVERLAP = os.environ.get("LSSPA_HOST_OVERLAP", "1") != "0"
+
+
 # ---------------------------------------------------------------------------
 # CUDA backend
 # ---------------------------------------------------------------------------
@@ -335,7 +339,7 @@ class CudaBackend:
                      else torch.full((1,), float("nan"), dtype=torch.float64, device=self.device))
         st.update(fac=fac, chunks=chunks, slot=slot,
                   flags=torch.cat([info, lift_cond, slot[q * q:q * q + 1]] + ([n_dev] if n_dev is not None else [])))
-        if small and is_train and fac.lift_gram is not None:
+        if small and is_train and fac.lift_gram is not None and HOST_OVERLAP:
             # the train half of the problem in the lift kernels' layout, assembled NOW (device work only, behind
             # the factorisation) rather than after the host has read the flags: the common outcome keeps it
             R, c, _ = ops.split_factor(slot, p)
@@ -516,7 +520,7 @@ def reduce_problem(backend, coll: Collective, X_train, X_test, y_train, y_test, 
                 # the host has not yet seen their flags (half a dozen small kernels that used to run one
                 # host round trip apart, after the read)
                 spec = backend.make_problem(st_tr["slot"], st_te["slot"], p, train=st_tr["spec_train"], ysq=float("nan"))
-            if prepare is not None:
+            if prepare is not None and HOST_OVERLAP:
                 prepare()              # host work of the caller that needs no result of the reduction
                 prepare = None
             both = torch.cat([st_tr["flags"], st_te["flags"]]).cpu()
